@@ -1,0 +1,167 @@
+/*
+ * p3d.h -- C-ABI of libp3d.so, the sm_100a replacement for pix2pix3D's render + StyleGAN2-op hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream; the caller owns all
+ * memory (allocates outputs, keeps inputs alive until the stream reaches the call). Nothing is
+ * retained past return and there is no global mutable state (the reference's __constant__ filter
+ * buffer, torch_utils/ops/filtered_lrelu.cu:81-82, is deliberately not reproduced).
+ *
+ * Return value: 0 = ok, <0 = p3d status (P3D_UNSUPPORTED: "no kernel for this configuration",
+ * the analogue of rc=-1 in torch_utils/ops/filtered_lrelu.cpp:56-60), >0 = cudaError_t of the launch.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef P3D_H_
+#define P3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* p3d_stream_t; /* cudaStream_t */
+
+enum {
+    P3D_OK          = 0,
+    P3D_UNSUPPORTED = -1,
+    P3D_BAD_ARG     = -2,
+};
+
+enum { /* element types of activation tensors */
+    P3D_F32 = 0,
+    P3D_F16 = 1,
+    P3D_F64 = 2,
+};
+
+/* Library ABI version (bumped on any signature change) and build info. */
+int         p3d_abi_version(void);
+const char* p3d_build_info(void);
+const char* p3d_status_string(int status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Renderer (training/volumetric_rendering/*)
+ * ------------------------------------------------------------------------------------------- */
+
+/* RaySampler.forward -- training/volumetric_rendering/ray_sampler.py:24-62.
+ * cam2world [B,16] row-major 4x4, intrinsics [B,9] row-major 3x3 (normalised),
+ * origins/dirs [B,res*res,3]; ray m = row*res + col. */
+int p3d_ray_sampler(const float* cam2world, const float* intrinsics, int B, int res,
+                    float* origins, float* dirs, p3d_stream_t stream);
+
+/* Layout change for the tri-plane gather: [N,C,H,W] (backbone output viewed as N = B*3 planes,
+ * training/triplane_cond.py:1042) -> [N,H,W,C] so that one bilinear tap of all C=32 channels is a
+ * single 128-byte line. */
+int p3d_planes_to_channels_last(const float* planes_nchw, float* planes_nhwc, int N, int C, int H, int W,
+                                p3d_stream_t stream);
+
+/* Decoder description: OSGDecoder (training/triplane.py:112-135), OSGDecoder_semantic
+ * (training/triplane_cond.py:859-887), OSGDecoder_semantic_lateSeparate (:926-970).
+ * Every net is FC(32->64) -> Softplus -> FC(64->33) (networks_stylegan2.py:96-127). */
+typedef struct {
+    int32_t n_nets;          /* 1 or 2 */
+    int32_t sigma_net;       /* which net's output channel 0 is sigma */
+    uint32_t sigmoid_mask[2];/* bit o set: colour output o (0..31) of that net gets sigmoid*1.002-0.001 */
+    /* raw parameters as stored in the module (not yet multiplied by the equalised-lr gains) */
+    const float* w1[2];      /* [64,32] */
+    const float* b1[2];      /* [64] */
+    const float* w2[2];      /* [33,64] */
+    const float* b2[2];      /* [33] */
+    float w1_gain[2], b1_gain[2], w2_gain[2], b2_gain[2]; /* FullyConnectedLayer.weight_gain / bias_gain */
+} p3d_decoder_t;
+
+#define P3D_DECODER_PACKED_FLOATS (2 * 4260)
+/* Multiplies by the gains exactly as FullyConnectedLayer.forward does (networks_stylegan2.py:111-119)
+ * and writes the kernel-side layout into packed[P3D_DECODER_PACKED_FLOATS]. */
+int p3d_pack_decoder(const p3d_decoder_t* dec, float* packed, p3d_stream_t stream);
+
+typedef struct {
+    /* inputs */
+    const float* planes_nhwc;    /* [B,3,H,W,32] fp32 */
+    const float* ray_origins;    /* [B,R,3] */
+    const float* ray_dirs;       /* [B,R,3] */
+    const float* depths_coarse;  /* [B,R,Sc]  (sample_stratified output, renderer.py:169-192) */
+    const float* u_importance;   /* [B*R,Sf]  uniform draws of sample_pdf (renderer.py:237); unused if Sf==0 */
+    const float* decoder_packed; /* from p3d_pack_decoder */
+    int32_t n_nets, sigma_net;
+    uint32_t sigmoid_mask[2];
+    int32_t B, R, H, W, Sc, Sf;
+    float   coord_scale;         /* 2/box_warp (renderer.py:61) */
+    int32_t white_back;          /* rendering_options.get('white_back') (ray_marcher.py:52) */
+    /* outputs */
+    float* out_feat;             /* [B,R,32*n_nets]  composite_rgb*2-1 */
+    float* out_depth;            /* [B,R]            clamped to the global [min,max] of all depths */
+    float* out_wsum;             /* [B,R]            weights.sum(2) (renderer.py:140) */
+    /* optional stage outputs for parity tests (NULL to skip) */
+    float*   dbg_weights_coarse; /* [B,R,Sc-1]   MipRayMarcher2 weights of the coarse pass */
+    float*   dbg_depths_fine;    /* [B,R,Sf] */
+    int32_t* dbg_inds;           /* [B,R,Sf]     searchsorted(cdf,u,right=True) (renderer.py:240) */
+    int32_t* dbg_perm;           /* [B,R,Sc+Sf]  sort permutation over cat(coarse,fine) (renderer.py:162) */
+    float*   dbg_weights_final;  /* [B,R,Sc+Sf-1] */
+    /* scratch: 4 x uint32, zeroed by the callee on the stream before launch */
+    uint32_t* workspace;
+} p3d_render_args_t;
+
+/* ImportanceRenderer.forward for scalar ray limits -- training/volumetric_rendering/renderer.py:88-140:
+ * coarse sample+decode -> MipRayMarcher2 weights (ray_marcher.py:25-57) -> sample_importance (:194-253)
+ * -> fine sample+decode -> unify_samples (:157-167) -> final ray march, as one persistent kernel. */
+int p3d_render_fwd(const p3d_render_args_t* args, p3d_stream_t stream);
+
+/* ImportanceRenderer.run_model -- renderer.py:142-148 (sample_from_planes :55-65 + decoder):
+ * coords [B,M,3] -> rgb [B,M,32*n_nets], sigma [B,M]. density_noise is added by the host wrapper. */
+int p3d_run_model(const float* planes_nhwc, const float* coords, const float* decoder_packed,
+                  int n_nets, int sigma_net, const uint32_t sigmoid_mask[2],
+                  int B, int M, int H, int W, float coord_scale,
+                  float* out_rgb, float* out_sigma, p3d_stream_t stream);
+
+/* sample_from_planes alone -- renderer.py:55-65: features [B,3,M,32] (the reference's output layout). */
+int p3d_sample_from_planes(const float* planes_nhwc, const float* coords, int B, int M, int H, int W,
+                           float coord_scale, float* out_features, p3d_stream_t stream);
+
+/* MipRayMarcher2.run_forward on explicit tensors -- ray_marcher.py:25-57.
+ * colors [N,S,Cc], densities [N,S], depths [N,S]; out_rgb [N,Cc], out_depth [N] (clamped),
+ * out_weights [N,S-1]. N = B*R rays. */
+int p3d_ray_march(const float* colors, const float* densities, const float* depths,
+                  int N, int S, int Cc, int white_back,
+                  float* out_rgb, float* out_depth, float* out_weights,
+                  uint32_t* workspace, p3d_stream_t stream);
+
+/* sample_importance + sample_pdf -- renderer.py:194-253. z_vals [N,S], weights [N,S-1], u [N,Sf];
+ * out_samples [N,Sf], out_inds [N,Sf] (may be NULL). */
+int p3d_sample_importance(const float* z_vals, const float* weights, const float* u,
+                          int N, int S, int Sf, float* out_samples, int32_t* out_inds, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * StyleGAN2 custom ops (torch_utils/ops/*)
+ * ------------------------------------------------------------------------------------------- */
+
+/* bias_act plugin -- torch_utils/ops/bias_act.cpp:36-94, kernel bias_act.cu:27-151.
+ * y = clamp(act(x + b[(i/step_b) % size_b]) * gain). grad = 0/1/2 selects forward / first / second
+ * order as in the reference; xref/yref/dy may be NULL when unused. act: 1..9 = linear, relu, lrelu,
+ * tanh, sigmoid, elu, selu, softplus, swish (bias_act.py:23-33 cuda_idx). clamp < 0 disables. */
+int p3d_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                 int dtype, int grad, int act, float alpha, float gain, float clamp,
+                 int64_t size_x, int size_b, int64_t step_b, p3d_stream_t stream);
+
+/* upfirdn2d plugin -- torch_utils/ops/upfirdn2d.cpp:20-102, kernels upfirdn2d.cu:33-204.
+ * x [N,C,inH,inW] with element strides x_stride[4] (n,c,h,w); f [fH,fW] fp32 contiguous (already
+ * expanded to 2-D); y [N,C,outH,outW] with strides y_stride[4]. */
+int p3d_upfirdn2d(const void* x, const float* f, void* y, int dtype,
+                  const int32_t x_size[4], const int64_t x_stride[4],
+                  const int32_t y_size[4], const int64_t y_stride[4],
+                  int fw, int fh, int upx, int upy, int downx, int downy,
+                  int padx0, int pady0, int flip, float gain, p3d_stream_t stream);
+
+/* Fused epilogue of an up=2 modulated conv (networks_stylegan2.py:324-331 + conv2d_resample.py:128):
+ * y = clamp(lrelu(upfirdn2d(x, f, pad, gain=up^2) [* dcoef[n,c]] + noise[h,w]*noise_strength + b[c]) * act_gain).
+ * One read of x, one write of y instead of three passes. Any of dcoef/noise/b may be NULL. */
+int p3d_fir_bias_act(const void* x, const float* f, const float* dcoef, const float* noise, const void* b, void* y,
+                     int dtype, const int32_t x_size[4], const int32_t y_size[4],
+                     int fw, int fh, int padx0, int pady0, float fir_gain,
+                     int act, float alpha, float act_gain, float clamp,
+                     int64_t noise_stride_n, p3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_H_ */

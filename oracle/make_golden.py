@@ -1,0 +1,302 @@
+"""Generate tests/golden/*.npz by running the REFERENCE implementation (imported read-only from /root/reference)
+on CPU with seeded inputs.
+
+Runs only in the authoring container: the GPU box has no /root/reference, which is why the outputs are committed.
+    python oracle/make_golden.py            # writes tests/golden/{renderer,ops,synthesis}_*.npz
+
+The renderer's two random draws (stratified jitter, renderer.py:190; importance u, renderer.py:237) are captured
+by wrapping torch.rand_like / torch.rand while the reference runs, and stored so that every implementation can be
+fed the identical noise.
+"""
+import contextlib
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'tests', 'golden')
+
+
+@contextlib.contextmanager
+def capture_rand(store):
+    o_like, o_rand, o_randn = torch.rand_like, torch.rand, torch.randn
+
+    def rl(x, *a, **k):
+        r = o_like(x, *a, **k); store.append(('rand_like', r.clone())); return r
+
+    def rr(*a, **k):
+        r = o_rand(*a, **k); store.append(('rand', r.clone())); return r
+
+    torch.rand_like, torch.rand = rl, rr
+    try:
+        yield
+    finally:
+        torch.rand_like, torch.rand, torch.randn = o_like, o_rand, o_randn
+
+
+def state_digest(module):
+    h = hashlib.sha256()
+    for k, v in sorted(module.state_dict().items()):
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def poses(n, seed, radius=2.7, pivot=(0, 0, -0.06), fov=18.837):
+    import camera_utils
+    g = np.random.RandomState(seed)
+    c = []
+    for _ in range(n):
+        yaw = np.pi / 2 + g.uniform(-0.35, 0.35)
+        pitch = np.pi / 2 + g.uniform(-0.25, 0.25)
+        c2w = camera_utils.LookAtPoseSampler.sample(yaw, pitch, torch.tensor(pivot, dtype=torch.float32), radius=radius)
+        K = camera_utils.FOV_to_intrinsics(fov)
+        c.append(torch.cat([c2w.reshape(1, 16), K.reshape(1, 9)], 1))
+    return torch.cat(c, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+def golden_renderer():
+    from training.volumetric_rendering.renderer import ImportanceRenderer
+    from training.volumetric_rendering.ray_sampler import RaySampler
+    from training.triplane import OSGDecoder
+    from training.triplane_cond import OSGDecoder_semantic_lateSeparate
+
+    cases = {
+        # name: (B, plane res, nrr, Sc, Sf, decoder, options)
+        'seg': (2, 32, 12, 12, 12, 'late6', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'seg48': (1, 40, 6, 48, 48, 'late6', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'car': (2, 24, 10, 16, 16, 'late1', dict(ray_start=0.1, ray_end=2.6, box_warp=1.6, white_back=True)),
+        'rgb_only': (1, 32, 9, 10, 6, 'osg', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'coarse_only': (1, 32, 8, 9, 0, 'osg', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'far_outside': (1, 32, 8, 12, 12, 'late6', dict(ray_start=0.5, ray_end=6.0, box_warp=1)),
+    }
+    for name, (B, H, nrr, Sc, Sf, dkind, extra) in cases.items():
+        torch.manual_seed(abs(hash(name)) % 1000 + 7)
+        torch.manual_seed({'seg': 11, 'seg48': 12, 'car': 13, 'rgb_only': 14, 'coarse_only': 15, 'far_outside': 16}[name])
+        planes = torch.randn(B, 3, 32, H, H)
+        if dkind == 'osg':
+            dec = OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32})
+        else:
+            cs = 6 if dkind == 'late6' else 1
+            dec = OSGDecoder_semantic_lateSeparate(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32,
+                                                        'sigmoid': cs == 1, 'semantic_channels': cs})
+        with torch.no_grad():   # make biases non-trivial
+            for p in dec.parameters():
+                if p.ndim == 1:
+                    p.copy_(torch.randn_like(p) * 0.5)
+        fov = 18.837 if 'car' not in name else 45.0
+        radius = 2.7 if 'car' not in name else 1.7
+        c = poses(B, 3, radius=radius, pivot=(0, 0, 0) if 'car' in name else (0, 0, -0.06), fov=fov)
+        c2w, K = c[:, :16].reshape(-1, 4, 4), c[:, 16:].reshape(-1, 3, 3)
+        o, d = RaySampler()(c2w, K, nrr)
+        opts = dict(depth_resolution=Sc, depth_resolution_importance=Sf, disparity_space_sampling=False,
+                    clamp_mode='softplus', **extra)
+        R = ImportanceRenderer()
+        # stage tensors through hooks on the methods
+        rec = {}
+        orig_imp, orig_march, orig_unify = R.sample_importance, R.ray_marcher.forward, R.unify_samples
+        march_calls = []
+
+        def march(colors, dens, depths, ro):
+            out = orig_march(colors, dens, depths, ro); march_calls.append(out[2].clone()); return out
+
+        def imp(z, w, n):
+            out = orig_imp(z, w, n); rec['depths_fine'] = out.clone(); return out
+
+        def unify(d1, c1, s1, d2, c2, s2):
+            alld = torch.cat([d1, d2], -2)
+            rec['perm'] = torch.sort(alld, dim=-2, stable=True)[1][..., 0].clone()
+            return orig_unify(d1, c1, s1, d2, c2, s2)
+
+        R.sample_importance, R.ray_marcher.forward, R.unify_samples = imp, march, unify
+        draws = []
+        with torch.no_grad(), capture_rand(draws):
+            feat, depth, wsum = R(planes, dec, o, d, opts)
+        jitter = draws[0][1]
+        u = draws[1][1] if Sf > 0 else torch.zeros(B * nrr * nrr, 0)
+        save = dict(planes=planes, cam2world=c2w, intrinsics=K, ray_origins=o, ray_dirs=d, jitter=jitter, u=u,
+                    feat=feat, depth=depth, wsum=wsum, weights_final=march_calls[-1][..., 0],
+                    Sc=Sc, Sf=Sf, nrr=nrr, decoder=dkind, **{'opt_' + k: v for k, v in extra.items()})
+        if Sf > 0:
+            save.update(weights_coarse=march_calls[0][..., 0], depths_fine=rec['depths_fine'][..., 0], perm=rec['perm'])
+        for k, v in dec.state_dict().items():
+            save['dec.' + k] = v
+        np.savez_compressed(os.path.join(OUT, f'renderer_{name}.npz'),
+                            **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in save.items()})
+        print('renderer', name, tuple(feat.shape))
+
+
+# ---------------------------------------------------------------------------------------------
+def golden_ops():
+    from torch_utils.ops import bias_act, upfirdn2d, conv2d_resample
+    from training.networks_stylegan2 import modulated_conv2d
+    save = {}
+    g = torch.Generator().manual_seed(5)
+    # bias_act: forward + first/second order gradients of the reference's _ref path via autograd (float64 for the grads)
+    x = torch.randn(3, 5, 4, 6, generator=g) * 2
+    b = torch.randn(5, generator=g)
+    save['ba_x'], save['ba_b'] = x, b
+    for act in bias_act.activation_funcs:
+        for tag, kw in (('d', {}), ('c', dict(gain=1.7, clamp=0.9, alpha=0.3))):
+            xx = x.clone().double().requires_grad_(True)
+            bb = b.clone().double().requires_grad_(True)
+            y = bias_act.bias_act(xx, bb, act=act, impl='ref', **kw)
+            gy = torch.randn(y.shape, generator=g).double()
+            gx, = torch.autograd.grad(y, xx, gy, create_graph=True)
+            ggx = torch.randn(gx.shape, generator=g).double()
+            if gx.requires_grad:
+                g2x, = torch.autograd.grad(gx, xx, ggx, allow_unused=True)
+                g2x = torch.zeros_like(xx) if g2x is None else g2x
+            else:
+                g2x = torch.zeros_like(xx)
+            save[f'ba_{act}_{tag}_y'] = bias_act.bias_act(x, b, act=act, impl='ref', **kw)
+            save[f'ba_{act}_{tag}_y64'] = y.detach()
+            save[f'ba_{act}_{tag}_gy'], save[f'ba_{act}_{tag}_gx'] = gy, gx.detach()
+            save[f'ba_{act}_{tag}_ggx'], save[f'ba_{act}_{tag}_g2x'] = ggx, g2x.detach()
+    # upfirdn2d: the shapes of SURVEY section 8(a19) at small size + odd cases
+    f4 = upfirdn2d.setup_filter([1, 3, 3, 1])
+    f8 = upfirdn2d.setup_filter([1, 2, 3, 4, 4, 3, 2, 1])           # separable (8 taps)
+    f32_ = upfirdn2d.setup_filter(torch.randn(3, 5, generator=g), normalize=False)
+    xs = torch.randn(2, 3, 9, 11, generator=g)
+    save['up_x'] = xs
+    save['up_f4'], save['up_f8'], save['up_f35'] = f4, f8, f32_
+    cfgs = {
+        'post_tconv': dict(f='f4', up=1, down=1, padding=[1, 1, 1, 1], gain=4),
+        'skip_up': dict(f='f4', up=2, down=1, padding=[2, 1, 2, 1], gain=4),
+        'down2': dict(f='f4', up=1, down=2, padding=[1, 1, 1, 1], gain=1),
+        'pre_sconv': dict(f='f4', up=1, down=1, padding=[2, 2, 2, 2], gain=1),
+        'sep8_up2': dict(f='f8', up=2, down=1, padding=[4, 3, 4, 3], gain=4),
+        'odd': dict(f='f35', up=[3, 2], down=[2, 1], padding=[2, 0, -1, 3], gain=0.7, flip_filter=True),
+        'crop': dict(f='f4', up=1, down=1, padding=[-1, 2, 0, -2], gain=1),
+        'identity': dict(f=None, up=1, down=1, padding=0, gain=1),
+    }
+    fmap = dict(f4=f4, f8=f8, f35=f32_)
+    for name, kw in cfgs.items():
+        kw = dict(kw)
+        f = fmap.get(kw.pop('f'))
+        save[f'up_{name}_y'] = upfirdn2d.upfirdn2d(xs, f, impl='ref', **kw)
+    # conv2d_resample + modulated_conv2d
+    xc = torch.randn(2, 6, 8, 8, generator=g)
+    w3 = torch.randn(5, 6, 3, 3, generator=g)
+    w1 = torch.randn(5, 6, 1, 1, generator=g)
+    st = torch.randn(2, 6, generator=g) + 1
+    nz = torch.randn(1, 1, 16, 16, generator=g) * 0.1
+    save.update(mc_x=xc, mc_w3=w3, mc_w1=w1, mc_styles=st, mc_noise16=nz)
+    save['cr_up2'] = conv2d_resample.conv2d_resample(xc, w3, f=f4, up=2, padding=1, flip_weight=False)
+    save['cr_down2'] = conv2d_resample.conv2d_resample(xc, w3, f=f4, down=2, padding=1)
+    save['cr_1x1_down2'] = conv2d_resample.conv2d_resample(xc, w1, f=f4, down=2)
+    save['cr_1x1_up2'] = conv2d_resample.conv2d_resample(xc, w1, f=f4, up=2)
+    save['cr_plain'] = conv2d_resample.conv2d_resample(xc, w3, padding=1)
+    for fused in (True, False):
+        t = 'f' if fused else 'n'
+        save[f'mc_up2_{t}'] = modulated_conv2d(xc.clone(), w3, st, noise=nz, up=2, padding=1, resample_filter=f4,
+                                               flip_weight=False, fused_modconv=fused)
+        save[f'mc_plain_{t}'] = modulated_conv2d(xc.clone(), w3, st, noise=nz[:, :, :8, :8], padding=1, fused_modconv=fused)
+        save[f'mc_torgb_{t}'] = modulated_conv2d(xc.clone(), w1, st, demodulate=False, fused_modconv=fused)
+    np.savez_compressed(os.path.join(OUT, 'ops.npz'), **{k: v.detach().numpy() for k, v in save.items()})
+    print('ops', len(save), 'arrays')
+
+
+# ---------------------------------------------------------------------------------------------
+SYNTH_CASES = {
+    # config-1-like smoke models (BASELINE.json configs[0]); weights come from torch.manual_seed(seed)
+    'seg_tiny': dict(seed=21, cls='TriPlaneSemanticEntangleGenerator', img_resolution=128, semantic_channels=6, nrr=16, Sc=12,
+                     Sf=12, B=2, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
+    'car_tiny': dict(seed=22, cls='TriPlaneSemanticEntangleGenerator', img_resolution=128, semantic_channels=1, nrr=16, Sc=8,
+                     Sf=8, B=1, channel_base=1024, channel_max=16, ray=(0.1, 2.6, 1.6), white_back=True, mapping='edge', in_res=32),
+    'rgb_tiny': dict(seed=23, cls='TriPlaneGenerator', img_resolution=128, semantic_channels=0, nrr=16, Sc=10, Sf=6, B=1,
+                     channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
+}
+
+
+def synth_kwargs(case):
+    sem = case['semantic_channels']
+    rk = dict(image_resolution=case['img_resolution'], disparity_space_sampling=False, clamp_mode='softplus',
+              superresolution_module='training.superresolution.SuperresolutionHybrid2X',
+              superresolution_module_semantic='training.superresolution.SuperresolutionHybrid2X_semantic',
+              c_gen_conditioning_zero=False, gpc_reg_prob=0.5, c_scale=1.0, superresolution_noise_mode='none',
+              density_reg=0.25, density_reg_p_dist=0.004, reg_type='l1', decoder_lr_mul=1.0, sr_antialias=True,
+              depth_resolution=case['Sc'], depth_resolution_importance=case['Sf'], ray_start=case['ray'][0],
+              ray_end=case['ray'][1], box_warp=case['ray'][2], avg_camera_radius=2.7, avg_camera_pivot=[0, 0, -0.06])
+    if case.get('white_back'):
+        rk['white_back'] = True
+    mk = dict(class_name='training.triplane_cond.' + ('MaskMappingNetwork_disentangle' if case['mapping'] == 'mask'
+                                                      else 'EdgeMappingNetwork_disentangle'),
+              num_layers=2, in_resolution=case['in_res'], in_channels=max(sem, 1) if case['mapping'] == 'mask' else 1)
+    if case['mapping'] == 'mask' and sem == 0:
+        mk['in_channels'] = 6
+    kw = dict(z_dim=32, c_dim=25, w_dim=512, img_resolution=case['img_resolution'], img_channels=3, mapping_kwargs=mk,
+              rendering_kwargs=rk, channel_base=case['channel_base'], channel_max=case['channel_max'],
+              fused_modconv_default='inference_only', num_fp16_res=0, sr_num_fp16_res=4, conv_clamp=None,
+              sr_kwargs=dict(channel_base=case['channel_base'], channel_max=case['channel_max'],
+                             fused_modconv_default='inference_only'))
+    if sem > 0:
+        kw['semantic_channels'] = sem
+    return kw
+
+
+def build_generator(module, case):
+    """`module` is training.triplane_cond of whichever implementation is being built."""
+    torch.manual_seed(case['seed'])
+    G = getattr(module, case['cls'])(**synth_kwargs(case)).eval().requires_grad_(False)
+    # make the noise / w_avg paths live (they initialise to zero: networks_stylegan2.py:310)
+    g = torch.Generator().manual_seed(case['seed'] + 1000)
+    for name, p in G.named_parameters():
+        if name.endswith('noise_strength'):
+            p.copy_(torch.randn([], generator=g) * 0.1)
+        if name.endswith('.bias') and p.ndim == 1 and 'affine' not in name:
+            p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return G
+
+
+def synth_inputs(case):
+    g = torch.Generator().manual_seed(case['seed'] + 2000)
+    B = case['B']
+    z = torch.randn(B, 32, generator=g)
+    c = poses(B, case['seed'])
+    if case['mapping'] == 'mask':
+        nclass = max(case['semantic_channels'], 1) if case['semantic_channels'] else 6
+        blocks = torch.randint(0, nclass, (B, 1, 4, 4), generator=g)
+        mask = blocks.repeat_interleave(case['in_res'] // 4, 2).repeat_interleave(case['in_res'] // 4, 3)
+    else:
+        mask = (torch.rand(B, 1, case['in_res'], case['in_res'], generator=g) < 0.05).float() * 2 - 1
+    return z, c, mask
+
+
+def golden_synthesis():
+    import training.triplane_cond as ref_tc
+    for name, case in SYNTH_CASES.items():
+        G = build_generator(ref_tc, case)
+        z, c, mask = synth_inputs(case)
+        draws = []
+        with torch.no_grad():
+            ws = G.mapping(z, c, {'mask': mask, 'pose': c})
+            with capture_rand(draws):
+                out = G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=case['nrr'])
+            planes = G.backbone.synthesis(ws, noise_mode='const')
+            pts = torch.rand(case['B'], 50, 3, generator=torch.Generator().manual_seed(9)) - 0.5
+            smp = G.sample_mixed(pts, None, ws, noise_mode='const')
+        save = dict(z=z, c=c, mask=mask, ws=ws, jitter=draws[0][1], u=draws[1][1], planes_sub=planes[:, :, 3::16, 5::16].contiguous(), pts=pts,
+                    sample_rgb=smp['rgb'], sample_sigma=smp['sigma'], **{'out_' + k: v for k, v in out.items()})
+        arrays = {k: v.detach().numpy() for k, v in save.items()}
+        arrays['state_digest'] = np.frombuffer(state_digest(G).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, f'synthesis_{name}.npz'), **arrays)
+        print('synthesis', name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+if __name__ == '__main__':
+    assert os.path.isdir(REF), 'the reference checkout is only available in the authoring container'
+    sys.path.insert(0, REF)
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ['renderer', 'ops', 'synthesis']
+    if 'renderer' in which:
+        golden_renderer()
+    if 'ops' in which:
+        golden_ops()
+    if 'synthesis' in which:
+        golden_synthesis()

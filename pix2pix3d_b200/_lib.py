@@ -1,0 +1,117 @@
+"""ctypes binding of libp3d.so (the C-ABI declared in include/p3d.h).
+
+The library is built ahead of time by `pix2pix3d_b200.build`; there is no JIT and no fallback: a CUDA
+tensor reaching an op without the library raises immediately.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libp3d.so')
+ABI_VERSION = 1
+
+_lib = None
+
+c_void_p, c_int, c_int32, c_int64, c_float, c_uint32 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint32)
+
+P3D_F32, P3D_F16, P3D_F64 = 0, 1, 2
+DTYPE_CODE = {torch.float32: P3D_F32, torch.float16: P3D_F16, torch.float64: P3D_F64}
+
+
+class DecoderDesc(ctypes.Structure):  # p3d_decoder_t
+    _fields_ = [
+        ('n_nets', c_int32), ('sigma_net', c_int32), ('sigmoid_mask', c_uint32 * 2),
+        ('w1', c_void_p * 2), ('b1', c_void_p * 2), ('w2', c_void_p * 2), ('b2', c_void_p * 2),
+        ('w1_gain', c_float * 2), ('b1_gain', c_float * 2), ('w2_gain', c_float * 2), ('b2_gain', c_float * 2),
+    ]
+
+
+class RenderArgs(ctypes.Structure):  # p3d_render_args_t
+    _fields_ = [
+        ('planes_nhwc', c_void_p), ('ray_origins', c_void_p), ('ray_dirs', c_void_p), ('depths_coarse', c_void_p),
+        ('u_importance', c_void_p), ('decoder_packed', c_void_p),
+        ('n_nets', c_int32), ('sigma_net', c_int32), ('sigmoid_mask', c_uint32 * 2),
+        ('B', c_int32), ('R', c_int32), ('H', c_int32), ('W', c_int32), ('Sc', c_int32), ('Sf', c_int32),
+        ('coord_scale', c_float), ('white_back', c_int32),
+        ('out_feat', c_void_p), ('out_depth', c_void_p), ('out_wsum', c_void_p),
+        ('dbg_weights_coarse', c_void_p), ('dbg_depths_fine', c_void_p), ('dbg_inds', c_void_p),
+        ('dbg_perm', c_void_p), ('dbg_weights_final', c_void_p),
+        ('workspace', c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    'p3d_abi_version': (c_int, []),
+    'p3d_build_info': (ctypes.c_char_p, []),
+    'p3d_status_string': (ctypes.c_char_p, [c_int]),
+    'p3d_ray_sampler': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'p3d_planes_to_channels_last': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'p3d_pack_decoder': (c_int, [ctypes.POINTER(DecoderDesc), c_void_p, c_void_p]),
+    'p3d_render_fwd': (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),
+    'p3d_run_model': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_uint32), c_int, c_int, c_int,
+                              c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    'p3d_sample_from_planes': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'p3d_ray_march': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
+    'p3d_sample_importance': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'p3d_bias_act': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                             c_float, c_float, c_int64, c_int, c_int64, c_void_p]),
+    'p3d_upfirdn2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int32), ctypes.POINTER(c_int64),
+                              ctypes.POINTER(c_int32), ctypes.POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_int, c_float, c_void_p]),
+    'p3d_fir_bias_act': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), c_int, c_int, c_int, c_int, c_float,
+                                 c_int, c_float, c_float, c_float, c_int64, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: build it with `python -m pix2pix3d_b200.build` '
+                '(there is no CPU or PyTorch fallback for CUDA tensors).')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        got = handle.p3d_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f'libp3d.so ABI {got} != expected {ABI_VERSION}; rebuild the library')
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().p3d_status_string(status).decode()
+        raise RuntimeError(f'{what} failed: {msg} (status {status})')
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+# count of native kernel launches issued through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def bump(n=1):
+    global launch_count
+    launch_count += n

@@ -1,0 +1,58 @@
+// Shared helpers for libp3d.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/p3d.h"
+
+#define P3D_LAUNCH_CHECK()                                  \
+    do {                                                    \
+        cudaError_t e_ = cudaGetLastError();                \
+        if (e_ != cudaSuccess) return (int)e_;              \
+    } while (0)
+
+#define P3D_CUDA_TRY(expr)                                  \
+    do {                                                    \
+        cudaError_t e_ = (expr);                            \
+        if (e_ != cudaSuccess) return (int)e_;              \
+    } while (0)
+
+namespace p3d {
+
+constexpr int kWarp = 32;
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Number of SMs of the current device (cached per process; read-only after first call).
+int sm_count();
+
+// Monotone float -> uint32 key (larger float => larger key), for min/max with integer atomics.
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// log(1 + exp(x)); agrees with F.softplus(beta=1, threshold=20) to ~1.5e-7 absolute.
+__device__ __forceinline__ float softplus_f(float x) {
+    float u = __expf(-fabsf(x));
+    return fmaxf(x, 0.f) + __logf(1.f + u);
+}
+
+// sigmoid(x) * (1 + 2*0.001) - 0.001  (training/triplane.py:133)
+__device__ __forceinline__ float sigmoid_clamp_f(float x) {
+    float s = __fdividef(1.f, 1.f + __expf(-x));
+    return fmaf(s, 1.002f, -0.001f);
+}
+
+}  // namespace p3d

@@ -1,0 +1,230 @@
+"""Tensor-level wrappers over the C-ABI: allocate outputs with torch, pass raw device pointers.
+
+These are the calls the reference-facing modules (training/..., torch_utils/ops/...) make; nothing here
+has a CPU branch.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+PACKED_FLOATS = 2 * 4260
+
+
+def _f32c(t):
+    assert t.is_cuda, 'native ops need CUDA tensors'
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def ray_sampler(cam2world, intrinsics, resolution):
+    """RaySampler.forward -> (origins [B,M,3], dirs [B,M,3])."""
+    c2w = _f32c(cam2world.reshape(-1, 16))
+    K = _f32c(intrinsics.reshape(-1, 9))
+    B = c2w.shape[0]
+    M = resolution * resolution
+    origins = torch.empty(B, M, 3, device=c2w.device, dtype=torch.float32)
+    dirs = torch.empty_like(origins)
+    with torch.cuda.device(c2w.device):
+        st = _lib.lib().p3d_ray_sampler(_lib.ptr(c2w), _lib.ptr(K), B, resolution, _lib.ptr(origins), _lib.ptr(dirs),
+                                        _lib.stream_ptr())
+    _lib.check(st, 'p3d_ray_sampler')
+    _lib.bump()
+    return origins, dirs
+
+
+def planes_to_channels_last(planes):
+    """[B,3,C,H,W] (or [N,C,H,W]) fp32 -> [B,3,H,W,C]."""
+    p = _f32c(planes)
+    shp = p.shape
+    C, H, W = shp[-3], shp[-2], shp[-1]
+    N = p.numel() // (C * H * W)
+    out = torch.empty(*shp[:-3], H, W, C, device=p.device, dtype=torch.float32)
+    with torch.cuda.device(p.device):
+        st = _lib.lib().p3d_planes_to_channels_last(_lib.ptr(p), _lib.ptr(out), N, C, H, W, _lib.stream_ptr())
+    _lib.check(st, 'p3d_planes_to_channels_last')
+    _lib.bump()
+    return out
+
+
+class PackedDecoder:
+    """Kernel-side weights of an OSG decoder plus its static description."""
+
+    def __init__(self, packed, n_nets, sigma_net, masks):
+        self.packed = packed
+        self.n_nets = n_nets
+        self.sigma_net = sigma_net
+        self.masks = masks
+        self.out_channels = 32 * n_nets
+
+
+def describe_decoder(decoder):
+    """Map a decoder module onto (nets, sigma_net, sigmoid masks); None if the layout is not one of the
+    OSG decoders the fused kernels implement (training/triplane.py:112, training/triplane_cond.py:859,926)."""
+    name = type(decoder).__name__
+    nets = []
+    full = 0xFFFFFFFF
+    if name == 'OSGDecoder':
+        nets, sigma_net, masks = [decoder.net], 0, [full, 0]
+    elif name == 'OSGDecoder_semantic':
+        nets, sigma_net, masks = [decoder.net], 0, [full if decoder.final_sigmoid else 0, 0]
+    elif name == 'OSGDecoder_semantic_lateSeparate':
+        nets, sigma_net = [decoder.net, decoder.net_semantic], 1
+        masks = [full, full if decoder.semantic_sigmoid else 0]
+    elif name == 'OSGDecoder_semantic_entangle':
+        if decoder.feature_sigmoid:
+            m = full
+        else:
+            cs = int(decoder.semantic_channels)
+            m = full & ~(((1 << cs) - 1) << 3)   # colour outputs 3..3+Cs-1 stay raw (triplane_cond.py:916-918)
+        nets, sigma_net, masks = [decoder.net], 0, [m & full, 0]
+    else:
+        return None
+    for net in nets:
+        fc1, fc2 = net[0], net[2]
+        if tuple(fc1.weight.shape) != (64, 32) or tuple(fc2.weight.shape) != (33, 64):
+            return None
+        if fc1.bias is None or fc2.bias is None:
+            return None
+    return nets, sigma_net, masks
+
+
+def pack_decoder(decoder):
+    desc = describe_decoder(decoder)
+    if desc is None:
+        raise NotImplementedError(f'no fused kernel for decoder type {type(decoder).__name__}')
+    nets, sigma_net, masks = desc
+    dev = nets[0][0].weight.device
+    d = _lib.DecoderDesc()
+    d.n_nets = len(nets)
+    d.sigma_net = sigma_net
+    keep = []
+    for i, net in enumerate(nets):
+        fc1, fc2 = net[0], net[2]
+        w1, b1, w2, b2 = (_f32c(t.detach()) for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias))
+        keep += [w1, b1, w2, b2]
+        d.w1[i], d.b1[i], d.w2[i], d.b2[i] = w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr()
+        d.w1_gain[i], d.b1_gain[i] = float(fc1.weight_gain), float(fc1.bias_gain)
+        d.w2_gain[i], d.b2_gain[i] = float(fc2.weight_gain), float(fc2.bias_gain)
+        d.sigmoid_mask[i] = masks[i]
+    packed = torch.empty(PACKED_FLOATS, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        st = _lib.lib().p3d_pack_decoder(ctypes.byref(d), _lib.ptr(packed), _lib.stream_ptr())
+    _lib.check(st, 'p3d_pack_decoder')
+    _lib.bump()
+    del keep
+    return PackedDecoder(packed, len(nets), sigma_net, masks)
+
+
+def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_warp, white_back=False, debug=False):
+    """Fused ImportanceRenderer.forward. Returns (feat [B,R,C], depth [B,R,1], wsum [B,R,1][, debug dict])."""
+    B, _, H, W, C = planes_nhwc.shape
+    assert C == 32
+    R = ray_origins.shape[1]
+    o, d = _f32c(ray_origins), _f32c(ray_dirs)
+    dc = _f32c(depths_coarse).reshape(B, R, -1)
+    Sc = dc.shape[-1]
+    Sf = 0 if u is None else int(u.shape[-1])
+    uu = None if u is None else _f32c(u)
+    dev = planes_nhwc.device
+    feat = torch.empty(B, R, dec.out_channels, device=dev, dtype=torch.float32)
+    depth = torch.empty(B, R, 1, device=dev, dtype=torch.float32)
+    wsum = torch.empty(B, R, 1, device=dev, dtype=torch.float32)
+    ws = torch.empty(4, device=dev, dtype=torch.int32)
+    a = _lib.RenderArgs()
+    a.planes_nhwc, a.ray_origins, a.ray_dirs = planes_nhwc.data_ptr(), o.data_ptr(), d.data_ptr()
+    a.depths_coarse = dc.data_ptr()
+    a.u_importance = None if uu is None else uu.data_ptr()
+    a.decoder_packed = dec.packed.data_ptr()
+    a.n_nets, a.sigma_net = dec.n_nets, dec.sigma_net
+    a.sigmoid_mask[0], a.sigmoid_mask[1] = dec.masks[0], dec.masks[1]
+    a.B, a.R, a.H, a.W, a.Sc, a.Sf = B, R, H, W, Sc, Sf
+    a.coord_scale = 2.0 / float(box_warp)
+    a.white_back = 1 if white_back else 0
+    a.out_feat, a.out_depth, a.out_wsum = feat.data_ptr(), depth.data_ptr(), wsum.data_ptr()
+    dbg = {}
+    if debug:
+        S = Sc + Sf
+        dbg['weights_final'] = torch.empty(B, R, S - 1, device=dev, dtype=torch.float32)
+        dbg['perm'] = torch.empty(B, R, S, device=dev, dtype=torch.int32)
+        a.dbg_weights_final, a.dbg_perm = dbg['weights_final'].data_ptr(), dbg['perm'].data_ptr()
+        if Sf > 0:
+            dbg['weights_coarse'] = torch.empty(B, R, Sc - 1, device=dev, dtype=torch.float32)
+            dbg['depths_fine'] = torch.empty(B, R, Sf, device=dev, dtype=torch.float32)
+            dbg['inds'] = torch.empty(B, R, Sf, device=dev, dtype=torch.int32)
+            a.dbg_weights_coarse = dbg['weights_coarse'].data_ptr()
+            a.dbg_depths_fine, a.dbg_inds = dbg['depths_fine'].data_ptr(), dbg['inds'].data_ptr()
+    a.workspace = ws.data_ptr()
+    with torch.cuda.device(dev):
+        st = _lib.lib().p3d_render_fwd(ctypes.byref(a), _lib.stream_ptr())
+    _lib.check(st, 'p3d_render_fwd')
+    _lib.bump()
+    if debug:
+        return feat, depth, wsum, dbg
+    return feat, depth, wsum
+
+
+def run_model(planes_nhwc, dec, coords, box_warp):
+    """Fused sample_from_planes + decoder: coords [B,M,3] -> (rgb [B,M,C], sigma [B,M,1])."""
+    B, _, H, W, _ = planes_nhwc.shape
+    c = _f32c(coords)
+    M = c.shape[1]
+    dev = planes_nhwc.device
+    rgb = torch.empty(B, M, dec.out_channels, device=dev, dtype=torch.float32)
+    sigma = torch.empty(B, M, 1, device=dev, dtype=torch.float32)
+    masks = (ctypes.c_uint32 * 2)(dec.masks[0], dec.masks[1])
+    with torch.cuda.device(dev):
+        st = _lib.lib().p3d_run_model(_lib.ptr(planes_nhwc), _lib.ptr(c), _lib.ptr(dec.packed), dec.n_nets, dec.sigma_net,
+                                      masks, B, M, H, W, 2.0 / float(box_warp), _lib.ptr(rgb), _lib.ptr(sigma),
+                                      _lib.stream_ptr())
+    _lib.check(st, 'p3d_run_model')
+    _lib.bump()
+    return rgb, sigma
+
+
+def sample_from_planes(planes_nhwc, coords, box_warp):
+    """coords [B,M,3] -> features [B,3,M,32] (reference layout of sample_from_planes)."""
+    B, _, H, W, _ = planes_nhwc.shape
+    c = _f32c(coords)
+    M = c.shape[1]
+    out = torch.empty(B, 3, M, 32, device=planes_nhwc.device, dtype=torch.float32)
+    with torch.cuda.device(planes_nhwc.device):
+        st = _lib.lib().p3d_sample_from_planes(_lib.ptr(planes_nhwc), _lib.ptr(c), B, M, H, W, 2.0 / float(box_warp),
+                                               _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(st, 'p3d_sample_from_planes')
+    _lib.bump()
+    return out
+
+
+def ray_march(colors, densities, depths, white_back=False):
+    """MipRayMarcher2.run_forward on [B,R,S,C] / [B,R,S,1] / [B,R,S,1] tensors."""
+    B, R, S, Cc = colors.shape
+    col, den, dep = _f32c(colors), _f32c(densities), _f32c(depths)
+    dev = col.device
+    rgb = torch.empty(B, R, Cc, device=dev, dtype=torch.float32)
+    depth = torch.empty(B, R, 1, device=dev, dtype=torch.float32)
+    weights = torch.empty(B, R, S - 1, 1, device=dev, dtype=torch.float32)
+    ws = torch.empty(4, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        st = _lib.lib().p3d_ray_march(_lib.ptr(col), _lib.ptr(den), _lib.ptr(dep), B * R, S, Cc, 1 if white_back else 0,
+                                      _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(weights), _lib.ptr(ws), _lib.stream_ptr())
+    _lib.check(st, 'p3d_ray_march')
+    _lib.bump()
+    return rgb, depth, weights
+
+
+def sample_importance(z_vals, weights, u, return_inds=False):
+    """z_vals [N,S], weights [N,S-1], u [N,Sf] -> samples [N,Sf] (and searchsorted indices)."""
+    z, w, uu = _f32c(z_vals), _f32c(weights), _f32c(u)
+    N, S = z.shape
+    Sf = uu.shape[1]
+    out = torch.empty(N, Sf, device=z.device, dtype=torch.float32)
+    inds = torch.empty(N, Sf, device=z.device, dtype=torch.int32) if return_inds else None
+    with torch.cuda.device(z.device):
+        st = _lib.lib().p3d_sample_importance(_lib.ptr(z), _lib.ptr(w), _lib.ptr(uu), N, S, Sf, _lib.ptr(out),
+                                              _lib.ptr(inds), _lib.stream_ptr())
+    _lib.check(st, 'p3d_sample_importance')
+    _lib.bump()
+    return (out, inds) if return_inds else out
