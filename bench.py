@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the pix2pix3D render hot path (BASELINE.json metric: rendered images/s at 512^2 output, 128^2
+neural-rendering resolution, 48+48 samples per ray).
+
+    python bench.py --gpus 1 --steps K --warmup W                     # this repository (CUDA, libp3d.so)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                              # CPU port of the reference path (oracle/)
+
+A step is one `G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=128)` of
+TriPlaneSemanticEntangleGenerator on a batch of 4 (BASELINE configs[1]); weights are seeded random, inputs synthetic.
+`value` is timed with CUDA events with inputs resident in HBM; `e2e` repeats the measurement through the same public
+call with pinned-host inputs copied in and the two 512^2 outputs copied back inside the timed region.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = 'seg2cat_512'
+METRIC = 'rendered images/sec (512^2, 128^2 NeRF res, 96 samples/ray)'
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return None
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'power_w_max': max(pw), 'samples': len(sm),
+                'reasons': sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            with open(path) as fh:
+                return json.load(fh), 'measured (MEASURED_PEAKS.json)'
+        except (OSError, ValueError):
+            pass
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_port_step(state, n_images=1):
+    """One pass of the oracle (CPU port of the reference path, oracle/p3d_oracle) over `n_images` config-2 images."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import p3d_oracle as O
+    sd, ws, c, cfg, jitter, u = state
+    for i in range(n_images):
+        O.networks.generator_synthesis(ws[i:i + 1], c[i:i + 1], sd, cfg, jitter[i:i + 1], u[i * cfg['nrr'] ** 2:(i + 1) * cfg['nrr'] ** 2])
+
+
+def cpu_port_state(batch):
+    import numpy as np
+    import torch
+    from pix2pix3d_b200 import configs
+    torch.set_num_threads(os.cpu_count())
+    G = configs.build_generator(WORKLOAD, seed=0, device='cpu', with_mapping=False)
+    sd = {k: v.numpy() for k, v in G.state_dict().items()}
+    rk = dict(G.rendering_kwargs)
+    w = configs.WORKLOADS[WORKLOAD]
+    nrr = w['nrr']
+    ws = configs.synthetic_ws(batch, G.backbone.num_ws, 1).numpy()
+    c = configs.camera_labels(batch, 2).numpy()
+    rng = np.random.RandomState(1234)
+    jitter = rng.rand(batch, nrr * nrr, rk['depth_resolution'], 1).astype(np.float32)
+    u = rng.rand(batch * nrr * nrr, rk['depth_resolution_importance']).astype(np.float32)
+    cfg = dict(nrr=nrr, rendering_kwargs=rk, semantic_channels=w['semantic_channels'], sr_kind='SuperresolutionHybrid8XDC',
+               sr_kind_semantic='SuperresolutionHybrid8XDC_semantic', sr_fp16=True)
+    return sd, ws, c, cfg, jitter, u
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference is Python (it cannot be compiled into oracle/_ref and its source tree does not
+    travel to the GPU box), so this arm times the oracle port of the same path on the host cores. One step = one
+    config-2 image (the workload's unit); steps are capped so the run ends within a few minutes."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    state = cpu_port_state(1)
+    t0 = time.perf_counter()
+    cpu_port_step(state)                     # warm-up 1 (also sizes the run)
+    t_step = time.perf_counter() - t0
+    warm = max(1, min(args.warmup, int(60 / max(t_step, 1e-3))))
+    for _ in range(warm - 1):
+        cpu_port_step(state)
+    steps = max(1, min(args.steps, int(200 / max(t_step, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(state)
+    dt = time.perf_counter() - t0
+    value = steps / dt
+    cores = os.cpu_count()
+    sample = 'G.synthesis of 1 image at config-2 shapes (256^2 planes, 128^2 rays x 96 samples, two 8XDC SR stacks), fp32'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': warm, 'ms_per_step': 1000 * dt / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'batch_per_step': 1, 'device': 'cpu'},
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (default: the workload batch, 4)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--force-fp32', action='store_true', help='run the SR stacks in fp32 (reference default is fp16)')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from pix2pix3d_b200 import _lib, configs, native
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback of the product path)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.lib()   # fail loudly if the native library is missing
+
+    w = configs.WORKLOADS[WORKLOAD]
+    B = args.batch or w['batch']
+    nrr = w['nrr']
+    G = configs.build_generator(WORKLOAD, seed=0, device=dev, with_mapping=False)
+    rk = G.rendering_kwargs
+    S = rk['depth_resolution'] + rk['depth_resolution_importance']
+    # every rank renders its own batch (weak scaling, no collective on the render path)
+    ws_host = configs.synthetic_ws(B, G.backbone.num_ws, 1 + rank).pin_memory()
+    c_host = configs.camera_labels(B, 2 + rank).pin_memory()
+    ws, c = ws_host.to(dev), c_host.to(dev)
+    syn_kw = dict(noise_mode='const', neural_rendering_resolution=nrr)
+    if args.force_fp32:
+        syn_kw['force_fp32'] = True
+
+    def step(ws_, c_):
+        with torch.no_grad():
+            return G.synthesis(ws_, c_, **syn_kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        out = step(ws, c)
+    barrier()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    native.kernel_events = []
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step(ws, c)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = (_lib.launch_count - launches0) / args.steps
+    kev = native.kernel_events
+    native.kernel_events = None
+    render_ms = [a.elapsed_time(b) for (name, a, b) in kev if name == 'render_fwd']
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- end-to-end: pinned host inputs in, 512^2 outputs back, every step ---------------------
+    img_host = torch.empty(B, 3, w['img_resolution'], w['img_resolution'], dtype=torch.float32).pin_memory()
+    sem_host = torch.empty(B, w['semantic_channels'], w['img_resolution'], w['img_resolution'], dtype=torch.float32).pin_memory()
+    ws_d, c_d = torch.empty_like(ws), torch.empty_like(c)
+
+    def e2e_step():
+        ws_d.copy_(ws_host, non_blocking=True)
+        c_d.copy_(c_host, non_blocking=True)
+        o = step(ws_d, c_d)
+        img_host.copy_(o['image'], non_blocking=True)
+        sem_host.copy_(o['semantic'], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
+    h2d = ws_host.numel() * 4 + c_host.numel() * 4
+    d2h = img_host.numel() * 4 + sem_host.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused render) ---------------------------------------
+    peaks, peak_src = measured_peaks()
+    alg_bytes = configs.render_algorithmic_bytes(B, nrr * nrr, S)
+    roofline = None
+    if render_ms:
+        t_k = sum(render_ms) / len(render_ms) / 1000.0
+        achieved = alg_bytes / t_k / 1e9
+        roofline = {'kernel': 'render_fwd_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
+                    'kernel_ms': t_k * 1000, 'algorithmic_bytes': alg_bytes, 'share_of_step': t_k * 1000 / (ms / args.steps),
+                    'rays_per_s': B * nrr * nrr / t_k}
+
+    # ---- CPU baseline: the oracle port on the host cores, one image ----------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        state = cpu_port_state(1)
+        t0 = time.perf_counter()
+        cpu_port_step(state)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {'value': 1.0 / dt, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                        'sample': '1 image of the config-2 workload through oracle/p3d_oracle (numpy + ATen conv), fp32, '
+                                  f'{dt:.1f} s'}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32' if args.force_fp32 else 'f32 (backbone, renderer) + f16 (super-resolution, as the reference)',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'neural_rendering_resolution': nrr,
+                   'samples_per_ray': S, 'img_resolution': w['img_resolution'], 'parallelism': f'dp{world} (batch-sharded, no collective)',
+                   'l2_policy': 'no flush: per-step working set (planes 100 MB + SR activations > 2 GB) exceeds the 126 MB L2'},
+        'rays_per_s': world * B * nrr * nrr * args.steps / (ms / 1000.0),
+        'gpu_launches': launches,
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': ms_e2e / args.steps},
+        'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -9,7 +9,8 @@ Pinning: the reference ships no tests or golden vectors. T
 reference's own Python implementation, imported from /root/reference and run on CPU in the authoring container by
 oracle/make_golden.py; the resulting fixtures live in tests/golden/ and tests/test_oracle_golden.py checks the
 oracle against them. Dense-convolution arithmetic that the reference itself delegates to ATen
-(F.conv2d / F.conv_transpose2d, torch_utils/ops/conv2d_gradfix.py:40-45) is restated with explicit
-im2col + matmul in numpy.
+(F.conv2d / F.conv_transpose2d, torch_utils/ops/conv2d_gradfix.py:40-45) is available both ways: ATen's CPU
+convolution (default; keeps the CPU baseline at the reference's own CPU speed) and an explicit im2col + matmul
+restatement in numpy (P3D_ORACLE_NUMPY_CONV=1); the tests check that the two agree.
 """
 from . import ops, renderer, networks  # noqa: F401

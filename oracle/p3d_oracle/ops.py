@@ -1,5 +1,7 @@
 """numpy restatement of the reference's custom ops: torch_utils/ops/{bias_act,upfirdn2d,conv2d_resample,fma}.py
 and modulated_conv2d (training/networks_stylegan2.py:34-91). float32 unless the input is float64."""
+import os
+
 import numpy as np
 
 f32 = np.float32
@@ -166,6 +168,17 @@ def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
     if not flip_filter:
         k = np.flip(k, tuple(range(k.ndim)))
 
+    torch = _aten()
+    if torch is not None:
+        # the reference filters with a depthwise ATen convolution (upfirdn2d.py:203-209)
+        zt = torch.from_numpy(np.ascontiguousarray(z))
+        kt = torch.from_numpy(k.copy())
+        if k.ndim == 2:
+            zt = torch.nn.functional.conv2d(zt, kt[None, None].repeat(c, 1, 1, 1), groups=c)
+        else:
+            zt = torch.nn.functional.conv2d(zt, kt[None, None, None, :].repeat(c, 1, 1, 1), groups=c)
+            zt = torch.nn.functional.conv2d(zt, kt[None, None, :, None].repeat(c, 1, 1, 1), groups=c)
+        return zt.numpy()[:, :, ::downy, ::downx].astype(t)
     if k.ndim == 2:
         kh, kw = k.shape
         oh, ow = z.shape[2] - kh + 1, z.shape[3] - kw + 1
@@ -219,9 +232,29 @@ def filter2d(x, f, padding=0, flip_filter=False, gain=1):
 # ---------------------------------------------------------------------------------------------
 # dense convolutions (F.conv2d / F.conv_transpose2d semantics), im2col + matmul
 # ---------------------------------------------------------------------------------------------
+def _aten():
+    """ATen's CPU convolution -- the very call the reference makes (torch_utils/ops/conv2d_gradfix.py:40-45).
+    Default backend of the two dense convolutions below (it keeps the CPU baseline representative of the
+    reference's CPU speed); P3D_ORACLE_NUMPY_CONV=1 selects the explicit im2col + matmul restatement instead.
+    tests/test_oracle_golden.py checks that the two agree."""
+    if os.environ.get('P3D_ORACLE_NUMPY_CONV', '0') == '1':
+        return None
+    try:
+        import torch
+        return torch
+    except ImportError:
+        return None
+
+
 def conv2d(x, w, stride=1, padding=0, groups=1):
     """Cross-correlation. x [N,Cin,H,W], w [Cout,Cin/groups,kh,kw]."""
     x = np.asarray(x)
+    torch = _aten()
+    if torch is not None:
+        pad = tuple(padding) if not isinstance(padding, int) else padding
+        y = torch.nn.functional.conv2d(torch.from_numpy(np.ascontiguousarray(x)), torch.from_numpy(np.ascontiguousarray(w, x.dtype)),
+                                       stride=stride, padding=pad, groups=groups)
+        return y.numpy()
     t = x.dtype.type
     cdt = np.float64 if x.dtype == np.float64 else np.float32
     x = x.astype(cdt)
@@ -249,6 +282,13 @@ def conv2d(x, w, stride=1, padding=0, groups=1):
 def conv_transpose2d(x, w, stride=1, padding=0, groups=1):
     """x [N,Cin,H,W], w [Cin,Cout/groups,kh,kw] (PyTorch layout); output (H-1)*stride - 2*pad + k."""
     x = np.asarray(x)
+    torch = _aten()
+    if torch is not None:
+        pad = tuple(padding) if not isinstance(padding, int) else padding
+        y = torch.nn.functional.conv_transpose2d(torch.from_numpy(np.ascontiguousarray(x)),
+                                                 torch.from_numpy(np.ascontiguousarray(w, x.dtype)), stride=stride, padding=pad,
+                                                 groups=groups)
+        return y.numpy()
     t = x.dtype.type
     cdt = np.float64 if x.dtype == np.float64 else np.float32
     x = x.astype(cdt)

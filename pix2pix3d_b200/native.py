@@ -11,6 +11,9 @@ from . import _lib
 
 PACKED_FLOATS = 2 * 4260
 
+# when set to a list, render_fwd appends ('render_fwd', start_event, end_event) around its launch (bench.py)
+kernel_events = None
+
 
 def _f32c(t):
     assert t.is_cuda, 'native ops need CUDA tensors'
@@ -157,8 +160,15 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
             a.dbg_weights_coarse = dbg['weights_coarse'].data_ptr()
             a.dbg_depths_fine, a.dbg_inds = dbg['depths_fine'].data_ptr(), dbg['inds'].data_ptr()
     a.workspace = ws.data_ptr()
+    ev = None
+    if kernel_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     with torch.cuda.device(dev):
         st = _lib.lib().p3d_render_fwd(ctypes.byref(a), _lib.stream_ptr())
+    if ev is not None:
+        ev[1].record()
+        kernel_events.append(('render_fwd', ev[0], ev[1]))
     _lib.check(st, 'p3d_render_fwd')
     _lib.bump()
     if debug:

@@ -1,0 +1,151 @@
+"""bias_act / upfirdn2d CUDA kernels through the reference-facing functions (torch_utils.ops.*) and the C-ABI,
+against the oracle and the reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+import p3d_oracle as O
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64, torch.float16])
+def test_bias_act_forward_all_activations(dtype):
+    from pix2pix3d_b200.torch_utils.ops import bias_act
+    g = load_golden('ops')
+    x = torch.from_numpy(g['ba_x']).cuda().to(dtype)
+    b = torch.from_numpy(g['ba_b']).cuda().to(dtype)
+    tol = {torch.float32: 2e-6, torch.float64: 1e-12, torch.float16: 2e-3}[dtype]
+    for act in bias_act.activation_funcs:
+        for kw in ({}, dict(gain=1.7, clamp=0.9, alpha=0.3)):
+            y = bias_act.bias_act(x, b, act=act, **kw)
+            assert y.dtype == dtype and y.shape == x.shape
+            ref = O.ops.bias_act(x.cpu().numpy().astype(np.float64 if dtype == torch.float64 else np.float32),
+                                 b.cpu().numpy().astype(np.float64 if dtype == torch.float64 else np.float32), act=act, **kw)
+            assert rel_err(y.float().cpu().numpy() if dtype != torch.float64 else y.cpu().numpy(), ref) < tol, (act, kw)
+        # channels_last keeps its layout and values
+        xc = x.contiguous(memory_format=torch.channels_last)
+        yc = bias_act.bias_act(xc, b, act=act)
+        assert yc.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(yc.contiguous(), bias_act.bias_act(x, b, act=act))
+    # bias along another dim, no bias, no-op
+    y = bias_act.bias_act(x, torch.arange(6, device='cuda', dtype=dtype), dim=3, act='relu')
+    ref = O.ops.bias_act(x.double().cpu().numpy(), np.arange(6, dtype=np.float64), dim=3, act='relu')
+    assert rel_err(y.double().cpu().numpy(), ref) < max(tol, 1e-3 if dtype == torch.float16 else 0)
+    assert bias_act.bias_act(x, None, act='linear', gain=1) is not None
+
+
+def test_bias_act_gradients_first_and_second_order():
+    from pix2pix3d_b200.torch_utils.ops import bias_act
+    g = load_golden('ops')
+    for act in bias_act.activation_funcs:
+        for tag, kw in (('d', {}), ('c', dict(gain=1.7, clamp=0.9, alpha=0.3))):
+            x = torch.from_numpy(g['ba_x']).cuda().double().requires_grad_(True)
+            b = torch.from_numpy(g['ba_b']).cuda().double().requires_grad_(True)
+            y = bias_act.bias_act(x, b, act=act, **kw)
+            assert rel_err(y.detach().cpu().numpy(), g[f'ba_{act}_{tag}_y64']) < 1e-12
+            gy = torch.from_numpy(g[f'ba_{act}_{tag}_gy']).cuda()
+            gx, gb = torch.autograd.grad(y, [x, b], gy, create_graph=True)
+            assert rel_err(gx.detach().cpu().numpy(), g[f'ba_{act}_{tag}_gx']) < 1e-10, (act, tag)
+            assert rel_err(gb.detach().cpu().numpy(), g[f'ba_{act}_{tag}_gx'].sum((0, 2, 3))) < 1e-10
+            ggx = torch.from_numpy(g[f'ba_{act}_{tag}_ggx']).cuda()
+            if gx.requires_grad:
+                g2x, = torch.autograd.grad(gx, x, ggx, allow_unused=True)
+                g2x = torch.zeros_like(x) if g2x is None else g2x
+                ref = g[f'ba_{act}_{tag}_g2x']
+                assert np.abs(g2x.cpu().numpy() - ref).max() < 1e-10 * max(1.0, np.abs(ref).max()), (act, tag)
+
+
+def test_bias_act_large_and_unaligned():
+    from pix2pix3d_b200.torch_utils.ops import bias_act
+    torch.manual_seed(0)
+    x = torch.randn(3, 7, 33, 31, device='cuda')          # numel not a multiple of 4, step_b odd
+    b = torch.randn(7, device='cuda')
+    y = bias_act.bias_act(x, b, act='lrelu', clamp=1.5)
+    ref = bias_act.bias_act(x.cpu(), b.cpu(), act='lrelu', clamp=1.5)
+    assert rel_err(y.cpu().numpy(), ref.numpy()) < 1e-6
+    xs = x.flatten()[1:].reshape(-1)                       # misaligned base pointer
+    y2 = bias_act.bias_act(xs, None, act='tanh')
+    assert rel_err(y2.cpu().numpy(), torch.tanh(xs).cpu().numpy()) < 2e-6
+    h = torch.randn(4, 128, 65, 65, device='cuda', dtype=torch.float16)
+    bh = torch.randn(128, device='cuda', dtype=torch.float16)
+    yh = bias_act.bias_act(h, bh, act='lrelu', gain=1.2, clamp=256)
+    rh = bias_act.bias_act(h.float().cpu(), bh.float().cpu(), act='lrelu', gain=1.2, clamp=256)
+    assert rel_err(yh.float().cpu().numpy(), rh.numpy()) < 2e-3
+
+
+UP_CFGS = {
+    'post_tconv': dict(f='f4', up=1, down=1, padding=[1, 1, 1, 1], gain=4),
+    'skip_up': dict(f='f4', up=2, down=1, padding=[2, 1, 2, 1], gain=4),
+    'down2': dict(f='f4', up=1, down=2, padding=[1, 1, 1, 1], gain=1),
+    'pre_sconv': dict(f='f4', up=1, down=1, padding=[2, 2, 2, 2], gain=1),
+    'sep8_up2': dict(f='f8', up=2, down=1, padding=[4, 3, 4, 3], gain=4),
+    'odd': dict(f='f35', up=[3, 2], down=[2, 1], padding=[2, 0, -1, 3], gain=0.7, flip_filter=True),
+    'crop': dict(f='f4', up=1, down=1, padding=[-1, 2, 0, -2], gain=1),
+    'identity': dict(f=None, up=1, down=1, padding=0, gain=1),
+}
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.float64])
+def test_upfirdn2d_variants(dtype):
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    g = load_golden('ops')
+    fm = {k: torch.from_numpy(g['up_' + k]).cuda() for k in ('f4', 'f8', 'f35')}
+    x = torch.from_numpy(g['up_x']).cuda().to(dtype)
+    tol = {torch.float32: 2e-6, torch.float64: 2e-6, torch.float16: 2e-3}[dtype]
+    for name, kw in UP_CFGS.items():
+        kw = dict(kw)
+        f = fm.get(kw.pop('f'))
+        y = upfirdn2d.upfirdn2d(x, f, **kw)
+        assert y.dtype == dtype and tuple(y.shape) == g[f'up_{name}_y'].shape, name
+        assert rel_err(y.double().cpu().numpy(), g[f'up_{name}_y']) < tol, (name, dtype)
+        if dtype == torch.float32:
+            yc = upfirdn2d.upfirdn2d(x.contiguous(memory_format=torch.channels_last), f, **kw)
+            assert rel_err(yc.cpu().numpy(), g[f'up_{name}_y']) < tol, name + ' channels_last'
+
+
+def test_upfirdn2d_hot_shapes_and_gradient():
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    torch.manual_seed(0)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    for (n, c, h) in ((2, 16, 65), (1, 96, 32), (2, 5, 129)):
+        x = torch.randn(n, c, h, h, device='cuda')
+        y = upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)
+        ref = O.ops.upfirdn2d(x.cpu().numpy(), f.cpu().numpy(), padding=[1, 1, 1, 1], gain=4)
+        assert rel_err(y.cpu().numpy(), ref) < 2e-6
+        y = upfirdn2d.upsample2d(x, f)
+        ref = O.ops.upsample2d(x.cpu().numpy(), f.cpu().numpy())
+        assert rel_err(y.cpu().numpy(), ref) < 2e-6
+        y = upfirdn2d.downsample2d(x, f)
+        ref = O.ops.downsample2d(x.cpu().numpy(), f.cpu().numpy())
+        assert rel_err(y.cpu().numpy(), ref) < 2e-6
+    x = torch.randn(1, 2, 6, 7, device='cuda', dtype=torch.float64, requires_grad=True)
+    f64 = f
+    assert torch.autograd.gradcheck(lambda a: upfirdn2d.upfirdn2d(a, f64, up=2, padding=[2, 1, 2, 1], gain=4), (x,))
+    assert torch.autograd.gradcheck(lambda a: upfirdn2d.upfirdn2d(a, f64, down=2, padding=[1, 1, 1, 1]), (x,))
+    assert torch.autograd.gradgradcheck(lambda a: upfirdn2d.upfirdn2d(a, f64, padding=[1, 1, 1, 1]), (x,))
+
+
+def test_fused_fir_bias_act_equals_composition():
+    """p3d_fir_bias_act = upfirdn2d -> (*dcoef) + noise -> bias_act, the epilogue of an up=2 SynthesisLayer."""
+    import ctypes
+    from pix2pix3d_b200 import _lib
+    from pix2pix3d_b200.torch_utils.ops import bias_act, upfirdn2d
+    torch.manual_seed(1)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    for dtype, tol in ((torch.float32, 2e-6), (torch.float16, 2e-3)):
+        x = torch.randn(2, 6, 17, 17, device='cuda').to(dtype)
+        noise = torch.randn(16, 16, device='cuda') * 0.3
+        b = torch.randn(6, device='cuda').to(dtype)
+        y = torch.empty(2, 6, 16, 16, device='cuda', dtype=dtype)
+        xs = (_lib.c_int32 * 4)(*x.shape)
+        ys = (_lib.c_int32 * 4)(*y.shape)
+        st = _lib.lib().p3d_fir_bias_act(_lib.ptr(x), _lib.ptr(f), None, _lib.ptr(noise), _lib.ptr(b), _lib.ptr(y),
+                                         _lib.DTYPE_CODE[dtype], xs, ys, 4, 4, 1, 1, 4.0, 3, 0.2, float(np.sqrt(2)), 256.0, 0,
+                                         _lib.stream_ptr())
+        _lib.check(st, 'p3d_fir_bias_act')
+        ref = upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)
+        ref = ref.add_(noise)
+        ref = bias_act.bias_act(ref, b, act='lrelu', clamp=256)
+        assert rel_err(y.float().cpu().numpy(), ref.float().cpu().numpy()) < tol

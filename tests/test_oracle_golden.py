@@ -85,7 +85,9 @@ def test_bias_act_forward_and_gradients():
                 assert np.abs(g2 - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()), (act, tag, 'grad2')
 
 
-def test_upfirdn2d_variants():
+@pytest.mark.parametrize('numpy_conv', ['0', '1'])
+def test_upfirdn2d_variants(numpy_conv, monkeypatch):
+    monkeypatch.setenv('P3D_ORACLE_NUMPY_CONV', numpy_conv)
     g = load_golden('ops')
     x = g['up_x']
     fm = dict(f4=g['up_f4'], f8=g['up_f8'], f35=g['up_f35'])
@@ -109,7 +111,9 @@ def test_upfirdn2d_variants():
         assert rel_err(y, g[f'up_{name}_y']) < 2e-6, name
 
 
-def test_conv_resample_and_modconv():
+@pytest.mark.parametrize('numpy_conv', ['0', '1'])
+def test_conv_resample_and_modconv(numpy_conv, monkeypatch):
+    monkeypatch.setenv('P3D_ORACLE_NUMPY_CONV', numpy_conv)
     g = load_golden('ops')
     x, w3, w1, st, nz, f4 = g['mc_x'], g['mc_w3'], g['mc_w1'], g['mc_styles'], g['mc_noise16'], g['up_f4']
     assert rel_err(O.ops.conv2d_resample(x, w3, f=f4, up=2, padding=1, flip_weight=False), g['cr_up2']) < 1e-5
