@@ -664,6 +664,8 @@ __global__ void __launch_bounds__(256, 2) render_fwd_kernel(const RenderParams P
 
     // ---- global depth clamp: torch.clamp(depth, min(depths), max(depths)) (ray_marcher.py:49-50) ----
     __shared__ bool is_last;
+    __threadfence();          // every thread publishes its out_depth stores before the CTA signs off
+    __syncthreads();
     if (tid == 0) {
         atomicMax(a.workspace + 0, cta_keys[0]);
         atomicMax(a.workspace + 1, cta_keys[1]);
@@ -821,6 +823,7 @@ __global__ void __launch_bounds__(128) ray_march_kernel(const float* __restrict_
         kmin = max(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     }
     if (lane == 0) { atomicMax(&keys[0], kmax); atomicMax(&keys[1], kmin); }
+    __threadfence();
     __syncthreads();
     __shared__ bool is_last;
     if (threadIdx.x == 0) {
