@@ -161,6 +161,63 @@ int p3d_fir_bias_act(const void* x, const float* f, const float* dcoef, const fl
                      int act, float alpha, float act_gain, float clamp,
                      int64_t noise_stride_n, p3d_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core convolution path (training/networks_stylegan2.py:34-91 modulated_conv2d,
+ * torch_utils/ops/conv2d_resample.py:48-143; the reference bottoms out in cuDNN through conv2d_gradfix.py:37-45)
+ *
+ * Activations of this path are NHWC fp16. A "split" tensor is a pair of fp16 planes (hi, lo) with x = hi + lo,
+ * laid out [2][B][H][W][C]; fp32 layers of the reference (the tri-plane backbone) run on split tensors with three
+ * tensor-core passes, fp16 layers (super-resolution) on single-plane tensors with one pass.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* x;            /* [x_planes][B][H][W][C] fp16, C % 64 == 0 */
+    const void* w;            /* [w_planes][Bw][Cout_padded][n_kblocks*C] fp16, K-major; Bw = B (modulated) or 1 */
+    int32_t x_planes, w_planes, B, Bw, H, W, C, Cout, Cout_padded;
+    int32_t n_kblocks;        /* number of C-sized K blocks stored in w (9 for a 3x3 kernel) */
+    int32_t n_taps;           /* taps used by this launch (<= 9) */
+    int8_t  tap_dy[9], tap_dx[9], tap_k[9];   /* input offset of each tap and its K block in w */
+    int32_t split;            /* 0: one pass (plane 0 x plane 0); 1: hi*hi + hi*lo + lo*hi */
+    int32_t gH, gW;           /* grid of output positions computed by this launch */
+    int32_t oH, oW, sy, oy, sx, ox;   /* output tensor size and the affine map grid -> output (Y = y*sy + oy) */
+    void* y; void* y_lo;      /* output NHWC; y_lo only for out_mode 1 */
+    int32_t y_cstride, y_coff;/* channel stride of the output tensor and first channel written */
+    int32_t out_mode;         /* 0 fp16, 1 fp16 split (hi, lo), 2 fp32, 3 fp32 accumulate (y += result) */
+    const float* bias;        /* [Cout] or NULL */
+    const float* noise;       /* [oH*oW] (already multiplied by noise_strength) or NULL */
+    const float* dscale;      /* [B*Cout] per-sample output scale (demodulation) or NULL */
+    int32_t act;              /* 1 linear, 3 lrelu */
+    float alpha, gain, clamp; /* activation slope, output gain, clamp (<0: none) */
+    float acc_scale;          /* multiplies the accumulator first (undoes the power-of-two weight scaling) */
+} p3d_conv_args_t;
+
+/* One implicit-GEMM convolution launch (tcgen05 + TMA): 3x3 / 1x1 convolutions and the four phases of a stride-2
+ * transposed 3x3 convolution are all expressed through the tap list and the output map. */
+int p3d_conv_gemm(const p3d_conv_args_t* args, p3d_stream_t stream);
+
+/* Per-sample modulated (and optionally demodulated) weights, modulated_conv2d lines :58-67:
+ *   w'[b,o,i,k] = weight[o,i,k] * styles[b,i];  d[b,o] = rsqrt(sum_{i,k} w'^2 + 1e-8);  out = w' * d * scale
+ * written K-major [planes][B][Cout_padded][kh*kw][Cin_padded] as fp16 (planes = 2: hi/lo split). Rows >= Cout and
+ * channels >= Cin are zero. pre_scale multiplies styles first (ToRGB's 1/sqrt(fan_in), :355). */
+int p3d_modulate_weights(const float* weight, const float* styles, int B, int Cout, int Cin, int ktaps,
+                         int Cout_padded, int Cin_padded, int demodulate, float pre_scale, float out_scale,
+                         int planes, void* out, p3d_stream_t stream);
+
+/* Layout / precision converters between the reference's NCHW tensors and the NHWC fp16 tensors of this path. */
+int p3d_nchw_to_nhwc_f16(const void* x, int src_dtype, int N, int C, int H, int W, int C_padded, int planes,
+                         void* out, p3d_stream_t stream);
+int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, float* out,
+                         p3d_stream_t stream);
+
+/* 4x4 FIR (upfirdn2d up=down=1) + noise + bias + lrelu + gain + clamp on NHWC tensors: the tail of an up=2
+ * SynthesisLayer (networks_stylegan2.py:324-331 after conv2d_resample.py:128). in_dtype: P3D_F32 or P3D_F16;
+ * out_planes 1 (fp16) or 2 (fp16 hi/lo). x [B,inH,inW,C] -> y [out_planes][B,outH,outW,C]. */
+int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
+                     int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                     float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
+
+/* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */
+int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,25 +49,39 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', 'nvcc')
     objs = []
     procs = []
+    hdr = hashlib.sha256()
+    for root in (CSRC, os.path.join(HERE, '..', 'include')):
+        for f in sorted(os.listdir(root)):
+            if f.endswith(('.cuh', '.h')):
+                with open(os.path.join(root, f), 'rb') as fh:
+                    hdr.update(fh.read())
+    hdr.update(' '.join(NVCC_FLAGS).encode())
     for src in sources():
         obj = src[:-3] + '.o'
         objs.append(obj)
+        with open(src, 'rb') as fh:
+            src_digest = hashlib.sha256(hdr.digest() + fh.read()).hexdigest()
+        tag = obj + '.sha'
+        if not force and os.path.exists(obj) and os.path.exists(tag) and open(tag).read().strip() == src_digest:
+            continue       # object is up to date (per-file incremental build)
         cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), tag, src_digest))
     log = []
-    for src, p in procs:
+    for src, p, tag, src_digest in procs:
         out, _ = p.communicate()
         log.append(out)
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError(f'nvcc failed for {src}')
-    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUT] + objs + ['-lcuda']
+        with open(tag, 'w') as fh:
+            fh.write(src_digest)
+        with open(src[:-3] + '.ptxas.log', 'w') as fh:
+            fh.write(out)
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', OUT] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError('link failed')
-    with open(os.path.join(CSRC, '.ptxas.log'), 'w') as fh:
-        fh.write('\n'.join(log))
     with open(STAMP, 'w') as fh:
         fh.write(digest)
     if verbose:

@@ -1,0 +1,166 @@
+"""Tensor-level wrappers of the tensor-core convolution path (include/p3d.h: p3d_conv_gemm and helpers).
+
+Tensors on this path are NHWC fp16; a *split* tensor is `[2,B,H,W,C]` (hi, lo) with value hi + lo.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+c_int8 = ctypes.c_int8
+
+WEIGHT_SCALE = 128.0   # power of two folded into the fp16 weights so that the `lo` halves stay normal numbers
+
+
+class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
+    _fields_ = [
+        ('x', ctypes.c_void_p), ('w', ctypes.c_void_p),
+        ('x_planes', ctypes.c_int32), ('w_planes', ctypes.c_int32), ('B', ctypes.c_int32), ('Bw', ctypes.c_int32),
+        ('H', ctypes.c_int32), ('W', ctypes.c_int32), ('C', ctypes.c_int32), ('Cout', ctypes.c_int32),
+        ('Cout_padded', ctypes.c_int32), ('n_kblocks', ctypes.c_int32), ('n_taps', ctypes.c_int32),
+        ('tap_dy', c_int8 * 9), ('tap_dx', c_int8 * 9), ('tap_k', c_int8 * 9),
+        ('split', ctypes.c_int32), ('gH', ctypes.c_int32), ('gW', ctypes.c_int32),
+        ('oH', ctypes.c_int32), ('oW', ctypes.c_int32), ('sy', ctypes.c_int32), ('oy', ctypes.c_int32),
+        ('sx', ctypes.c_int32), ('ox', ctypes.c_int32),
+        ('y', ctypes.c_void_p), ('y_lo', ctypes.c_void_p),
+        ('y_cstride', ctypes.c_int32), ('y_coff', ctypes.c_int32), ('out_mode', ctypes.c_int32),
+        ('bias', ctypes.c_void_p), ('noise', ctypes.c_void_p), ('dscale', ctypes.c_void_p),
+        ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
+        ('acc_scale', ctypes.c_float),
+    ]
+
+
+def pad_to(n, m):
+    return (n + m - 1) // m * m
+
+
+def to_nhwc_f16(x, c_padded=None, planes=1):
+    """NCHW fp32/fp16 -> [planes,N,H,W,Cp] fp16."""
+    assert x.is_cuda and x.ndim == 4
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    cp = c_padded or c
+    out = torch.empty(planes, n, h, w, cp, device=x.device, dtype=torch.float16)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().p3d_nchw_to_nhwc_f16(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], n, c, h, w, cp, planes, _lib.ptr(out),
+                                             _lib.stream_ptr())
+    _lib.check(st, 'p3d_nchw_to_nhwc_f16')
+    _lib.bump()
+    return out
+
+
+def nhwc_to_nchw_f32(x, channels=None, c_offset=0):
+    """[N,H,W,Cs] fp32 -> [N,channels,H,W] fp32 taking channels [c_offset, c_offset+channels)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.ndim == 4 and x.is_contiguous()
+    n, h, w, cs = x.shape
+    c = channels or cs
+    out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().p3d_nhwc_to_nchw_f32(_lib.ptr(x), n, c, h, w, cs, c_offset, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(st, 'p3d_nhwc_to_nchw_f32')
+    _lib.bump()
+    return out
+
+
+def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, cin_padded=None, out_scale=WEIGHT_SCALE):
+    """weight [O,I,kh,kw] fp32, styles [B,I] fp32 -> [planes,B,Op,kh*kw*Ip] fp16, K-major (tap-major, then channel)."""
+    w = weight.detach().float().contiguous()
+    s = styles.detach().float().contiguous()
+    o, i, kh, kw = w.shape
+    b = s.shape[0]
+    op, ip = pad_to(o, 16), (cin_padded or pad_to(i, 64))
+    out = torch.empty(planes, b, op, kh * kw * ip, device=w.device, dtype=torch.float16)
+    with torch.cuda.device(w.device):
+        st = _lib.lib().p3d_modulate_weights(_lib.ptr(w), _lib.ptr(s), b, o, i, kh * kw, op, ip, 1 if demodulate else 0,
+                                             float(pre_scale), float(out_scale), planes, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(st, 'p3d_modulate_weights')
+    _lib.bump()
+    return out
+
+
+def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
+              noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE):
+    """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;
+    out: NHWC tensor [B,oH,oW,Cs] (fp16 or fp32); out_map = (sy, oy, sx, ox)."""
+    xp, b, h, wd, c = x.shape
+    wp, bw, op, kk = w.shape
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.is_contiguous() and w.is_contiguous()
+    assert kk % c == 0
+    a = ConvArgs()
+    a.x, a.w = x.data_ptr(), w.data_ptr()
+    a.x_planes, a.w_planes, a.B, a.Bw, a.H, a.W, a.C = xp, wp, b, bw, h, wd, c
+    a.Cout, a.Cout_padded, a.n_kblocks, a.n_taps = cout, op, kk // c, len(taps)
+    for i, (dy, dx, kb) in enumerate(taps):
+        a.tap_dy[i], a.tap_dx[i], a.tap_k[i] = dy, dx, kb
+    a.split = 1 if split else 0
+    a.gH, a.gW = grid_hw
+    ob, oh, ow, ocs = out.shape
+    assert ob == b and out.is_contiguous()
+    a.oH, a.oW = oh, ow
+    a.sy, a.oy, a.sx, a.ox = out_map
+    a.y = out.data_ptr()
+    a.y_lo = None if out_lo is None else out_lo.data_ptr()
+    a.y_cstride, a.y_coff, a.out_mode = ocs, y_coff, out_mode
+    if out_mode in (0, 1):
+        assert out.dtype == torch.float16
+    else:
+        assert out.dtype == torch.float32
+    a.bias = None if bias is None else bias.data_ptr()
+    a.noise = None if noise is None else noise.data_ptr()
+    a.dscale = None if dscale is None else dscale.data_ptr()
+    for t in (bias, noise, dscale):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    a.act, a.alpha, a.gain, a.clamp, a.acc_scale = act, alpha, gain, clamp, acc_scale
+    with torch.cuda.device(x.device):
+        st = _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr())
+    _lib.check(st, 'p3d_conv_gemm')
+    _lib.bump()
+    return out
+
+
+TAPS_3X3 = [(ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+TAPS_1X1 = [(0, 0, 0)]
+
+
+def tconv_phase_taps(py, px):
+    """Taps of output phase (py, px) of conv_transpose2d(stride=2, k=3): out[2j+py] += x[j - (ky-py)/2] * w[ky]."""
+    kys = (0, 2) if py == 0 else (1,)
+    kxs = (0, 2) if px == 0 else (1,)
+    return [(-(ky - py) // 2, -(kx - px) // 2, ky * 3 + kx) for ky in kys for kx in kxs]
+
+
+def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SCALE):
+    """Stride-2 transposed 3x3 convolution as four phase GEMMs: x [xp,B,h,w,C] -> out [B,2h+1,2w+1,Cs] (pre-FIR)."""
+    _, b, h, wd, c = x.shape
+    for py in (0, 1):
+        for px in (0, 1):
+            gh = h + 1 if py == 0 else h
+            gw = wd + 1 if px == 0 else wd
+            conv_gemm(x, w, cout, tconv_phase_taps(py, px), (gh, gw), out, out_mode=2 if out.dtype == torch.float32 else 0,
+                      out_map=(2, py, 2, px), split=split, acc_scale=acc_scale)
+    return out
+
+
+def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):
+    """x [B,inH,inW,C] fp32/fp16 NHWC -> [out_planes,B,outH,outW,C] fp16."""
+    b, ih, iw, c = x.shape
+    oh, ow = out_hw
+    y = torch.empty(out_planes, b, oh, ow, c, device=x.device, dtype=torch.float16)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().p3d_fir_act_nhwc(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias),
+                                         _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha,
+                                         act_gain, clamp, _lib.stream_ptr())
+    _lib.check(st, 'p3d_fir_act_nhwc')
+    _lib.bump()
+    return y
+
+
+def upsample2x_nhwc(x, f):
+    b, h, w, c = x.shape
+    y = torch.empty(b, 2 * h, 2 * w, c, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().p3d_upsample2x_nhwc(_lib.ptr(x), _lib.ptr(f), _lib.ptr(y), b, h, w, c, _lib.stream_ptr())
+    _lib.check(st, 'p3d_upsample2x_nhwc')
+    _lib.bump()
+    return y

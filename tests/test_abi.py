@@ -40,15 +40,17 @@ def test_struct_layouts_match_header_sizes():
     import subprocess
     import tempfile
     from pix2pix3d_b200 import _lib
-    prog = '#include <stdio.h>\n#include "p3d.h"\nint main(){printf("%zu %zu\\n", sizeof(p3d_decoder_t), sizeof(p3d_render_args_t));return 0;}\n'
+    prog = '#include <stdio.h>\n#include "p3d.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(p3d_decoder_t), sizeof(p3d_render_args_t), sizeof(p3d_conv_args_t));return 0;}\n'
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, 't.c')
         open(c, 'w').write(prog)
         exe = os.path.join(td, 't')
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
-        a, b = (int(v) for v in subprocess.check_output([exe]).split())
+        a, b, c = (int(v) for v in subprocess.check_output([exe]).split())
+    from pix2pix3d_b200 import tcconv
     assert ctypes.sizeof(_lib.DecoderDesc) == a
     assert ctypes.sizeof(_lib.RenderArgs) == b
+    assert ctypes.sizeof(tcconv.ConvArgs) == c
 
 
 def test_cuda_ops_fail_loudly_without_library(monkeypatch):

@@ -1,0 +1,194 @@
+"""Tensor-core convolution path (p3d_conv_gemm + helpers) against float64 torch references."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _h(x):   # value after fp16 rounding, as float64
+    return x.half().double()
+
+
+def _weights_kmajor(w, planes=1, scale=1.0):
+    """[O,I,kh,kw] fp32 -> [planes,1,Op,kh*kw*Ip] fp16 K-major (tap-major) without modulation."""
+    from pix2pix3d_b200 import tcconv
+    o, i, kh, kw = w.shape
+    ones = torch.ones(1, i, device=w.device)
+    return tcconv.modulate_weights(w, ones, demodulate=False, planes=planes, out_scale=scale)
+
+
+@pytest.mark.parametrize('shape', [(1, 64, 8, 16, 32), (2, 128, 5, 7, 48), (1, 64, 16, 16, 130), (3, 192, 4, 4, 16)])
+def test_gemm_as_1x1_conv(shape):
+    from pix2pix3d_b200 import tcconv
+    b, c, h, w, cout = shape
+    torch.manual_seed(0)
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 1, 1, device='cuda') / np.sqrt(c)
+    xn = tcconv.to_nhwc_f16(x)
+    wk = _weights_kmajor(wt)
+    out = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float32)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_1X1, (h, w), out, out_mode=2, acc_scale=1.0)
+    ref = F.conv2d(_h(x).cpu(), _h(wt).cpu())
+    assert rel_err(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize('shape', [(2, 64, 16, 16, 64), (1, 128, 9, 13, 32), (1, 64, 32, 32, 256), (2, 64, 4, 4, 16)])
+def test_conv3x3_single_pass(shape):
+    from pix2pix3d_b200 import tcconv
+    b, c, h, w, cout = shape
+    torch.manual_seed(1)
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    xn = tcconv.to_nhwc_f16(x)
+    wk = _weights_kmajor(wt, scale=tcconv.WEIGHT_SCALE)
+    out = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float32)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), out, out_mode=2)
+    ref = F.conv2d(_h(x).cpu(), _h(wt * tcconv.WEIGHT_SCALE).cpu() / tcconv.WEIGHT_SCALE, padding=1)
+    assert rel_err(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-6
+
+
+def test_conv3x3_split_three_pass_is_fp32_accurate():
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(2)
+    b, c, h, w, cout = 2, 128, 16, 16, 96
+    x = torch.randn(b, c, h, w, device='cuda') * 3
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    xn = tcconv.to_nhwc_f16(x, planes=2)
+    assert rel_err((xn[0].float() + xn[1].float()).permute(0, 3, 1, 2).cpu().numpy(), x.cpu().numpy()) < 1e-6
+    wk = _weights_kmajor(wt, planes=2, scale=tcconv.WEIGHT_SCALE)
+    out = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float32)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), out, out_mode=2, split=True)
+    ref = F.conv2d(x.double().cpu(), wt.double().cpu(), padding=1)
+    assert rel_err(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-6      # fp32-level, not fp16-level
+    single = torch.zeros_like(out)
+    tcconv.conv_gemm(xn[:1].contiguous(), wk[:1].contiguous(), cout, tcconv.TAPS_3X3, (h, w), single, out_mode=2)
+    assert rel_err(single.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) > 1e-5    # the one-pass result is visibly coarser
+
+
+@pytest.mark.parametrize('hw', [(4, 4), (8, 8), (7, 5), (16, 16), (33, 33)])
+def test_transposed_conv_phases(hw):
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(3)
+    b, c, cout = 2, 64, 48
+    h, w = hw
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    xn = tcconv.to_nhwc_f16(x)
+    wk = _weights_kmajor(wt, scale=tcconv.WEIGHT_SCALE)
+    out = torch.full((b, 2 * h + 1, 2 * w + 1, cout), float('nan'), device='cuda', dtype=torch.float32)
+    tcconv.conv_transpose3x3_s2(xn, wk, cout, out)
+    assert torch.isfinite(out).all(), 'every output pixel must be written by exactly one phase'
+    ref = F.conv_transpose2d(_h(x).cpu(), (_h(wt * tcconv.WEIGHT_SCALE).cpu() / tcconv.WEIGHT_SCALE).transpose(0, 1), stride=2)
+    assert rel_err(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-6
+
+
+def test_epilogue_noise_bias_lrelu_clamp_and_output_modes():
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(4)
+    b, c, h, w, cout = 2, 64, 12, 12, 40
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    bias = torch.randn(cout, device='cuda')
+    noise = torch.randn(h, w, device='cuda') * 0.5
+    dscale = torch.rand(b, cout, device='cuda') + 0.5
+    xn = tcconv.to_nhwc_f16(x)
+    wk = _weights_kmajor(wt, scale=tcconv.WEIGHT_SCALE)
+    ref = F.conv2d(_h(x).cpu(), _h(wt * tcconv.WEIGHT_SCALE).cpu() / tcconv.WEIGHT_SCALE, padding=1)
+    ref = ref * dscale.double().cpu()[:, :, None, None] + noise.double().cpu() + bias.double().cpu()[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) * np.sqrt(2)
+    ref = ref.clamp(-1.5, 1.5)
+    kw = dict(bias=bias, noise=noise, dscale=dscale, act=3, alpha=0.2, gain=float(np.sqrt(2)), clamp=1.5)
+    o32 = torch.zeros(b, h, w, cout, device='cuda')
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), o32, out_mode=2, **kw)
+    assert rel_err(o32.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 3e-6
+    # fp16 and split outputs, written at a channel offset inside a wider tensor
+    wide = torch.zeros(b, h, w, 64, device='cuda', dtype=torch.float16)
+    wide_lo = torch.zeros_like(wide)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), wide, out_lo=wide_lo, out_mode=1, y_coff=8, **kw)
+    assert (wide[..., :8] == 0).all() and (wide[..., 48:] == 0).all()
+    got = (wide.float() + wide_lo.float())[..., 8:48].permute(0, 3, 1, 2)
+    assert rel_err(got.cpu().numpy(), ref.numpy()) < 3e-6
+    assert rel_err(wide[..., 8:48].float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 1e-3
+    # accumulate mode
+    acc = torch.ones(b, h, w, cout, device='cuda')
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), acc, out_mode=3, **kw)
+    assert rel_err((acc - 1).permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 3e-6
+
+
+def test_modulate_weights_matches_modulated_conv2d_formula():
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(5)
+    b, o, i = 3, 40, 100
+    wt = torch.randn(o, i, 3, 3, device='cuda')
+    st = torch.randn(b, i, device='cuda') + 1
+    for demod in (True, False):
+        wk = tcconv.modulate_weights(wt, st, demodulate=demod, pre_scale=0.7, planes=2, out_scale=4.0)
+        assert wk.shape == (2, b, 48, 9 * 128)
+        w = wt.double()[None] * (st.double() * 0.7)[:, None, :, None, None]
+        if demod:
+            w = w * (w.square().sum(dim=[2, 3, 4], keepdim=True) + 1e-8).rsqrt()
+        ref = torch.zeros(b, 48, 9, 128, dtype=torch.float64, device='cuda')
+        ref[:, :o, :, :i] = (w * 4.0).permute(0, 1, 3, 4, 2).reshape(b, o, 9, i)
+        got = (wk[0].double() + wk[1].double()).reshape(b, 48, 9, 128)
+        assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+
+
+def test_layout_converters_roundtrip():
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(6)
+    x = torch.randn(2, 37, 9, 11, device='cuda')
+    n = tcconv.to_nhwc_f16(x, c_padded=64, planes=2)
+    assert n.shape == (2, 2, 9, 11, 64) and (n[..., 37:] == 0).all()
+    back = (n[0].float() + n[1].float())[..., :37].permute(0, 3, 1, 2)
+    assert rel_err(back.cpu().numpy(), x.cpu().numpy()) < 1e-6
+    img = torch.randn(2, 9, 11, 96, device='cuda')
+    p = tcconv.nhwc_to_nchw_f32(img, channels=32, c_offset=32)
+    assert torch.equal(p, img[..., 32:64].permute(0, 3, 1, 2).contiguous())
+
+
+def test_fir_act_nhwc_and_upsample_match_reference_ops():
+    from pix2pix3d_b200 import tcconv
+    from pix2pix3d_b200.torch_utils.ops import bias_act, upfirdn2d
+    torch.manual_seed(7)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    b, c, h = 2, 64, 9
+    x = torch.randn(b, c, 2 * h + 1, 2 * h + 1, device='cuda')
+    noise = torch.randn(2 * h, 2 * h, device='cuda') * 0.3
+    bias = torch.randn(c, device='cuda')
+    ref = upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)
+    ref = bias_act.bias_act(ref + noise, bias, act='lrelu', gain=1.3, clamp=2.0)
+    y = tcconv.fir_act_nhwc(x.permute(0, 2, 3, 1).contiguous(), f, noise, bias, 2, (2 * h, 2 * h), act_gain=1.3 * float(np.sqrt(2)) / float(np.sqrt(2)) * float(np.sqrt(2)),
+                            clamp=2.0)
+    got = (y[0].float() + y[1].float()).permute(0, 3, 1, 2)
+    ref2 = bias_act.bias_act(upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4) + noise, bias, act='lrelu', gain=1.3 * float(np.sqrt(2)), clamp=2.0)
+    assert rel_err(got.cpu().numpy(), ref2.cpu().numpy()) < 2e-6
+    xh = x.half()
+    yh = tcconv.fir_act_nhwc(xh.permute(0, 2, 3, 1).contiguous(), f, noise, bias.float(), 1, (2 * h, 2 * h), act_gain=float(np.sqrt(2)), clamp=256.0)
+    refh = bias_act.bias_act(upfirdn2d.upfirdn2d(xh, f, padding=[1, 1, 1, 1], gain=4).add_(noise), bias.half(), act='lrelu', clamp=256)
+    assert rel_err(yh[0].float().permute(0, 3, 1, 2).cpu().numpy(), refh.float().cpu().numpy()) < 2e-3
+    img = torch.randn(2, 6, 7, 5, device='cuda')
+    up = tcconv.upsample2x_nhwc(img.permute(0, 2, 3, 1).contiguous(), f)
+    assert rel_err(up.permute(0, 3, 1, 2).cpu().numpy(), upfirdn2d.upsample2d(img, f).cpu().numpy()) < 2e-6
+
+
+def test_conv_large_tile_counts_and_fp16_output():
+    """SR-sized layer slice: 128 channels at 128^2, many tiles per launch; fp16 NHWC output."""
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(8)
+    b, c, h, w, cout = 1, 128, 128, 128, 128
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    st = torch.randn(b, c, device='cuda') + 1
+    xn = tcconv.to_nhwc_f16(x)
+    wk = tcconv.modulate_weights(wt, st, demodulate=True)
+    out = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float16)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), out, out_mode=0)
+    wm = wt[None] * st[:, None, :, None, None]
+    wm = wm * (wm.square().sum(dim=[2, 3, 4], keepdim=True) + 1e-8).rsqrt()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.half().float(), wm[0], padding=1)
+    assert rel_err(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.cpu().numpy()) < 2e-3
