@@ -197,10 +197,11 @@ int p3d_conv_gemm(const p3d_conv_args_t* args, p3d_stream_t stream);
 /* Per-sample modulated (and optionally demodulated) weights, modulated_conv2d lines :58-67:
  *   w'[b,o,i,k] = weight[o,i,k] * styles[b,i];  d[b,o] = rsqrt(sum_{i,k} w'^2 + 1e-8);  out = w' * d * scale
  * written K-major [planes][B][Cout_padded][kh*kw][Cin_padded] as fp16 (planes = 2: hi/lo split). Rows >= Cout and
- * channels >= Cin are zero. pre_scale multiplies styles first (ToRGB's 1/sqrt(fan_in), :355). */
+ * channels outside [cin_offset, cin_offset+Cin) are zero (cin_offset lets a layer read a channel slice of a wider
+ * activation tensor). pre_scale multiplies styles first (ToRGB's 1/sqrt(fan_in), :355). */
 int p3d_modulate_weights(const float* weight, const float* styles, int B, int Cout, int Cin, int ktaps,
-                         int Cout_padded, int Cin_padded, int demodulate, float pre_scale, float out_scale,
-                         int planes, void* out, p3d_stream_t stream);
+                         int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
+                         float out_scale, int planes, void* out, p3d_stream_t stream);
 
 /* Layout / precision converters between the reference's NCHW tensors and the NHWC fp16 tensors of this path. */
 int p3d_nchw_to_nhwc_f16(const void* x, int src_dtype, int N, int C, int H, int W, int C_padded, int planes,

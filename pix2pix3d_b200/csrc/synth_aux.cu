@@ -14,7 +14,7 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
 // modulated_conv2d weight preparation (networks_stylegan2.py:58-67)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) modulate_weights_kernel(const float* __restrict__ weight, const float* __restrict__ styles,
-                                                               int Cout, int Cin, int ktaps, int Cout_p, int Cin_p, int demod,
+                                                               int Cout, int Cin, int ktaps, int Cout_p, int Cin_p, int cin_off, int demod,
                                                                float pre_scale, float out_scale, int planes, int B,
                                                                __half* __restrict__ out) {
     const int o = blockIdx.x, b = blockIdx.y;
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(256) modulate_weights_kernel(const float* __re
     }
     const float d = demod ? dcoef : 1.f;
     for (int idx = threadIdx.x; idx < ktaps * Cin_p; idx += blockDim.x) {
-        const int t = idx / Cin_p, i = idx % Cin_p;
+        const int t = idx / Cin_p, i = idx % Cin_p - cin_off;
         float v = 0.f;
-        if (i < Cin) v = __ldg(w + (size_t)i * ktaps + t) * (__ldg(s + i) * pre_scale) * d * out_scale;
+        if (i >= 0 && i < Cin) v = __ldg(w + (size_t)i * ktaps + t) * (__ldg(s + i) * pre_scale) * d * out_scale;
         __half hi, lo;
         split_half(v, hi, lo);
         out[row + idx] = hi;
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
         }
         const float nz = noise ? __ldg(noise + (size_t)oy * outW + ox) : 0.f;
         const size_t o = (((size_t)b * outH + oy) * outW + ox) * C + c;
+        __align__(16) __half hv[VEC], lv[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
             float v = acc[k] * fir_gain;
@@ -173,10 +174,14 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
             if (act == 3) v = v > 0.f ? v : v * alpha;
             v *= act_gain;
             if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
-            __half hi, lo;
-            split_half(v, hi, lo);
-            y[o + k] = hi;
-            if (out_planes == 2) y[out_plane_stride + o + k] = lo;
+            split_half(v, hv[k], lv[k]);
+        }
+        if (VEC == 8) {
+            *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
+            if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
+        } else {
+            *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
+            if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
         }
     }
 }
@@ -220,13 +225,13 @@ static unsigned grid1d(int64_t items, int block) {
 using namespace p3d;
 
 extern "C" int p3d_modulate_weights(const float* weight, const float* styles, int B, int Cout, int Cin, int ktaps,
-                                    int Cout_padded, int Cin_padded, int demodulate, float pre_scale, float out_scale,
-                                    int planes, void* out, p3d_stream_t stream) {
+                                    int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
+                                    float out_scale, int planes, void* out, p3d_stream_t stream) {
     if (!weight || !styles || !out || B <= 0 || Cout <= 0 || Cin <= 0 || ktaps <= 0) return P3D_BAD_ARG;
-    if (Cout_padded < Cout || Cin_padded < Cin || planes < 1 || planes > 2 || B > 65535) return P3D_BAD_ARG;
+    if (Cout_padded < Cout || cin_offset < 0 || Cin_padded < Cin + cin_offset || planes < 1 || planes > 2 || B > 65535) return P3D_BAD_ARG;
     dim3 grid(Cout_padded, B);
     modulate_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, styles, Cout, Cin, ktaps, Cout_padded, Cin_padded,
-                                                                    demodulate, pre_scale, out_scale, planes, B, (__half*)out);
+                                                                    cin_offset, demodulate, pre_scale, out_scale, planes, B, (__half*)out);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

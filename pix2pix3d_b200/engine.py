@@ -1,0 +1,263 @@
+"""Inference engine for the StyleGAN2 synthesis / super-resolution blocks on the tensor-core path.
+
+Executes `SynthesisBlock` / `SynthesisBlockNoUp` stacks (reference training/networks_stylegan2.py:419-463,
+training/superresolution.py:244-289) with NHWC fp16 activations: per-sample modulated weights
+(`p3d_modulate_weights`), tcgen05 implicit-GEMM convolutions (`p3d_conv_gemm`) with noise/bias/lrelu/clamp in the
+epilogue, the four-phase stride-2 transposed convolution followed by one fused FIR+noise+bias+lrelu pass for up=2
+layers, and ToRGB accumulated straight into the upsampled fp32 skip image.
+
+fp32 blocks (the tri-plane backbone, or any block under force_fp32) run on hi/lo split fp16 tensors with three
+tensor-core passes (fp32-level accuracy); fp16 blocks run single pass, rounding where the reference rounds.
+The module classes call into this when the inputs are CUDA tensors, no gradient is required and the noise mode is
+'const' or 'none'; every other case keeps the generic op-by-op formulation.
+"""
+import numpy as np
+import torch
+
+from . import tcconv
+
+_SQRT2 = float(np.sqrt(2))
+
+# set False to force the generic op-by-op formulation (A/B checks in tests)
+enabled = True
+
+
+def block_supported(block, ws, noise_mode, need_grad):
+    if not enabled or ws.device.type != 'cuda' or need_grad:
+        return False
+    if noise_mode not in ('const', 'none'):
+        return False
+    if block.architecture != 'skip':
+        return False
+    for name in ('conv0', 'conv1'):
+        layer = getattr(block, name, None)
+        if layer is not None and (layer.activation != 'lrelu' or layer.weight.shape[-1] != 3):
+            return False
+    return hasattr(block, 'torgb')
+
+
+def grad_needed(*modules_and_tensors):
+    if not torch.is_grad_enabled():
+        return False
+    for m in modules_and_tensors:
+        if isinstance(m, torch.nn.Module):
+            if any(p.requires_grad for p in m.parameters()):
+                return True
+        elif isinstance(m, torch.Tensor) and m.requires_grad:
+            return True
+    return False
+
+
+def _pad_vec(v, n):
+    v = v.detach().float()
+    if v.numel() == n:
+        return v.contiguous()
+    out = torch.zeros(n, device=v.device, dtype=torch.float32)
+    out[:v.numel()] = v
+    return out
+
+
+def _noise(layer, noise_mode):
+    if noise_mode == 'const' and layer.use_noise:
+        return (layer.noise_const * layer.noise_strength).detach().float().contiguous()
+    return None
+
+
+def _alloc(planes, b, h, w, c, cp, device):
+    shape = (planes, b, h, w, cp)
+    return torch.zeros(shape, device=device, dtype=torch.float16) if cp != c else torch.empty(shape, device=device, dtype=torch.float16)
+
+
+def synthesis_layer(layer, x, w_lat, noise_mode, split, gain=1.0, cin_offset=0):
+    """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]."""
+    planes = 2 if split else 1
+    styles = layer.affine(w_lat.float())
+    b = styles.shape[0]
+    cin_p = x.shape[-1]
+    cout = layer.out_channels
+    cout_p = tcconv.pad_to(cout, 64)
+    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset)
+    noise = _noise(layer, noise_mode)
+    bias = _pad_vec(layer.bias, cout_p)
+    act_gain = layer.act_gain * gain
+    clamp = float(layer.conv_clamp * gain) if layer.conv_clamp is not None else -1.0
+    dev = x.device
+    if layer.up == 1:
+        h, w = x.shape[2], x.shape[3]
+        y = _alloc(planes, b, h, w, cout, cout_p, dev)
+        tcconv.conv_gemm(x, wk, cout, tcconv.TAPS_3X3, (h, w), y[0], out_lo=(y[1] if split else None), out_mode=1 if split else 0,
+                         split=split, bias=bias, noise=noise, act=3, alpha=0.2, gain=act_gain, clamp=clamp)
+        return y
+    assert layer.up == 2
+    h, w = x.shape[2], x.shape[3]
+    tmp_dtype = torch.float32 if split else torch.float16
+    if cout_p != cout:
+        tmp = torch.zeros(b, 2 * h + 1, 2 * w + 1, cout_p, device=dev, dtype=tmp_dtype)
+    else:
+        tmp = torch.empty(b, 2 * h + 1, 2 * w + 1, cout_p, device=dev, dtype=tmp_dtype)
+    tcconv.conv_transpose3x3_s2(x, wk, cout, tmp, split=split)
+    return tcconv.fir_act_nhwc(tmp, layer.resample_filter, noise, bias, planes, (2 * h, 2 * w), pad0=(1, 1), fir_gain=4.0, act=3,
+                               alpha=0.2, act_gain=act_gain, clamp=clamp)
+
+
+def torgb_layer(layer, x, w_lat, img, split):
+    """ToRGBLayer.forward (:354-359) accumulated into the fp32 NHWC skip image (or creating it)."""
+    planes = 2 if split else 1
+    styles = layer.affine(w_lat.float())
+    b = styles.shape[0]
+    cout = layer.out_channels
+    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes,
+                                 cin_padded=x.shape[-1])
+    h, w = x.shape[2], x.shape[3]
+    bias = layer.bias.detach().float().contiguous()
+    clamp = float(layer.conv_clamp) if layer.conv_clamp is not None else -1.0
+    if img is None:
+        img = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float32)
+        mode = 2
+    else:
+        mode = 3
+    if not split:
+        # fp16 blocks: the reference rounds the ToRGB output to fp16 before the fp32 skip add (:455-457)
+        y16 = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float16)
+        tcconv.conv_gemm(x, wk, cout, tcconv.TAPS_1X1, (h, w), y16, out_mode=0, bias=bias, act=1, gain=1.0, clamp=clamp)
+        if mode == 2:
+            img.copy_(y16)
+        else:
+            img.add_(y16)
+        return img
+    tcconv.conv_gemm(x, wk, cout, tcconv.TAPS_1X1, (h, w), img, out_mode=mode, split=True, bias=bias, act=1, gain=1.0, clamp=clamp)
+    return img
+
+
+def synthesis_block(block, x, img, ws, noise_mode='const', force_fp32=False, upsample=True, cin_offset=0):
+    """One block on NHWC tensors. x: [planes,B,h,w,Cp] fp16 or None (first block); img: [B,h,w,Ci] fp32 or None.
+    Returns (x, img) in the same representation. The precision of x switches at block boundaries as
+    `x.to(dtype)` does in the reference (:438)."""
+    split = not (block.use_fp16 and not force_fp32)
+    planes = 2 if split else 1
+    w_iter = iter(ws.unbind(dim=1))
+    b = ws.shape[0]
+    if block.in_channels == 0:
+        c = block.const.shape[0]
+        x = tcconv.to_nhwc_f16(block.const.detach().float().unsqueeze(0).expand(b, -1, -1, -1).contiguous(),
+                               c_padded=tcconv.pad_to(c, 64), planes=planes)
+        x = synthesis_layer(block.conv1, x, next(w_iter), noise_mode, split)
+    else:
+        if x.shape[0] != planes:   # precision change between blocks
+            x = x[:1].contiguous() if planes == 1 else torch.stack([x[0], torch.zeros_like(x[0])])
+        x = synthesis_layer(block.conv0, x, next(w_iter), noise_mode, split, cin_offset=cin_offset)
+        x = synthesis_layer(block.conv1, x, next(w_iter), noise_mode, split)
+    if upsample and img is not None:
+        img = tcconv.upsample2x_nhwc(img, block.resample_filter)
+    img = torgb_layer(block.torgb, x, next(w_iter), img, split)
+    return x, img
+
+
+def synthesis_network(net, ws, noise_mode='const', force_fp32=False):
+    """SynthesisNetwork.forward (:505-520) -> fp32 NHWC image [B,R,R,img_channels]."""
+    ws = ws.to(torch.float32)
+    x = img = None
+    w_idx = 0
+    for res in net.block_resolutions:
+        block = getattr(net, f'b{res}')
+        cur = ws.narrow(1, w_idx, block.num_conv + block.num_torgb)
+        w_idx += block.num_conv
+        x, img = synthesis_block(block, x, img, cur, noise_mode=noise_mode, force_fp32=force_fp32)
+    return img
+
+
+def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=False):
+    """Superresolution*.forward (superresolution.py:48-57) with the feature image as NCHW fp32 and the low-res image as
+    fp32 NHWC; returns the fp32 NHWC output image."""
+    ws = ws[:, -1:, :].repeat(1, 3, 1).to(torch.float32)
+    split0 = not (sr.block0.use_fp16 and not force_fp32)
+    x = tcconv.to_nhwc_f16(feat_nchw, c_padded=tcconv.pad_to(feat_nchw.shape[1], 64), planes=2 if split0 else 1)
+    up0 = sr.block0.conv0.up == 2
+    x, img = synthesis_block(sr.block0, x, rgb_nhwc, ws, noise_mode=noise_mode, force_fp32=force_fp32, upsample=up0)
+    x, img = synthesis_block(sr.block1, x, img, ws, noise_mode=noise_mode, force_fp32=force_fp32, upsample=True)
+    return img
+
+
+# ----------------------------------------------------------------------------------------------
+# whole-generator fast path
+# ----------------------------------------------------------------------------------------------
+def _sr_supported(sr, ws, noise_mode, feat_res):
+    return (hasattr(sr, 'block0') and hasattr(sr, 'block1') and feat_res == sr.input_resolution
+            and block_supported(sr.block0, ws, noise_mode, False) and block_supported(sr.block1, ws, noise_mode, False))
+
+
+def generator_supported(gen, ws, c, synthesis_kwargs, use_cached_backbone):
+    """Can `TriPlane*Generator.synthesis` run end to end on the tensor-core / fused-render path?"""
+    if ws.device.type != 'cuda' or grad_needed(gen, ws, c):
+        return False
+    extra = set(synthesis_kwargs) - {'noise_mode', 'force_fp32', 'fused_modconv'}
+    if extra:
+        return False
+    noise_mode = synthesis_kwargs.get('noise_mode', 'random')
+    net = gen.backbone.synthesis
+    if net.img_channels != 96:
+        return False
+    if not all(block_supported(getattr(net, f'b{r}'), ws, noise_mode, False) for r in net.block_resolutions):
+        return False
+    gen.renderer.plane_axes = gen.renderer.plane_axes.to(ws.device)
+    if not gen.renderer.fusable_options(gen.decoder, gen.rendering_kwargs):
+        return False
+    if gen.rendering_kwargs['ray_start'] == 'auto':
+        return False
+    sr_noise = gen.rendering_kwargs['superresolution_noise_mode']
+    nrr = gen.neural_rendering_resolution
+    srs = [gen.superresolution] + ([gen.superresolution_semantic] if hasattr(gen, 'superresolution_semantic') else [])
+    return all(_sr_supported(sr, ws, sr_noise, nrr) for sr in srs)
+
+
+def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=False, noise_mode='random', force_fp32=False):
+    """TriPlaneGenerator / TriPlaneSemanticEntangleGenerator.synthesis (triplane_cond.py:661-697, 1020-1061) without
+    leaving the NHWC representation between the backbone, the fused renderer and the super-resolution stacks."""
+    from . import native
+    nrr = gen.neural_rendering_resolution
+    b = ws.shape[0]
+    cam2world = c[:, :16].view(-1, 4, 4)
+    intrinsics = c[:, 16:25].view(-1, 3, 3)
+    ray_origins, ray_directions = gen.ray_sampler(cam2world, intrinsics, nrr)
+    if use_cached_backbone and gen._last_planes is not None:
+        planes_nchw = gen._last_planes
+        planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
+    else:
+        img = synthesis_network(gen.backbone.synthesis, ws, noise_mode=noise_mode, force_fp32=force_fp32)   # [B,H,W,96]
+        h, w = img.shape[1], img.shape[2]
+        planes_cl = img.view(b, h, w, 3, 32).permute(0, 3, 1, 2, 4).contiguous()
+        if cache_backbone:
+            gen._last_planes = tcconv.nhwc_to_nchw_f32(img)
+    feats, depth, wsum = gen.renderer(None, gen.decoder, ray_origins, ray_directions, gen.rendering_kwargs,
+                                      planes_channels_last=planes_cl)
+    nch = feats.shape[-1]
+    fimg = feats.view(b, nrr, nrr, nch)                     # [B,R,C] is already NHWC
+    depth_image = depth.permute(0, 2, 1).reshape(b, 1, nrr, nrr)
+    sr_noise = gen.rendering_kwargs['superresolution_noise_mode']
+    semantic = hasattr(gen, 'superresolution_semantic')
+    half = nch // 2 if semantic else nch
+
+    def run_sr(sr, c_off, n_img):
+        split0 = not (sr.block0.use_fp16 and not force_fp32)
+        if split0:
+            hi = fimg.half()
+            x = torch.stack([hi, (fimg - hi.float()).half()])
+        else:
+            x = fimg.half().unsqueeze(0)
+        if nch % 64:
+            x = torch.nn.functional.pad(x, (0, tcconv.pad_to(nch, 64) - nch))
+        x = x.contiguous()
+        rgb = fimg[..., c_off:c_off + n_img].contiguous()
+        w3 = ws[:, -1:, :].repeat(1, 3, 1).to(torch.float32)
+        up0 = sr.block0.conv0.up == 2
+        x, im = synthesis_block(sr.block0, x, rgb, w3, noise_mode=sr_noise, force_fp32=force_fp32, upsample=up0, cin_offset=c_off)
+        x, im = synthesis_block(sr.block1, x, im, w3, noise_mode=sr_noise, force_fp32=force_fp32, upsample=True)
+        return tcconv.nhwc_to_nchw_f32(im)
+
+    out = {'image': run_sr(gen.superresolution, 0, 3),
+           'image_raw': fimg[..., :3].permute(0, 3, 1, 2).contiguous(), 'image_depth': depth_image}
+    if semantic:
+        cs = gen.semantic_channels
+        out['semantic'] = run_sr(gen.superresolution_semantic, half, cs)
+        out['semantic_raw'] = fimg[..., half:half + cs].permute(0, 3, 1, 2).contiguous()
+    return out

@@ -63,7 +63,8 @@ def nhwc_to_nchw_f32(x, channels=None, c_offset=0):
     return out
 
 
-def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, cin_padded=None, out_scale=WEIGHT_SCALE):
+def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, cin_padded=None, out_scale=WEIGHT_SCALE,
+                     cin_offset=0):
     """weight [O,I,kh,kw] fp32, styles [B,I] fp32 -> [planes,B,Op,kh*kw*Ip] fp16, K-major (tap-major, then channel)."""
     w = weight.detach().float().contiguous()
     s = styles.detach().float().contiguous()
@@ -72,7 +73,7 @@ def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, c
     op, ip = pad_to(o, 16), (cin_padded or pad_to(i, 64))
     out = torch.empty(planes, b, op, kh * kw * ip, device=w.device, dtype=torch.float16)
     with torch.cuda.device(w.device):
-        st = _lib.lib().p3d_modulate_weights(_lib.ptr(w), _lib.ptr(s), b, o, i, kh * kw, op, ip, 1 if demodulate else 0,
+        st = _lib.lib().p3d_modulate_weights(_lib.ptr(w), _lib.ptr(s), b, o, i, kh * kw, op, ip, cin_offset, 1 if demodulate else 0,
                                              float(pre_scale), float(out_scale), planes, _lib.ptr(out), _lib.stream_ptr())
     _lib.check(st, 'p3d_modulate_weights')
     _lib.bump()

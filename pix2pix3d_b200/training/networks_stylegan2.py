@@ -421,6 +421,14 @@ class SynthesisNetwork(torch.nn.Module):
 
     def forward(self, ws, **block_kwargs):
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
+        if ws.device.type == 'cuda':
+            from .. import engine, tcconv
+            noise_mode = block_kwargs.get('noise_mode', 'random')
+            extra = set(block_kwargs) - {'noise_mode', 'force_fp32', 'fused_modconv', 'update_emas'}
+            if (not extra and not engine.grad_needed(self, ws)
+                    and all(engine.block_supported(getattr(self, f'b{r}'), ws, noise_mode, False) for r in self.block_resolutions)):
+                img = engine.synthesis_network(self, ws, noise_mode=noise_mode, force_fp32=bool(block_kwargs.get('force_fp32', False)))
+                return tcconv.nhwc_to_nchw_f32(img)
         ws = ws.to(torch.float32)
         x = img = None
         w_idx = 0

@@ -63,6 +63,15 @@ class _TwoBlockSR(torch.nn.Module):
             size = (self.input_resolution, self.input_resolution)
             x = torch.nn.functional.interpolate(x, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)
             rgb = torch.nn.functional.interpolate(rgb, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)
+        if ws.device.type == 'cuda':
+            from .. import engine, tcconv
+            noise_mode = block_kwargs.get('noise_mode', 'random')
+            extra = set(block_kwargs) - {'noise_mode', 'force_fp32', 'fused_modconv', 'update_emas'}
+            if (not extra and not engine.grad_needed(self, ws, x, rgb) and engine.block_supported(self.block0, ws, noise_mode, False)
+                    and engine.block_supported(self.block1, ws, noise_mode, False)):
+                img = engine.superresolution(self, rgb.float().permute(0, 2, 3, 1).contiguous(), x.float(), ws, noise_mode=noise_mode,
+                                             force_fp32=bool(block_kwargs.get('force_fp32', False)))
+                return tcconv.nhwc_to_nchw_f32(img)
         x, rgb = self.block0(x, rgb, ws, **block_kwargs)
         x, rgb = self.block1(x, rgb, ws, **block_kwargs)
         return rgb

@@ -64,6 +64,20 @@ def render_to_images(gen, ws, c, neural_rendering_resolution, update_emas, cache
     return feature_image, depth_image
 
 
+def fast_synthesis(gen, ws, c, neural_rendering_resolution, cache_backbone, use_cached_backbone, synthesis_kwargs):
+    """Whole-generator tensor-core / fused-render path (pix2pix3d_b200/engine.py); None when it does not apply."""
+    if ws.device.type != 'cuda':
+        return None
+    from .. import engine
+    if neural_rendering_resolution is not None:
+        gen.neural_rendering_resolution = neural_rendering_resolution
+    if not engine.generator_supported(gen, ws, c, synthesis_kwargs, use_cached_backbone):
+        return None
+    return engine.generator_synthesis(gen, ws, c, cache_backbone=cache_backbone, use_cached_backbone=use_cached_backbone,
+                                      noise_mode=synthesis_kwargs.get('noise_mode', 'random'),
+                                      force_fp32=bool(synthesis_kwargs.get('force_fp32', False)))
+
+
 def _sr_kwargs(synthesis_kwargs):
     return {k: v for k, v in synthesis_kwargs.items() if k != 'noise_mode'}
 
@@ -105,6 +119,9 @@ class TriPlaneGenerator(torch.nn.Module):
 
     def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
                   use_cached_backbone=False, **synthesis_kwargs):
+        fast = fast_synthesis(self, ws, c, neural_rendering_resolution, cache_backbone, use_cached_backbone, synthesis_kwargs)
+        if fast is not None:
+            return fast
         feature_image, depth_image = render_to_images(self, ws, c, neural_rendering_resolution, update_emas,
                                                       cache_backbone, use_cached_backbone, synthesis_kwargs)
         rgb_image = feature_image[:, :3]

@@ -16,7 +16,7 @@ from ..torch_utils import misc
 from ..torch_utils import persistence
 from .networks_stylegan2 import DiscriminatorBlock, FullyConnectedLayer, SynthesisNetwork, normalize_2nd_moment
 from .networks_stylegan2 import Generator as StyleGAN2Backbone
-from .triplane import OSGDecoder, _decoder_mlp, _mipnerf_sigmoid, _sr_kwargs, query_points, render_to_images
+from .triplane import OSGDecoder, _decoder_mlp, _mipnerf_sigmoid, _sr_kwargs, fast_synthesis, query_points, render_to_images
 from .volumetric_rendering.ray_sampler import RaySampler
 from .volumetric_rendering.renderer import ImportanceRenderer
 
@@ -401,6 +401,9 @@ class TriPlaneGenerator(_CondGeneratorBase):
 
     def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
                   use_cached_backbone=False, **synthesis_kwargs):
+        fast = fast_synthesis(self, ws, c, neural_rendering_resolution, cache_backbone, use_cached_backbone, synthesis_kwargs)
+        if fast is not None:
+            return fast
         feature_image, depth_image = render_to_images(self, ws, c, neural_rendering_resolution, update_emas,
                                                       cache_backbone, use_cached_backbone, synthesis_kwargs)
         rgb_image = feature_image[:, :3]
@@ -448,6 +451,9 @@ class TriPlaneSemanticEntangleGenerator(_CondGeneratorBase):
 
     def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
                   use_cached_backbone=False, **synthesis_kwargs):
+        fast = fast_synthesis(self, ws, c, neural_rendering_resolution, cache_backbone, use_cached_backbone, synthesis_kwargs)
+        if fast is not None:
+            return fast
         feature_image, depth_image = render_to_images(self, ws, c, neural_rendering_resolution, update_emas,
                                                       cache_backbone, use_cached_backbone, synthesis_kwargs)
         rgb_image, sr_image, sem_image, sr_sem = _semantic_heads(self, feature_image, ws, synthesis_kwargs)

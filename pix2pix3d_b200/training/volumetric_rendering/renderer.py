@@ -70,8 +70,10 @@ class ImportanceRenderer(torch.nn.Module):
         self.plane_axes = generate_planes()
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options):
-        """planes [B,3,32,H,W]; rays [B,M,3] -> (features [B,M,C], depth [B,M,1], weight sum [B,M,1]) (:88-140)."""
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, planes_channels_last=None):
+        """planes [B,3,32,H,W]; rays [B,M,3] -> (features [B,M,C], depth [B,M,1], weight sum [B,M,1]) (:88-140).
+        `planes_channels_last` ([B,3,H,W,32] fp32, optional) lets a caller that already holds the gather layout skip the
+        transpose; `planes` may then be None."""
         self.plane_axes = self.plane_axes.to(ray_origins.device)
         opts = rendering_options
 
@@ -88,15 +90,28 @@ class ImportanceRenderer(torch.nn.Module):
                                                    opts['disparity_space_sampling'])
         n_importance = opts['depth_resolution_importance']
 
-        if self._fusable(planes, decoder, ray_origins, ray_directions, opts):
+        if planes_channels_last is not None or self._fusable(planes, decoder, ray_origins, ray_directions, opts):
             b, r = ray_origins.shape[:2]
-            u = torch.rand(b * r, n_importance, device=planes.device) if n_importance > 0 else None
+            u = torch.rand(b * r, n_importance, device=ray_origins.device) if n_importance > 0 else None
             dec = native.pack_decoder(decoder)
-            planes_cl = native.planes_to_channels_last(planes)
+            planes_cl = planes_channels_last if planes_channels_last is not None else native.planes_to_channels_last(planes)
             return native.render_fwd(planes_cl, dec, ray_origins, ray_directions, depths_coarse, u, opts['box_warp'],
                                      white_back=bool(opts.get('white_back', False)))
 
         return self._forward_staged(planes, decoder, ray_origins, ray_directions, depths_coarse, n_importance, opts)
+
+    def fusable_options(self, decoder, opts):
+        """True when the rendering options and decoder are covered by the fused kernel (independent of the planes)."""
+        if opts.get('density_noise', 0) > 0 or opts['clamp_mode'] != 'softplus':
+            return False
+        if not self._axes_ok():
+            return False
+        s_total = opts['depth_resolution'] + opts['depth_resolution_importance']
+        if opts['depth_resolution'] > 64 or opts['depth_resolution_importance'] > 64 or s_total > 256:
+            return False
+        if opts['depth_resolution_importance'] > 0 and opts['depth_resolution'] < 4:
+            return False
+        return native.describe_decoder(decoder) is not None
 
     def _fusable(self, planes, decoder, ray_origins, ray_directions, opts):
         if planes.device.type != 'cuda' or planes.ndim != 5 or planes.shape[1] != 3 or planes.shape[2] != 32:

@@ -1,0 +1,89 @@
+"""Tensor-core inference engine (pix2pix3d_b200/engine.py) against the generic op-by-op formulation and the fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(channel_base, channel_max, res, img_channels, num_fp16_res=0, conv_clamp=None):
+    from pix2pix3d_b200.training.networks_stylegan2 import SynthesisNetwork
+    torch.manual_seed(0)
+    net = SynthesisNetwork(w_dim=64, img_resolution=res, img_channels=img_channels, channel_base=channel_base,
+                           channel_max=channel_max, num_fp16_res=num_fp16_res, conv_clamp=conv_clamp).eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(1)
+    for name, p in net.named_parameters():
+        if name.endswith('noise_strength'):
+            p.copy_(torch.randn([], generator=g) * 0.2)
+        if name.endswith('.bias') and 'affine' not in name:
+            p.copy_(torch.randn(p.shape, generator=g) * 0.2)
+    return net.cuda()
+
+
+@pytest.mark.parametrize('cfg', [dict(channel_base=2048, channel_max=64, res=32, img_channels=96),
+                                 dict(channel_base=4096, channel_max=128, res=64, img_channels=3),
+                                 dict(channel_base=1024, channel_max=16, res=16, img_channels=6)])
+@pytest.mark.parametrize('noise_mode', ['const', 'none'])
+def test_synthesis_network_engine_matches_generic_fp32(cfg, noise_mode):
+    from pix2pix3d_b200 import _lib, engine
+    net = _net(**cfg)
+    ws = torch.randn(3, net.num_ws, 64, device='cuda')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        engine.enabled = False
+        try:
+            ref = net(ws, noise_mode=noise_mode)
+        finally:
+            engine.enabled = True
+        n0 = _lib.launch_count
+        out = net(ws, noise_mode=noise_mode)
+    assert _lib.launch_count - n0 > 10
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5      # three-pass split keeps fp32-level accuracy
+
+
+def test_synthesis_network_engine_fp16_blocks():
+    """fp16 blocks with conv_clamp (the super-resolution configuration): engine vs the reference-style fp16 path."""
+    from pix2pix3d_b200 import engine
+    net = _net(channel_base=2048, channel_max=64, res=64, img_channels=3, num_fp16_res=2, conv_clamp=256)
+    ws = torch.randn(2, net.num_ws, 64, device='cuda')
+    with torch.no_grad():
+        engine.enabled = False
+        try:
+            ref16 = net(ws, noise_mode='const')
+            ref32 = net(ws, noise_mode='const', force_fp32=True)
+        finally:
+            engine.enabled = True
+        out16 = net(ws, noise_mode='const')
+        out32 = net(ws, noise_mode='const', force_fp32=True)
+    assert rel_err(out32.cpu().numpy(), ref32.cpu().numpy()) < 2e-5
+    e_ref = rel_err(ref16.cpu().numpy(), ref32.cpu().numpy())          # how far the fp16 reference path is from fp32
+    e_out = rel_err(out16.cpu().numpy(), ref32.cpu().numpy())
+    assert e_out < max(2 * e_ref, 5e-3)                               # the engine's fp16 path is no worse than that
+    assert rel_err(out16.cpu().numpy(), ref16.cpu().numpy()) < max(3 * e_ref, 5e-3)
+
+
+def test_superresolution_engine_matches_generic():
+    from pix2pix3d_b200 import engine
+    from pix2pix3d_b200.training.superresolution import SuperresolutionHybrid2X, SuperresolutionHybrid8XDC_semantic
+    torch.manual_seed(3)
+    for cls, res_in, kw in ((SuperresolutionHybrid2X, 64, {}), (SuperresolutionHybrid8XDC_semantic, 128, dict(semantic_channels=6))):
+        sr = cls(channels=32, img_resolution=128 if res_in == 64 else 512, sr_num_fp16_res=4, sr_antialias=True, **kw).eval().requires_grad_(False).cuda()
+        n_img = sr.block0.img_channels
+        b = 1 if res_in == 128 else 2
+        x = torch.randn(b, 32, res_in, res_in, device='cuda')
+        rgb = torch.randn(b, n_img, res_in, res_in, device='cuda')
+        ws = torch.randn(b, 14, 512, device='cuda')
+        with torch.no_grad():
+            engine.enabled = False
+            try:
+                ref = sr(rgb, x, ws, noise_mode='none', force_fp32=True)
+            finally:
+                engine.enabled = True
+            out = sr(rgb, x, ws, noise_mode='none', force_fp32=True)
+            out16 = sr(rgb, x, ws, noise_mode='none')
+        assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5
+        assert rel_err(out16.cpu().numpy(), ref.cpu().numpy()) < 2e-2
