@@ -107,6 +107,13 @@ typedef struct {
  * -> fine sample+decode -> unify_samples (:157-167) -> final ray march, as one persistent kernel. */
 int p3d_render_fwd(const p3d_render_args_t* args, p3d_stream_t stream);
 
+/* Tensor-core variant of the same pipeline (decoder MLP on tcgen05 with fp16 hi/lo split operands and fp32 TMEM
+ * accumulation; pix2pix3d_b200/csrc/render_tc.cu). Takes the decoder image of p3d_pack_decoder_tc. Returns
+ * P3D_UNSUPPORTED when Sc or Sf is not a multiple of 8 (callers then use p3d_render_fwd). */
+#define P3D_DECODER_TC_PACKED_BYTES (65536 + 324 * 4)
+int p3d_pack_decoder_tc(const p3d_decoder_t* dec, void* packed, p3d_stream_t stream);
+int p3d_render_fwd_tc(const p3d_render_args_t* args, p3d_stream_t stream);
+
 /* ImportanceRenderer.run_model -- renderer.py:142-148 (sample_from_planes :55-65 + decoder):
  * coords [B,M,3] -> rgb [B,M,32*n_nets], sigma [B,M]. density_noise is added by the host wrapper. */
 int p3d_run_model(const float* planes_nhwc, const float* coords, const float* decoder_packed,

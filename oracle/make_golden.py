@@ -73,10 +73,18 @@ def golden_renderer():
         'rgb_only': (1, 32, 9, 10, 6, 'osg', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
         'coarse_only': (1, 32, 8, 9, 0, 'osg', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
         'far_outside': (1, 32, 8, 12, 12, 'late6', dict(ray_start=0.5, ray_end=6.0, box_warp=1)),
+        # sample counts that are multiples of 8 (the tensor-core renderer's domain)
+        'seg16': (2, 32, 9, 16, 8, 'late6', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'rgb24': (1, 32, 8, 24, 24, 'osg', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'coarse8': (1, 32, 8, 8, 0, 'osg', dict(ray_start=2.25, ray_end=3.3, box_warp=1)),
+        'car64': (1, 24, 6, 64, 64, 'late1', dict(ray_start=0.1, ray_end=2.6, box_warp=1.6, white_back=True)),
     }
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 else None
     for name, (B, H, nrr, Sc, Sf, dkind, extra) in cases.items():
-        torch.manual_seed(abs(hash(name)) % 1000 + 7)
-        torch.manual_seed({'seg': 11, 'seg48': 12, 'car': 13, 'rgb_only': 14, 'coarse_only': 15, 'far_outside': 16}[name])
+        if only is not None and name not in only:
+            continue
+        torch.manual_seed({'seg': 11, 'seg48': 12, 'car': 13, 'rgb_only': 14, 'coarse_only': 15, 'far_outside': 16,
+                           'seg16': 17, 'rgb24': 18, 'coarse8': 19, 'car64': 20}[name])
         planes = torch.randn(B, 3, 32, H, H)
         if dkind == 'osg':
             dec = OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32})
@@ -208,6 +216,9 @@ SYNTH_CASES = {
                      Sf=12, B=2, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
     'car_tiny': dict(seed=22, cls='TriPlaneSemanticEntangleGenerator', img_resolution=128, semantic_channels=1, nrr=16, Sc=8,
                      Sf=8, B=1, channel_base=1024, channel_max=16, ray=(0.1, 2.6, 1.6), white_back=True, mapping='edge', in_res=32),
+    # neural rendering at the super-resolution stack's native input resolution (no resize): the whole-generator fast path
+    'seg_nrr64': dict(seed=24, cls='TriPlaneSemanticEntangleGenerator', img_resolution=128, semantic_channels=6, nrr=64, Sc=8,
+                      Sf=8, B=1, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
     'rgb_tiny': dict(seed=23, cls='TriPlaneGenerator', img_resolution=128, semantic_channels=0, nrr=16, Sc=10, Sf=6, B=1,
                      channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
 }
@@ -269,7 +280,10 @@ def synth_inputs(case):
 
 def golden_synthesis():
     import training.triplane_cond as ref_tc
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 else None
     for name, case in SYNTH_CASES.items():
+        if only is not None and name not in only:
+            continue
         G = build_generator(ref_tc, case)
         z, c, mask = synth_inputs(case)
         draws = []

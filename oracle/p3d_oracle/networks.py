@@ -123,21 +123,27 @@ SR_KINDS = {  # class name -> (input_resolution, block0 upsamples?, resize only 
 }
 
 
-def superresolution(rgb, x, ws, sd, prefix, kind, noise_mode='none', fused_modconv=True, use_fp16_clamp=True):
+def superresolution(rgb, x, ws, sd, prefix, kind, noise_mode='none', fused_modconv=True, use_fp16_clamp=True, return_raw=False):
     """Superresolution*.forward (superresolution.py:48-57, 312-323). conv_clamp is 256 when the module was built
     with sr_num_fp16_res > 0 (it is kept even when the block runs in fp32)."""
     in_res, up0, only_smaller = SR_KINDS[kind]
     ws = np.asarray(ws, f32)[:, -1:, :].repeat(3, axis=1)
     need = (x.shape[-1] < in_res) if only_smaller else (x.shape[-1] != in_res)
+    raw = rgb
     if need:
         x = bilinear_antialias_resize(x, (in_res, in_res))
         rgb = bilinear_antialias_resize(rgb, (in_res, in_res))
     clamp = 256 if use_fp16_clamp else None
     x, rgb = synthesis_block(x, rgb, ws, sd, prefix + '.block0', upsample=up0, noise_mode=noise_mode,
                              fused_modconv=fused_modconv, conv_clamp=clamp)
+    if not up0 and not need:
+        # SynthesisBlockNoUp adds its ToRGB in place into the image it was handed (superresolution.py:283 `img.add_(y)`);
+        # without a resize that image is the `feature_image[:, :3]` view which synthesis also returns as the raw image
+        # (triplane_cond.py:1055-1061), so the returned raw image carries the block-0 ToRGB term.
+        raw = rgb
     x, rgb = synthesis_block(x, rgb, ws, sd, prefix + '.block1', upsample=True, noise_mode=noise_mode,
                              fused_modconv=fused_modconv, conv_clamp=clamp)
-    return rgb
+    return (rgb, raw) if return_raw else rgb
 
 
 def decoder_from_state_dict(sd, prefix, kind, semantic_sigmoid=False, lr_mul=1.0):
@@ -180,14 +186,14 @@ def generator_synthesis(ws, c, sd, cfg, jitter, u, noise_mode='const'):
     if cs > 0:
         half = fimg.shape[1] // 2
         rgb_f, sem_f = fimg[:, :half], fimg[:, half:]
-        out['image_raw'] = rgb_f[:, :3]
-        out['image'] = superresolution(rgb_f[:, :3], rgb_f, ws, sd, 'superresolution', cfg['sr_kind'], noise_mode=sr_noise,
-                                       fused_modconv=fused, use_fp16_clamp=cfg.get('sr_fp16', True))
-        out['semantic_raw'] = sem_f[:, :cs]
-        out['semantic'] = superresolution(sem_f[:, :cs], sem_f, ws, sd, 'superresolution_semantic', cfg['sr_kind_semantic'],
-                                          noise_mode=sr_noise, fused_modconv=fused, use_fp16_clamp=cfg.get('sr_fp16', True))
+        out['image'], out['image_raw'] = superresolution(rgb_f[:, :3], rgb_f, ws, sd, 'superresolution', cfg['sr_kind'],
+                                                         noise_mode=sr_noise, fused_modconv=fused,
+                                                         use_fp16_clamp=cfg.get('sr_fp16', True), return_raw=True)
+        out['semantic'], out['semantic_raw'] = superresolution(sem_f[:, :cs], sem_f, ws, sd, 'superresolution_semantic',
+                                                               cfg['sr_kind_semantic'], noise_mode=sr_noise, fused_modconv=fused,
+                                                               use_fp16_clamp=cfg.get('sr_fp16', True), return_raw=True)
     else:
-        out['image_raw'] = fimg[:, :3]
-        out['image'] = superresolution(fimg[:, :3], fimg, ws, sd, 'superresolution', cfg['sr_kind'], noise_mode=sr_noise,
-                                       fused_modconv=fused, use_fp16_clamp=cfg.get('sr_fp16', True))
+        out['image'], out['image_raw'] = superresolution(fimg[:, :3], fimg, ws, sd, 'superresolution', cfg['sr_kind'],
+                                                         noise_mode=sr_noise, fused_modconv=fused,
+                                                         use_fp16_clamp=cfg.get('sr_fp16', True), return_raw=True)
     return out

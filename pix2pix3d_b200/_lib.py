@@ -51,6 +51,8 @@ _SIGNATURES = {
     'p3d_planes_to_channels_last': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'p3d_pack_decoder': (c_int, [ctypes.POINTER(DecoderDesc), c_void_p, c_void_p]),
     'p3d_render_fwd': (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),
+    'p3d_pack_decoder_tc': (c_int, [ctypes.POINTER(DecoderDesc), c_void_p, c_void_p]),
+    'p3d_render_fwd_tc': (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),
     'p3d_run_model': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_uint32), c_int, c_int, c_int,
                               c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'p3d_sample_from_planes': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),

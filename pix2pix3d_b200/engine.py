@@ -250,14 +250,19 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
         rgb = fimg[..., c_off:c_off + n_img].contiguous()
         w3 = ws[:, -1:, :].repeat(1, 3, 1).to(torch.float32)
         up0 = sr.block0.conv0.up == 2
+        # reference quirk kept: a NoUp block0 accumulates its ToRGB into the very tensor it was handed
+        # (superresolution.py:283 `img.add_(y)` on the `feature_image[:, :3]` view), so the raw image returned by
+        # synthesis includes that term whenever no resize happened; with an upsampling block0 it does not.
+        raw = rgb if up0 else rgb.clone()
         x, im = synthesis_block(sr.block0, x, rgb, w3, noise_mode=sr_noise, force_fp32=force_fp32, upsample=up0, cin_offset=c_off)
+        if not up0:
+            raw = im
         x, im = synthesis_block(sr.block1, x, im, w3, noise_mode=sr_noise, force_fp32=force_fp32, upsample=True)
-        return tcconv.nhwc_to_nchw_f32(im)
+        return tcconv.nhwc_to_nchw_f32(im), raw.permute(0, 3, 1, 2).contiguous()
 
-    out = {'image': run_sr(gen.superresolution, 0, 3),
-           'image_raw': fimg[..., :3].permute(0, 3, 1, 2).contiguous(), 'image_depth': depth_image}
+    image, image_raw = run_sr(gen.superresolution, 0, 3)
+    out = {'image': image, 'image_raw': image_raw, 'image_depth': depth_image}
     if semantic:
         cs = gen.semantic_channels
-        out['semantic'] = run_sr(gen.superresolution_semantic, half, cs)
-        out['semantic_raw'] = fimg[..., half:half + cs].permute(0, 3, 1, 2).contiguous()
+        out['semantic'], out['semantic_raw'] = run_sr(gen.superresolution_semantic, half, cs)
     return out

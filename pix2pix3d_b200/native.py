@@ -10,6 +10,10 @@ import torch
 from . import _lib
 
 PACKED_FLOATS = 2 * 4260
+TC_PACKED_BYTES = 65536 + 324 * 4
+
+# which fused renderer `render_fwd` uses: 'auto' (tensor-core decoder when the sample counts allow it), 'tc', 'simt'
+render_impl = 'auto'
 
 # when set to a list, render_fwd appends ('render_fwd', start_event, end_event) around its launch (bench.py)
 kernel_events = None
@@ -55,8 +59,9 @@ def planes_to_channels_last(planes):
 class PackedDecoder:
     """Kernel-side weights of an OSG decoder plus its static description."""
 
-    def __init__(self, packed, n_nets, sigma_net, masks):
+    def __init__(self, packed, n_nets, sigma_net, masks, packed_tc=None):
         self.packed = packed
+        self.packed_tc = packed_tc
         self.n_nets = n_nets
         self.sigma_net = sigma_net
         self.masks = masks
@@ -116,12 +121,16 @@ def pack_decoder(decoder):
     with torch.cuda.device(dev):
         st = _lib.lib().p3d_pack_decoder(ctypes.byref(d), _lib.ptr(packed), _lib.stream_ptr())
     _lib.check(st, 'p3d_pack_decoder')
-    _lib.bump()
+    packed_tc = torch.empty(TC_PACKED_BYTES, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        st = _lib.lib().p3d_pack_decoder_tc(ctypes.byref(d), _lib.ptr(packed_tc), _lib.stream_ptr())
+    _lib.check(st, 'p3d_pack_decoder_tc')
+    _lib.bump(2)
     del keep
-    return PackedDecoder(packed, len(nets), sigma_net, masks)
+    return PackedDecoder(packed, len(nets), sigma_net, masks, packed_tc)
 
 
-def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_warp, white_back=False, debug=False):
+def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_warp, white_back=False, debug=False, impl=None):
     """Fused ImportanceRenderer.forward. Returns (feat [B,R,C], depth [B,R,1], wsum [B,R,1][, debug dict])."""
     B, _, H, W, C = planes_nhwc.shape
     assert C == 32
@@ -164,8 +173,16 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
     if kernel_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
+    impl = impl or render_impl
+    use_tc = impl in ('auto', 'tc') and Sc % 8 == 0 and Sf % 8 == 0 and Sc <= 128 and Sf <= 128 and dec.packed_tc is not None
+    if impl == 'tc' and not use_tc:
+        raise ValueError('tensor-core renderer needs sample counts that are multiples of 8')
     with torch.cuda.device(dev):
-        st = _lib.lib().p3d_render_fwd(ctypes.byref(a), _lib.stream_ptr())
+        if use_tc:
+            a.decoder_packed = dec.packed_tc.data_ptr()
+            st = _lib.lib().p3d_render_fwd_tc(ctypes.byref(a), _lib.stream_ptr())
+        else:
+            st = _lib.lib().p3d_render_fwd(ctypes.byref(a), _lib.stream_ptr())
     if ev is not None:
         ev[1].record()
         kernel_events.append(('render_fwd', ev[0], ev[1]))

@@ -80,10 +80,11 @@ def test_superresolution_engine_matches_generic():
         with torch.no_grad():
             engine.enabled = False
             try:
-                ref = sr(rgb, x, ws, noise_mode='none', force_fp32=True)
+                # SynthesisBlockNoUp adds ToRGB into the image it was given (superresolution.py:283): pass clones
+                ref = sr(rgb.clone(), x.clone(), ws, noise_mode='none', force_fp32=True)
             finally:
                 engine.enabled = True
-            out = sr(rgb, x, ws, noise_mode='none', force_fp32=True)
-            out16 = sr(rgb, x, ws, noise_mode='none')
+            out = sr(rgb.clone(), x.clone(), ws, noise_mode='none', force_fp32=True)
+            out16 = sr(rgb.clone(), x.clone(), ws, noise_mode='none')
         assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5
         assert rel_err(out16.cpu().numpy(), ref.cpu().numpy()) < 2e-2

@@ -23,6 +23,7 @@ def test_bias_act_forward_all_activations(dtype):
         for kw in ({}, dict(gain=r32(1.7), clamp=r32(0.9), alpha=r32(0.3))):
             y = bias_act.bias_act(x, b, act=act, **kw)
             assert y.dtype == dtype and y.shape == x.shape
+            kw = dict(kw, gain=r32(kw.get('gain', bias_act.activation_funcs[act].def_gain)))   # defaults cross the ABI as floats too
             ref = O.ops.bias_act(x.cpu().numpy().astype(np.float64 if dtype == torch.float64 else np.float32),
                                  b.cpu().numpy().astype(np.float64 if dtype == torch.float64 else np.float32), act=act, **kw)
             assert rel_err(y.float().cpu().numpy() if dtype != torch.float64 else y.cpu().numpy(), ref) < tol, (act, kw)
@@ -48,6 +49,7 @@ def test_bias_act_gradients_first_and_second_order():
     for act in bias_act.activation_funcs:
         for tag, kw in (('d', {}), ('c', dict(gain=1.7, clamp=0.9, alpha=0.3))):
             kw32 = {k: r32(v) for k, v in kw.items()}
+            kw32['gain'] = r32(kw.get('gain', bias_act.activation_funcs[act].def_gain))
             x = torch.from_numpy(g['ba_x']).cuda().double().requires_grad_(True)
             b = torch.from_numpy(g['ba_b']).cuda().double().requires_grad_(True)
             y = bias_act.bias_act(x, b, act=act, **kw)

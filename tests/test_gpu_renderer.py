@@ -6,7 +6,7 @@ import torch
 
 import p3d_oracle as O
 from conftest import load_golden, rel_err
-from test_oracle_golden import RENDER_CASES, oracle_decoder, render_opts
+from test_oracle_golden import RENDER_CASES, TC_RENDER_CASES, oracle_decoder, render_opts
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3          # north_star tolerance
@@ -31,7 +31,7 @@ def torch_decoder(g, device):
     return dec.to(device).requires_grad_(False)
 
 
-def run_fused(g, debug=True):
+def run_fused(g, debug=True, impl='simt'):
     from pix2pix3d_b200 import native
     dev = torch.device('cuda')
     opts = render_opts(g)
@@ -42,15 +42,18 @@ def run_fused(g, debug=True):
     u = torch.from_numpy(g['u']).to(dev) if int(g['Sf']) > 0 else None
     res = native.render_fwd(native.planes_to_channels_last(planes), dec, torch.from_numpy(g['ray_origins']).to(dev),
                             torch.from_numpy(g['ray_dirs']).to(dev), torch.from_numpy(dc).to(dev), u, opts['box_warp'],
-                            white_back=opts['white_back'], debug=debug)
+                            white_back=opts['white_back'], debug=debug, impl=impl)
     torch.cuda.synchronize()
     return res, dc, opts
 
 
-@pytest.mark.parametrize('case', RENDER_CASES)
-def test_fused_render_matches_reference_and_oracle(case):
+IMPL_CASES = [(c, 'simt') for c in RENDER_CASES] + [(c, 'tc') for c in TC_RENDER_CASES]
+
+
+@pytest.mark.parametrize('case,impl', IMPL_CASES)
+def test_fused_render_matches_reference_and_oracle(case, impl):
     g = load_golden('renderer_' + case)
-    (feat, depth, wsum, dbg), dc, opts = run_fused(g)
+    (feat, depth, wsum, dbg), dc, opts = run_fused(g, impl=impl)
     assert rel_err(feat.cpu().numpy(), g['feat']) < TOL
     assert rel_err(depth.cpu().numpy(), g['depth']) < TOL
     assert rel_err(wsum.cpu().numpy(), g['wsum']) < TOL
@@ -63,12 +66,12 @@ def test_fused_render_matches_reference_and_oracle(case):
     assert rel_err(dbg['weights_final'].cpu().numpy(), odbg['weights_final']) < 2e-4
 
 
-@pytest.mark.parametrize('case', [c for c in RENDER_CASES if c != 'coarse_only'])
-def test_sampling_bookkeeping_is_bit_exact(case):
+@pytest.mark.parametrize('case,impl', [ci for ci in IMPL_CASES if ci[0] not in ('coarse_only', 'coarse8')])
+def test_sampling_bookkeeping_is_bit_exact(case, impl):
     """Feed the oracle the kernel's OWN coarse weights: searchsorted indices, fine depths and the sort permutation
     must then be identical bit for bit (integer bookkeeping of renderer.py:240-252 and :162)."""
     g = load_golden('renderer_' + case)
-    (feat, depth, wsum, dbg), dc, opts = run_fused(g)
+    (feat, depth, wsum, dbg), dc, opts = run_fused(g, impl=impl)
     b, m = g['ray_origins'].shape[:2]
     sc, sf = opts['depth_resolution'], opts['depth_resolution_importance']
     wc = dbg['weights_coarse'].cpu().numpy()
@@ -136,7 +139,8 @@ def test_ray_march_standalone_matches_oracle():
         assert depth[0, 0, 0].item() == depths.max()
 
 
-def test_full_size_properties_config2():
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_full_size_properties_config2(impl):
     """BASELINE config 2 sizes (B=4, 128^2 rays, 48+48 samples): size-independent properties."""
     from pix2pix3d_b200 import native
     from pix2pix3d_b200.training.triplane_cond import OSGDecoder_semantic_lateSeparate
@@ -156,8 +160,8 @@ def test_full_size_properties_config2():
     u = torch.rand(B * R, Sf, device=dev)
     dec = native.pack_decoder(dec_m)
     pcl = native.planes_to_channels_last(planes)
-    feat, depth, wsum, dbg = native.render_fwd(pcl, dec, o, d, dc, u, 1.0, debug=True)
-    feat2, depth2, wsum2 = native.render_fwd(pcl, dec, o, d, dc, u, 1.0)
+    feat, depth, wsum, dbg = native.render_fwd(pcl, dec, o, d, dc, u, 1.0, debug=True, impl=impl)
+    feat2, depth2, wsum2 = native.render_fwd(pcl, dec, o, d, dc, u, 1.0, impl=impl)
     torch.cuda.synchronize()
     assert torch.equal(feat, feat2) and torch.equal(depth, depth2) and torch.equal(wsum, wsum2)   # deterministic
     assert torch.isfinite(feat).all() and torch.isfinite(depth).all()
@@ -172,7 +176,7 @@ def test_full_size_properties_config2():
     assert (dbg['inds'] >= 1).all() and (dbg['inds'] <= Sc - 2).all()
     # image 2 rendered alone equals its slice of the batch (rays are independent; depth only via the global clamp)
     f1, d1, w1 = native.render_fwd(pcl[2:3].contiguous(), dec, o[2:3].contiguous(), d[2:3].contiguous(), dc[2:3].contiguous(),
-                                   u[2 * R:3 * R].contiguous(), 1.0)
+                                   u[2 * R:3 * R].contiguous(), 1.0, impl=impl)
     assert torch.equal(f1[0], feat[2]) and torch.equal(w1[0], wsum[2])
     # sampled check of full-size output against the oracle on 64 rays
     idx = torch.randperm(R, device=dev)[:64]
@@ -206,7 +210,7 @@ def test_importance_renderer_module_dispatches_to_fused_kernel():
                                                      torch.from_numpy(g['ray_dirs']).to(dev), opts)
     finally:
         torch.rand_like, torch.rand = o_like, o_rand
-    assert _lib.launch_count - before == 3          # pack_decoder, planes transpose, fused render
+    assert _lib.launch_count - before == 4          # pack_decoder (2 images), planes transpose, fused render
     assert rel_err(feat.cpu().numpy(), g['feat']) < TOL
     assert rel_err(depth.cpu().numpy(), g['depth']) < TOL
     assert rel_err(wsum.cpu().numpy(), g['wsum']) < TOL

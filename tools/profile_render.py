@@ -5,7 +5,7 @@ import torch
 from pix2pix3d_b200 import native, configs
 from pix2pix3d_b200.training.triplane_cond import OSGDecoder_semantic_lateSeparate
 
-def main(reps=3, B=4, H=256, nrr=128, Sc=48, Sf=48):
+def main(reps=3, impl='auto', B=4, H=256, nrr=128, Sc=48, Sf=48):
     dev = torch.device('cuda')
     torch.manual_seed(0)
     planes = torch.randn(B, 3, 32, H, H, device=dev)
@@ -19,17 +19,17 @@ def main(reps=3, B=4, H=256, nrr=128, Sc=48, Sf=48):
     dec = native.pack_decoder(dec_m)
     pcl = native.planes_to_channels_last(planes)
     for _ in range(2):
-        native.render_fwd(pcl, dec, o, d, dc, u, 1.0)
+        native.render_fwd(pcl, dec, o, d, dc, u, 1.0, impl=impl)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        native.render_fwd(pcl, dec, o, d, dc, u, 1.0)
+        native.render_fwd(pcl, dec, o, d, dc, u, 1.0, impl=impl)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     gb = configs.render_algorithmic_bytes(B, R, Sc + Sf) / 1e9
-    print(f'render_fwd: {ms:.3f} ms  {gb / ms * 1e3:.1f} GB/s touched  ({B * R / ms * 1e3:.3e} rays/s)')
+    print(f'render_fwd[{impl}]: {ms:.3f} ms  {gb / ms * 1e3:.1f} GB/s touched  ({B * R / ms * 1e3:.3e} rays/s)')
 
 if __name__ == '__main__':
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 3)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 3, sys.argv[2] if len(sys.argv) > 2 else 'auto')
