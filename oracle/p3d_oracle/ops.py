@@ -68,9 +68,11 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None):
     return y.astype(t)
 
 
-def bias_act_grad(dy, x, b, y, dim=1, act='linear', alpha=None, gain=None, clamp=None, order=1, dy1=None):
+def bias_act_grad(dy, x, b, y, dim=1, act='linear', alpha=None, gain=None, clamp=None, order=1, dy1=None, plugin_semantics=False):
     """First (order=1: dx given dy) and second (order=2: d_x given d_dx=`dy` and the first-order `dy1`) gradient
-    forms of the plugin (bias_act.cu:44-146 with grad = 1 / 2). x: forward input, y: forward output."""
+    forms of the plugin (bias_act.cu:44-146 with grad = 1 / 2). x: forward input, y: forward output.
+    plugin_semantics: the CUDA autograd wrapper only saves y when the activation's `ref` contains 'y' (bias_act.py:160-163),
+    so for 'linear' the plugin sees yref = 0 and the clamp does NOT mask the gradient -- unlike autograd through `_ref`."""
     da, dg = ACT[act][0], ACT[act][1]
     alpha = float(da if alpha is None else alpha)
     gain = float(dg if gain is None else gain)
@@ -84,6 +86,8 @@ def bias_act_grad(dy, x, b, y, dim=1, act='linear', alpha=None, gain=None, clamp
     if xr is not None and b is not None:
         xr = xr + np.asarray(b).astype(cdt).reshape(_bshape(g, dim))
     yr = None if y is None else np.asarray(y).astype(cdt)
+    if plugin_semantics and 'y' not in ACT[act][3]:
+        yr = np.zeros_like(g)
     yy = (yr / cdt(gain)) if (yr is not None and gain != 0) else (np.zeros_like(g))
     if act == 'linear':
         r = g if order == 1 else np.zeros_like(g)

@@ -62,7 +62,7 @@ def test_fused_render_matches_reference_and_oracle(case, impl):
                                                       return_debug=True)
     assert rel_err(feat.cpu().numpy(), of) < TIGHT
     assert rel_err(depth.cpu().numpy(), od) < TIGHT
-    assert rel_err(wsum.cpu().numpy()[..., 0], ow[..., 0] if ow.ndim == 3 else ow) < TIGHT
+    assert rel_err(wsum.cpu().numpy()[..., 0], ow[..., 0] if ow.ndim == 3 else ow) < 1e-4   # tiny sums of 1-exp(-x)
     assert rel_err(dbg['weights_final'].cpu().numpy(), odbg['weights_final']) < 2e-4
 
 
