@@ -30,6 +30,7 @@ struct ConvKernelArgs {
     int Cin;
     // tiling
     int BW, BH, tiles_x, tiles_y, BN, w_per_sample;
+    int MT, NT;                       // 128-row sub-tiles per CTA along pixels / output channels (operand reuse in smem)
     uint32_t idesc, tmem_cols;
     // epilogue
     int gH, gW;                       // size of the computed grid (phase grid for transposed conv)
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][A 16 KB][B BN*128 B] | barriers | tmem ptr
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = kBM * 128, b_bytes = (uint32_t)a.BN * 128;
+    const uint32_t a_bytes = (uint32_t)a.MT * kBM * 128, b_bytes = (uint32_t)a.NT * a.BN * 128;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
     uint64_t* empty_bar = full_bar + kStages;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x, tile_n = blockIdx.y, b = blockIdx.z;
     const int ty = tile_m / a.tiles_x, tx = tile_m % a.tiles_x;
-    const int n0 = tile_n * a.BN;
+    const int n0 = tile_n * a.BN * a.NT;
     const int total_k = a.n_groups * a.kc_steps;
 
     if (warp == 0 && lane == 0) {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int g = 0; g < a.n_groups; ++g) {
-                const int x0 = tx * a.BW + a.dx[g], y0 = ty * a.BH + a.dy[g];
+                const int x0 = tx * a.BW + a.dx[g], y0 = ty * a.BH * a.MT + a.dy[g];
                 const int kb = a.tap[g] * a.Cin;
                 for (int kc = 0; kc < a.kc_steps; ++kc) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -101,9 +102,15 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
                 tc::tc_fence_after();
                 const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
                 const uint64_t da = tc::umma_desc_k128(sa), db = tc::umma_desc_k128(sa + a_bytes);
+                // every (pixel sub-tile, channel sub-tile) pair has its own 128-column accumulator; operands are shared
+                for (int mt = 0; mt < a.MT; ++mt)
+                    for (int nt = 0; nt < a.NT; ++nt) {
+                        const uint64_t dam = da + (uint64_t)(mt * (kBM * 128 >> 4)), dbn = db + (uint64_t)(nt * (a.BN * 128 >> 4));
+                        const uint32_t acc = tmem_base + (uint32_t)((mt * a.NT + nt) * 128);
 #pragma unroll
-                for (int j = 0; j < kBK / 16; ++j)   // 4 MMAs of K=16: advance 32 bytes inside the swizzle span
-                    tc::umma_f16(tmem_base, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
+                        for (int j = 0; j < kBK / 16; ++j)   // 4 MMAs of K=16: advance 32 bytes inside the swizzle span
+                            tc::umma_f16(acc, dam + (uint64_t)(j * 2), dbn + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
+                    }
                 tc::umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
                 if (k == total_k - 1) tc::umma_commit(tmem_full_bar);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -113,19 +120,21 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
         const int q = warp & 3;
         const int m = q * 32 + lane;                    // tile row = TMEM lane
-        const int gy = ty * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
+        tc::mbar_wait(tmem_full_bar, 0);
+        tc::tc_fence_after();
+        for (int mt = 0; mt < a.MT; ++mt) {
+        const int gy = (ty * a.MT + mt) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
         const bool pix_ok = (gy < a.gH) && (gx < a.gW);
         const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
         const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
         const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) : 0.f;
-        tc::mbar_wait(tmem_full_bar, 0);
-        tc::tc_fence_after();
+        for (int nt = 0; nt < a.NT; ++nt)
         for (int c0 = 0; c0 < a.BN; c0 += 32) {
             uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * a.NT + nt) * 128 + c0), v);
             tc::tmem_ld_wait();
             if (!pix_ok) continue;
-            const int ch0 = n0 + c0;
+            const int ch0 = n0 + nt * a.BN + c0;
             if (ch0 >= a.Cout) continue;
             float r[32];
 #pragma unroll
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
                 }
             }
         }
+        }   // mt
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -252,6 +262,15 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     }
     const int BH = kBM / BW;
     const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
+    // operand reuse: up to 2 x 2 sub-tiles per CTA (A and B stages are shared by the accumulators), as long as the
+    // grid still fills the machine; it halves the L2 -> shared-memory traffic per FLOP, which is what bounds this kernel
+    int MT = 1, NT = 1;
+    {
+        const long ctas1 = (long)ceil_div(p->gW, BW) * ceil_div(p->gH, BH) * ceil_div(p->Cout_padded, BN) * p->B;
+        const int nsm = sm_count();
+        if (BN == 128 && p->Cout_padded >= 256 && ctas1 / 2 >= nsm) NT = 2;
+        if (2 * BH <= 256 && p->gH >= 2 * BH && ctas1 / (2 * NT) >= nsm) MT = 2;
+    }
     const int K = p->n_kblocks * p->C;
     if (p->n_kblocks < 1) return P3D_BAD_ARG;
 
@@ -260,14 +279,14 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)p->x_planes};
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
-        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)BH, 1, 1};
+        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)(BH * MT), 1, 1};
         int rc = make_tmap(&tmA, p->x, 5, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)p->Cout_padded, (uint64_t)p->Bw, (uint64_t)p->w_planes};
         uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)p->Cout_padded * K * 2, (uint64_t)p->Bw * p->Cout_padded * K * 2};
-        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(BN * NT), 1, 1};
         int rc = make_tmap(&tmB, p->w, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
@@ -287,20 +306,22 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.kc_steps = p->C / kBK;
     a.Cin = p->C;
     a.BW = BW; a.BH = BH;
-    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, BH);
+    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, BH * MT);
+    a.MT = MT; a.NT = NT;
     a.BN = BN; a.w_per_sample = p->Bw > 1 ? 1 : 0;
     a.idesc = tc::umma_idesc_f16(kBM, BN, 0);
-    a.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;
+    a.tmem_cols = (MT * NT > 1) ? (uint32_t)(MT * NT * 128) : (BN <= 32 ? 32u : BN <= 64 ? 64u : 128u);
+    if (a.tmem_cols == 384) a.tmem_cols = 512;
     a.gH = p->gH; a.gW = p->gW; a.oH = p->oH; a.oW = p->oW; a.sy = p->sy; a.oy = p->oy; a.sx = p->sx; a.ox = p->ox;
     a.Cout = p->Cout; a.y_cstride = p->y_cstride; a.y_coff = p->y_coff;
     a.y = p->y; a.y_lo = p->y_lo; a.out_mode = p->out_mode;
     a.bias = p->bias; a.noise = p->noise; a.dscale = p->dscale;
     a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp; a.acc_scale = p->acc_scale;
 
-    constexpr int kStages = 3;   // 3 x 32 KB: two CTAs per SM overlap one tile's epilogue with the other's MMAs
-    const size_t smem = (size_t)kStages * (kBM * 128 + (size_t)BN * 128) + (2 * kStages + 1) * 8 + 16 + 1024;
+    constexpr int kStages = 3;   // 3 stages: with 1x1 sub-tiles (96 KB) two CTAs per SM overlap epilogue and MMA phases
+    const size_t smem = (size_t)kStages * ((size_t)MT * kBM * 128 + (size_t)NT * BN * 128) + (2 * kStages + 1) * 8 + 16 + 1024;
     P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
+    dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN * NT), p->B);
     conv_gemm_kernel<kStages><<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, a);
     P3D_LAUNCH_CHECK();
     return P3D_OK;

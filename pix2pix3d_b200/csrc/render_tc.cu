@@ -188,23 +188,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
     auto group_sync = [&]() { tc::tc_fence_before(); tc::named_bar_sync(1 + grp, 128); tc::tc_fence_after(); };
     auto wait_mma = [&]() { tc::mbar_wait(&mma_bar[grp], bar_phase); bar_phase ^= 1; tc::tc_fence_after(); };
 
-    // warp-cooperative gather of this warp's 32 rows into feature tile `tile` (lane = channel)
+    // warp-cooperative gather of this warp's 32 rows into feature tile `tile`.
+    // Step 1 (lane = sample): every lane computes the 12 bilinear taps of ITS OWN row once and parks them in that row
+    // of the feature tile (the row is free until its features are written). Step 2 (lane = channel): the warp walks
+    // its rows two at a time, broadcasts the parked taps with 7 LDS.128 each, fetches 12 coalesced 128-byte texel lines
+    // per row and overwrites the row with the fp16 (hi | lo) features.
     auto gather_rows = [&](int tile, bool valid, int b, float px, float py, float pz) {
-        unsigned active = __ballot_sync(0xffffffffu, valid);
-        const size_t isz = (size_t)3 * a.H * a.W * kC;
         uint8_t* tb = feat + tile * 16384;
-        while (active) {
-            const int s = __ffs(active) - 1;
-            active &= active - 1;
-            const int bs = __shfl_sync(0xffffffffu, b, s);
-            const float x = __shfl_sync(0xffffffffu, px, s), y = __shfl_sync(0xffffffffu, py, s), z = __shfl_sync(0xffffffffu, pz, s);
-            float f0, f1, f2;
-            plane_values(a.planes_nhwc + (size_t)bs * isz, a.H, a.W, x, y, z, lane, f0, f1, f2);
-            const float f = plane_mean(f0, f1, f2);
+        const int myrow = q * 32 + lane;
+        if (valid) {
+            const Taps t0 = make_taps(px, py, a.H, a.W), t1 = make_taps(px, pz, a.H, a.W), t2 = make_taps(pz, px, a.H, a.W);
+            uint8_t* r = tb + myrow * 128;
+            const int sw = myrow & 7;
+            *reinterpret_cast<int4*>(r + ((0 ^ sw) << 4)) = make_int4(t0.o00, t0.o01, t0.o10, t0.o11);
+            *reinterpret_cast<int4*>(r + ((1 ^ sw) << 4)) = make_int4(t1.o00, t1.o01, t1.o10, t1.o11);
+            *reinterpret_cast<int4*>(r + ((2 ^ sw) << 4)) = make_int4(t2.o00, t2.o01, t2.o10, t2.o11);
+            *reinterpret_cast<float4*>(r + ((3 ^ sw) << 4)) = make_float4(t0.w00, t0.w01, t0.w10, t0.w11);
+            *reinterpret_cast<float4*>(r + ((4 ^ sw) << 4)) = make_float4(t1.w00, t1.w01, t1.w10, t1.w11);
+            *reinterpret_cast<float4*>(r + ((5 ^ sw) << 4)) = make_float4(t2.w00, t2.w01, t2.w10, t2.w11);
+            *reinterpret_cast<int4*>(r + ((6 ^ sw) << 4)) = make_int4(b, 0, 0, 0);
+        }
+        __syncwarp();
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        const size_t psz = (size_t)a.H * a.W * kC, isz = 3 * psz;
+        auto fetch = [&](int row, float& f) {
+            const uint8_t* r = tb + row * 128;
+            const int sw = row & 7;
+            const int4 o0 = *reinterpret_cast<const int4*>(r + ((0 ^ sw) << 4));
+            const int4 o1 = *reinterpret_cast<const int4*>(r + ((1 ^ sw) << 4));
+            const int4 o2 = *reinterpret_cast<const int4*>(r + ((2 ^ sw) << 4));
+            const float4 w0 = *reinterpret_cast<const float4*>(r + ((3 ^ sw) << 4));
+            const float4 w1 = *reinterpret_cast<const float4*>(r + ((4 ^ sw) << 4));
+            const float4 w2 = *reinterpret_cast<const float4*>(r + ((5 ^ sw) << 4));
+            const int bs = reinterpret_cast<const int4*>(r + ((6 ^ sw) << 4))->x;
+            const float* p0 = a.planes_nhwc + (size_t)bs * isz + lane;
+            const float* p1 = p0 + psz;
+            const float* p2 = p1 + psz;
+            const float v00 = __ldg(p0 + (size_t)o0.x * kC), v01 = __ldg(p0 + (size_t)o0.y * kC);
+            const float v02 = __ldg(p0 + (size_t)o0.z * kC), v03 = __ldg(p0 + (size_t)o0.w * kC);
+            const float v10 = __ldg(p1 + (size_t)o1.x * kC), v11 = __ldg(p1 + (size_t)o1.y * kC);
+            const float v12 = __ldg(p1 + (size_t)o1.z * kC), v13 = __ldg(p1 + (size_t)o1.w * kC);
+            const float v20 = __ldg(p2 + (size_t)o2.x * kC), v21 = __ldg(p2 + (size_t)o2.y * kC);
+            const float v22 = __ldg(p2 + (size_t)o2.z * kC), v23 = __ldg(p2 + (size_t)o2.w * kC);
+            const float f0 = fmaf(v03, w0.w, fmaf(v02, w0.z, fmaf(v01, w0.y, __fmul_rn(v00, w0.x))));
+            const float f1 = fmaf(v13, w1.w, fmaf(v12, w1.z, fmaf(v11, w1.y, __fmul_rn(v10, w1.x))));
+            const float f2 = fmaf(v23, w2.w, fmaf(v22, w2.z, fmaf(v21, w2.y, __fmul_rn(v20, w2.x))));
+            f = plane_mean(f0, f1, f2);
+        };
+        auto store = [&](int row, float f) {
             const __half hi = __float2half_rn(f), lo = __float2half_rn(f - __half2float(hi));
-            const int row = q * 32 + s;
             *reinterpret_cast<__half*>(tb + sw128(row, lane * 2)) = hi;
             *reinterpret_cast<__half*>(tb + sw128(row, 64 + lane * 2)) = lo;
+        };
+        while (active) {
+            const int s0 = __ffs(active) - 1;
+            active &= active - 1;
+            int s1 = -1;
+            if (active) { s1 = __ffs(active) - 1; active &= active - 1; }
+            float fa = 0.f, fb = 0.f;
+            fetch(q * 32 + s0, fa);
+            if (s1 >= 0) fetch(q * 32 + s1, fb);
+            __syncwarp();            // every lane has read the parked taps before the rows are overwritten
+            store(q * 32 + s0, fa);
+            if (s1 >= 0) store(q * 32 + s1, fb);
         }
     };
     // sigma of this thread's row after layer 1 of the sigma net landed in D1[:, 0:64)

@@ -129,59 +129,87 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
                                                            int B, int inH, int inW, int outH, int outW, int C, int padx0,
                                                            int pady0, float fir_gain, int act, float alpha, float act_gain,
                                                            float clamp) {
-    float ft[4][4];   // mirrored taps: true convolution (upfirdn2d default flip_filter=False)
+    // Each thread produces a 2x2 block of output pixels for VEC channels: the 5x5 input window is streamed row by
+    // row (25 vector loads for 4 outputs instead of 64), taps are mirrored (true convolution, flip_filter=False).
+    float ft[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) ft[j][i] = __ldg(f + (3 - j) * 4 + (3 - i));
     const int cg = C / VEC;
-    const int64_t total = (int64_t)B * outH * outW * cg;
+    const int bw = (outW + 1) >> 1, bh = (outH + 1) >> 1;
+    const int64_t total = (int64_t)B * bh * bw * cg;
     const bool round16 = (sizeof(TIn) == 2);   // fp16 pipeline rounds after the FIR and after the noise add
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cg) * VEC;
         int64_t t = idx / cg;
-        const int ox = (int)(t % outW); t /= outW;
-        const int oy = (int)(t % outH);
-        const int b = (int)(t / outH);
-        float acc[VEC];
+        const int ox = (int)(t % bw) * 2; t /= bw;
+        const int oy = (int)(t % bh) * 2;
+        const int b = (int)(t / bh);
+        float acc[2][2][VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[i][j][k] = 0.f;
         const TIn* xb = x + (size_t)b * inH * inW * C + c;
 #pragma unroll
-        for (int ty = 0; ty < 4; ++ty) {
-            const int iy = oy - pady0 + ty;
+        for (int r = 0; r < 5; ++r) {
+            const int iy = oy - pady0 + r;
             if (iy < 0 || iy >= inH) continue;
+            float v[5][VEC];
 #pragma unroll
-            for (int tx = 0; tx < 4; ++tx) {
-                const int ix = ox - padx0 + tx;
-                if (ix < 0 || ix >= inW) continue;
-                float v[VEC];
-                load_vec<TIn, VEC>(xb + ((size_t)iy * inW + ix) * C, v);
+            for (int cc = 0; cc < 5; ++cc) {
+                const int ix = ox - padx0 + cc;
+                if (ix >= 0 && ix < inW) {
+                    load_vec<TIn, VEC>(xb + ((size_t)iy * inW + ix) * C, v[cc]);
+                } else {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[k] = fmaf(ft[ty][tx], v[k], acc[k]);
+                    for (int k = 0; k < VEC; ++k) v[cc][k] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {          // output row oy + i uses filter row r - i
+                const int ty = r - i;
+                if (ty < 0 || ty > 3) continue;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int tx = 0; tx < 4; ++tx)
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc[i][j][k] = fmaf(ft[ty][tx], v[tx + j][k], acc[i][j][k]);
             }
         }
-        const float nz = noise ? __ldg(noise + (size_t)oy * outW + ox) : 0.f;
-        const size_t o = (((size_t)b * outH + oy) * outW + ox) * C + c;
-        __align__(16) __half hv[VEC], lv[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            float v = acc[k] * fir_gain;
-            if (round16) v = __half2float(__float2half_rn(v));
-            v += nz;
-            if (round16 && noise) v = __half2float(__float2half_rn(v));
-            if (bias) v += __ldg(bias + c + k);
-            if (act == 3) v = v > 0.f ? v : v * alpha;
-            v *= act_gain;
-            if (clamp >= 0.f) v = fminf(fmaxf(v, -clamp), clamp);
-            split_half(v, hv[k], lv[k]);
-        }
-        if (VEC == 8) {
-            *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
-            if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
-        } else {
-            *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
-            if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int py = oy + i, px = ox + j;
+                if (py >= outH || px >= outW) continue;
+                const float nz = noise ? __ldg(noise + (size_t)py * outW + px) : 0.f;
+                const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
+                __align__(16) __half hv[VEC], lv[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    float val = acc[i][j][k] * fir_gain;
+                    if (round16) val = __half2float(__float2half_rn(val));
+                    val += nz;
+                    if (round16 && noise) val = __half2float(__float2half_rn(val));
+                    if (bias) val += __ldg(bias + c + k);
+                    if (act == 3) val = val > 0.f ? val : val * alpha;
+                    val *= act_gain;
+                    if (clamp >= 0.f) val = fminf(fmaxf(val, -clamp), clamp);
+                    split_half(val, hv[k], lv[k]);
+                }
+                if (VEC == 8) {
+                    *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
+                    if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
+                } else {
+                    *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
+                    if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
+                }
+            }
         }
     }
 }
@@ -269,13 +297,13 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
     const size_t ps = (size_t)B * outH * outW * C;
     if (in_dtype == P3D_F32) {
         if (C % 4) return P3D_UNSUPPORTED;
-        int64_t items = (int64_t)B * outH * outW * (C / 4);
+        int64_t items = (int64_t)B * ((outH + 1) / 2) * ((outW + 1) / 2) * (C / 4);
         fir_act_nhwc_kernel<float, 4><<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(
             (const float*)x, f, noise, bias, (__half*)y, out_planes, ps, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
             alpha, act_gain, clamp);
     } else if (in_dtype == P3D_F16) {
         if (C % 8) return P3D_UNSUPPORTED;
-        int64_t items = (int64_t)B * outH * outW * (C / 8);
+        int64_t items = (int64_t)B * ((outH + 1) / 2) * ((outW + 1) / 2) * (C / 8);
         fir_act_nhwc_kernel<__half, 8><<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(
             (const __half*)x, f, noise, bias, (__half*)y, out_planes, ps, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
             alpha, act_gain, clamp);
