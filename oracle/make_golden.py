@@ -205,6 +205,22 @@ def golden_ops():
                                                flip_weight=False, fused_modconv=fused)
         save[f'mc_plain_{t}'] = modulated_conv2d(xc.clone(), w3, st, noise=nz[:, :, :8, :8], padding=1, fused_modconv=fused)
         save[f'mc_torgb_{t}'] = modulated_conv2d(xc.clone(), w1, st, demodulate=False, fused_modconv=fused)
+    # filtered_lrelu (generic composition path of the reference, filtered_lrelu.py:123-155)
+    from torch_utils.ops import filtered_lrelu
+    xf = torch.randn(2, 4, 12, 12, generator=g)
+    bf = torch.randn(4, generator=g)
+    fd3 = upfirdn2d.setup_filter([1, 2, 1])
+    save.update(fl_x=xf, fl_b=bf, fl_fd=fd3)
+    save['fl_up2_down2'] = filtered_lrelu.filtered_lrelu(xf, f4, fd3, bf, up=2, down=2, padding=[3, 2, 3, 2], clamp=0.8, impl='ref')
+    save['fl_up1'] = filtered_lrelu.filtered_lrelu(xf, None, f4, bf, up=1, down=1, padding=2, gain=1.3, slope=0.1, impl='ref')
+    # DualDiscriminator forward (config-5 component), weights from the seed
+    import training.dual_discriminator as dd
+    torch.manual_seed(31)
+    D = dd.DualDiscriminator(c_dim=25, img_resolution=64, img_channels=3, channel_base=1024, channel_max=32,
+                             mapping_kwargs={}, epilogue_kwargs={'mbstd_group_size': 2}).eval().requires_grad_(False)
+    img = {'image': torch.randn(2, 3, 64, 64, generator=g), 'image_raw': torch.randn(2, 3, 16, 16, generator=g)}
+    cc = torch.randn(2, 25, generator=g)
+    save.update(dd_image=img['image'], dd_image_raw=img['image_raw'], dd_c=cc, dd_logits=D(img, cc.clone()))
     np.savez_compressed(os.path.join(OUT, 'ops.npz'), **{k: v.detach().numpy() for k, v in save.items()})
     print('ops', len(save), 'arrays')
 

@@ -394,3 +394,14 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     if noise is not None:
         y = y + np.asarray(noise, f32)
     return y.astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------
+# filtered_lrelu.py:123-155 (generic composition)
+# ---------------------------------------------------------------------------------------------
+def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=_SQ2, slope=0.2, clamp=None, flip_filter=False):
+    px0, px1, py0, py1 = _pad4(padding)
+    x = bias_act(x, b)
+    x = upfirdn2d(x, fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
+    x = bias_act(x, act='lrelu', alpha=slope, gain=gain, clamp=clamp)
+    return upfirdn2d(x, fd, down=down, flip_filter=flip_filter)

@@ -172,3 +172,29 @@ def test_fused_fir_bias_act_equals_composition():
         ref = ref.add_(noise)
         ref = bias_act.bias_act(ref, b, act='lrelu', clamp=256)
         assert rel_err(y.float().cpu().numpy(), ref.float().cpu().numpy()) < tol
+
+
+def test_filtered_lrelu_cuda_matches_oracle_and_reference():
+    from pix2pix3d_b200.torch_utils.ops import filtered_lrelu
+    g = load_golden('ops')
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    y = filtered_lrelu.filtered_lrelu(t('fl_x'), t('up_f4'), t('fl_fd'), t('fl_b'), up=2, down=2, padding=[3, 2, 3, 2], clamp=0.8)
+    assert rel_err(y.cpu().numpy(), g['fl_up2_down2']) < 2e-6
+    ref = O.ops.filtered_lrelu(g['fl_x'], g['up_f4'], g['fl_fd'], g['fl_b'], up=2, down=2, padding=[3, 2, 3, 2], clamp=0.8)
+    assert rel_err(y.cpu().numpy(), ref) < 2e-6
+    x = t('fl_x').double().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda a: filtered_lrelu.filtered_lrelu(a, t('up_f4'), t('fl_fd'), None, up=2, down=2, padding=[3, 2, 3, 2]), (x,))
+
+
+def test_dual_discriminator_cuda_forward():
+    from pix2pix3d_b200.training.dual_discriminator import DualDiscriminator
+    g = load_golden('ops')
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    torch.manual_seed(31)
+    D = DualDiscriminator(c_dim=25, img_resolution=64, img_channels=3, channel_base=1024, channel_max=32, mapping_kwargs={},
+                          epilogue_kwargs={'mbstd_group_size': 2}).eval().requires_grad_(False).cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        out = D({'image': t('dd_image'), 'image_raw': t('dd_image_raw')}, t('dd_c').clone(), force_fp32=True)
+    assert rel_err(out.cpu().numpy(), g['dd_logits']) < 1e-3

@@ -108,3 +108,17 @@ def test_ray_limits_box_matches_reference_semantics():
     assert abs(tmin[0].item() - 1.5) < 1e-5 and abs(tmax[0].item() - 2.5) < 1e-5
     assert tmin[1].item() == -1 and tmax[1].item() == -2
     assert tmin[2].item() == -1 and tmax[2].item() == -2
+
+
+def test_filtered_lrelu_and_dual_discriminator_match_reference():
+    from pix2pix3d_b200.torch_utils.ops import filtered_lrelu
+    from pix2pix3d_b200.training.dual_discriminator import DualDiscriminator
+    g = load_golden('ops')
+    t = lambda k: torch.from_numpy(g[k])
+    y = filtered_lrelu.filtered_lrelu(t('fl_x'), t('up_f4'), t('fl_fd'), t('fl_b'), up=2, down=2, padding=[3, 2, 3, 2], clamp=0.8)
+    assert rel_err(y.numpy(), g['fl_up2_down2']) < 1e-6
+    torch.manual_seed(31)
+    D = DualDiscriminator(c_dim=25, img_resolution=64, img_channels=3, channel_base=1024, channel_max=32, mapping_kwargs={},
+                          epilogue_kwargs={'mbstd_group_size': 2}).eval().requires_grad_(False)
+    out = D({'image': t('dd_image'), 'image_raw': t('dd_image_raw')}, t('dd_c').clone())
+    assert rel_err(out.numpy(), g['dd_logits']) < 1e-5

@@ -152,3 +152,11 @@ def test_generator_synthesis_matches_reference(name):
     for k in ('image_raw', 'image_depth', 'image', 'semantic_raw', 'semantic'):
         if 'out_' + k in g:
             assert rel_err(out[k], g['out_' + k]) < 1e-3, k
+
+
+def test_filtered_lrelu_composition():
+    g = load_golden('ops')
+    y = O.ops.filtered_lrelu(g['fl_x'], g['up_f4'], g['fl_fd'], g['fl_b'], up=2, down=2, padding=[3, 2, 3, 2], clamp=0.8)
+    assert y.shape == g['fl_up2_down2'].shape and rel_err(y, g['fl_up2_down2']) < 2e-6
+    y = O.ops.filtered_lrelu(g['fl_x'], None, g['up_f4'], g['fl_b'], up=1, down=1, padding=2, gain=1.3, slope=0.1)
+    assert rel_err(y, g['fl_up1']) < 2e-6
