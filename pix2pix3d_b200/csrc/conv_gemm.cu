@@ -13,6 +13,7 @@
 //   hi*hi + hi*lo + lo*hi, accumulated in the same fp32 TMEM tile (error ~2^-22, products are exact in fp32).
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2-5 = epilogue
 //   (tcgen05.ld -> scale/noise/bias/activation/clamp -> NHWC store). mbarrier ring of kStages smem stages.
+#include <stdlib.h>
 #include <string.h>
 #include "p3d_common.cuh"
 #include "tc05.cuh"
@@ -264,12 +265,17 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
     // operand reuse: up to 2 x 2 sub-tiles per CTA (A and B stages are shared by the accumulators), as long as the
     // grid still fills the machine; it halves the L2 -> shared-memory traffic per FLOP, which is what bounds this kernel
+    // (measured on B200, profiles/r01_conv_subtiles.md: 1x1 with two co-resident CTAs per SM beats 2x1 / 2x2 with one
+    //  CTA per SM by ~1.5x, because the second CTA hides the epilogue and the TMA latency; so 1x1 is the default and the
+    //  larger shapes stay selectable through P3D_CONV_MT / P3D_CONV_NT for experiments.)
     int MT = 1, NT = 1;
     {
+        const char* emt = getenv("P3D_CONV_MT");
+        const char* ent = getenv("P3D_CONV_NT");
         const long ctas1 = (long)ceil_div(p->gW, BW) * ceil_div(p->gH, BH) * ceil_div(p->Cout_padded, BN) * p->B;
         const int nsm = sm_count();
-        if (BN == 128 && p->Cout_padded >= 256 && ctas1 / 2 >= nsm) NT = 2;
-        if (2 * BH <= 256 && p->gH >= 2 * BH && ctas1 / (2 * NT) >= nsm) MT = 2;
+        if (ent && atoi(ent) == 2 && BN == 128 && p->Cout_padded >= 256 && ctas1 / 2 >= nsm) NT = 2;
+        if (emt && atoi(emt) == 2 && 2 * BH <= 256 && p->gH >= 2 * BH && ctas1 / (2 * NT) >= nsm) MT = 2;
     }
     const int K = p->n_kblocks * p->C;
     if (p->n_kblocks < 1) return P3D_BAD_ARG;

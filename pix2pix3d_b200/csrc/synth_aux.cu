@@ -122,6 +122,11 @@ __device__ __forceinline__ void load_vec<__half, 8>(const __half* p, float (&v)[
     for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
+// Shared-memory tiled version: a CTA produces an 8 x 16 pixel tile for a 128-byte channel block (64 fp16 or 32 fp32
+// channels). The (8+3) x (16+3) input halo is staged once with fully coalesced 16-byte loads (all issued up front),
+// then every thread computes a 2x2 output block for one 16-byte channel vector from 25 conflict-free LDS.128.
+constexpr int kFirTH = 8, kFirTW = 16, kFirIH = kFirTH + 3, kFirIW = kFirTW + 3;
+
 template <class TIn, int VEC>
 __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict__ x, const float* __restrict__ f,
                                                            const float* __restrict__ noise, const float* __restrict__ bias,
@@ -129,86 +134,94 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
                                                            int B, int inH, int inW, int outH, int outW, int C, int padx0,
                                                            int pady0, float fir_gain, int act, float alpha, float act_gain,
                                                            float clamp) {
-    // Each thread produces a 2x2 block of output pixels for VEC channels: the 5x5 input window is streamed row by
-    // row (25 vector loads for 4 outputs instead of 64), taps are mirrored (true convolution, flip_filter=False).
-    float ft[4][4];
+    __shared__ uint4 tile[kFirIH * kFirIW * 8];      // 209 pixels x 128 bytes
+    float ft[4][4];                                  // mirrored taps: true convolution (flip_filter=False)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) ft[j][i] = __ldg(f + (3 - j) * 4 + (3 - i));
-    const int cg = C / VEC;
-    const int bw = (outW + 1) >> 1, bh = (outH + 1) >> 1;
-    const int64_t total = (int64_t)B * bh * bw * cg;
-    const bool round16 = (sizeof(TIn) == 2);   // fp16 pipeline rounds after the FIR and after the noise add
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % cg) * VEC;
-        int64_t t = idx / cg;
-        const int ox = (int)(t % bw) * 2; t /= bw;
-        const int oy = (int)(t % bh) * 2;
-        const int b = (int)(t / bh);
-        float acc[2][2][VEC];
+    constexpr int CB = 8 * VEC;                      // channels per block (8 vectors of 16 bytes)
+    const int tiles_x = (outW + kFirTW - 1) / kFirTW;
+    const int tx0 = (blockIdx.x % tiles_x) * kFirTW, ty0 = (blockIdx.x / tiles_x) * kFirTH;
+    const int c0 = blockIdx.y * CB, b = blockIdx.z;
+    const bool round16 = (sizeof(TIn) == 2);
+    // ---- stage the input halo (zero outside the image) ----
+    const TIn* xb = x + (size_t)b * inH * inW * C + c0;
+    for (int i = threadIdx.x; i < kFirIH * kFirIW * 8; i += 256) {
+        const int v = i & 7, p = i >> 3;
+        const int iy = ty0 - pady0 + p / kFirIW, ix = tx0 - padx0 + p % kFirIW;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < inH && ix >= 0 && ix < inW)
+            val = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)iy * inW + ix) * C) + v);
+        tile[i] = val;
+    }
+    __syncthreads();
+    // ---- 2x2 outputs per thread ----
+    const int v = threadIdx.x & 7, blk = threadIdx.x >> 3;          // 32 blocks: 4 rows x 8 cols of 2x2
+    const int by = (blk >> 3) * 2, bx = (blk & 7) * 2;
+    float acc[2][2][VEC];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) acc[i][j][k] = 0.f;
-        const TIn* xb = x + (size_t)b * inH * inW * C + c;
+            for (int k = 0; k < VEC; ++k) acc[i][j][k] = 0.f;
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const int iy = oy - pady0 + r;
-            if (iy < 0 || iy >= inH) continue;
-            float v[5][VEC];
+    for (int r = 0; r < 5; ++r) {
+        float win[5][VEC];
 #pragma unroll
-            for (int cc = 0; cc < 5; ++cc) {
-                const int ix = ox - padx0 + cc;
-                if (ix >= 0 && ix < inW) {
-                    load_vec<TIn, VEC>(xb + ((size_t)iy * inW + ix) * C, v[cc]);
-                } else {
+        for (int cc = 0; cc < 5; ++cc) {
+            const uint4 raw = tile[((by + r) * kFirIW + bx + cc) * 8 + v];
+            if (sizeof(TIn) == 2) {
+                const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) v[cc][k] = 0.f;
-                }
-            }
+                for (int k = 0; k < VEC / 2; ++k) { float2 t = __half22float2(h[k]); win[cc][2 * k] = t.x; win[cc][2 * k + 1] = t.y; }
+            } else {
+                const float* fp = reinterpret_cast<const float*>(&raw);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {          // output row oy + i uses filter row r - i
-                const int ty = r - i;
-                if (ty < 0 || ty > 3) continue;
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int tx = 0; tx < 4; ++tx)
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) acc[i][j][k] = fmaf(ft[ty][tx], v[tx + j][k], acc[i][j][k]);
+                for (int k = 0; k < VEC; ++k) win[cc][k] = fp[k];
             }
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
+            const int ty = r - i;
+            if (ty < 0 || ty > 3) continue;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int py = oy + i, px = ox + j;
-                if (py >= outH || px >= outW) continue;
-                const float nz = noise ? __ldg(noise + (size_t)py * outW + px) : 0.f;
-                const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
-                __align__(16) __half hv[VEC], lv[VEC];
+            for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    float val = acc[i][j][k] * fir_gain;
-                    if (round16) val = __half2float(__float2half_rn(val));
-                    val += nz;
-                    if (round16 && noise) val = __half2float(__float2half_rn(val));
-                    if (bias) val += __ldg(bias + c + k);
-                    if (act == 3) val = val > 0.f ? val : val * alpha;
-                    val *= act_gain;
-                    if (clamp >= 0.f) val = fminf(fmaxf(val, -clamp), clamp);
-                    split_half(val, hv[k], lv[k]);
-                }
-                if (VEC == 8) {
-                    *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
-                    if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
-                } else {
-                    *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
-                    if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
-                }
+                for (int tx = 0; tx < 4; ++tx)
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) acc[i][j][k] = fmaf(ft[ty][tx], win[tx + j][k], acc[i][j][k]);
+        }
+    }
+    const int c = c0 + v * VEC;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int py = ty0 + by + i, px = tx0 + bx + j;
+            if (py >= outH || px >= outW) continue;
+            const float nz = noise ? __ldg(noise + (size_t)py * outW + px) : 0.f;
+            const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
+            __align__(16) __half hv[VEC], lv[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                float val = acc[i][j][k] * fir_gain;
+                if (round16) val = __half2float(__float2half_rn(val));
+                val += nz;
+                if (round16 && noise) val = __half2float(__float2half_rn(val));
+                if (bias) val += __ldg(bias + c + k);
+                if (act == 3) val = val > 0.f ? val : val * alpha;
+                val *= act_gain;
+                if (clamp >= 0.f) val = fminf(fmaxf(val, -clamp), clamp);
+                split_half(val, hv[k], lv[k]);
+            }
+            if (VEC == 8) {
+                *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
+                if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
+            } else {
+                *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
+                if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
             }
         }
     }
@@ -295,16 +308,18 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
     if (!x || !f || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
     if (act != 1 && act != 3) return P3D_UNSUPPORTED;
     const size_t ps = (size_t)B * outH * outW * C;
+    const int tiles = ceil_div(outW, kFirTW) * ceil_div(outH, kFirTH);
+    if (B > 65535) return P3D_UNSUPPORTED;
     if (in_dtype == P3D_F32) {
-        if (C % 4) return P3D_UNSUPPORTED;
-        int64_t items = (int64_t)B * ((outH + 1) / 2) * ((outW + 1) / 2) * (C / 4);
-        fir_act_nhwc_kernel<float, 4><<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(
+        if (C % 32) return P3D_UNSUPPORTED;
+        dim3 grid(tiles, C / 32, B);
+        fir_act_nhwc_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
             (const float*)x, f, noise, bias, (__half*)y, out_planes, ps, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
             alpha, act_gain, clamp);
     } else if (in_dtype == P3D_F16) {
-        if (C % 8) return P3D_UNSUPPORTED;
-        int64_t items = (int64_t)B * ((outH + 1) / 2) * ((outW + 1) / 2) * (C / 8);
-        fir_act_nhwc_kernel<__half, 8><<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(
+        if (C % 64) return P3D_UNSUPPORTED;
+        dim3 grid(tiles, C / 64, B);
+        fir_act_nhwc_kernel<__half, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
             (const __half*)x, f, noise, bias, (__half*)y, out_planes, ps, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
             alpha, act_gain, clamp);
     } else {

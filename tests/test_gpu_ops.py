@@ -35,7 +35,7 @@ def test_bias_act_forward_all_activations(dtype):
         assert torch.equal(yc.contiguous(), bias_act.bias_act(x, b, act=act))
     # bias along another dim, no bias, no-op
     y = bias_act.bias_act(x, torch.arange(6, device='cuda', dtype=dtype), dim=3, act='relu')
-    ref = O.ops.bias_act(x.double().cpu().numpy(), np.arange(6, dtype=np.float64), dim=3, act='relu')
+    ref = O.ops.bias_act(x.double().cpu().numpy(), np.arange(6, dtype=np.float64), dim=3, act='relu', gain=r32(np.sqrt(2)))
     assert rel_err(y.double().cpu().numpy(), ref) < max(tol, 1e-3 if dtype == torch.float16 else 0)
     assert bias_act.bias_act(x, None, act='linear', gain=1) is not None
 
