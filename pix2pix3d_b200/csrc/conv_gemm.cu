@@ -31,7 +31,6 @@ struct ConvKernelArgs {
     int Cin;
     // tiling
     int BW, BH, tiles_x, tiles_y, BN, w_per_sample;
-    int MT, NT;                       // 128-row sub-tiles per CTA along pixels / output channels (operand reuse in smem)
     uint32_t idesc, tmem_cols;
     // epilogue
     int gH, gW;                       // size of the computed grid (phase grid for transposed conv)
@@ -40,27 +39,55 @@ struct ConvKernelArgs {
     void* y; void* y_lo;
     int out_mode;                     // 0: f16, 1: f16 hi/lo split, 2: f32, 3: f32 accumulate (+=)
     const float* bias; const float* noise; const float* dscale;
-    int act; float alpha, gain, clamp, acc_scale;
+    float alpha, clamp, acc_scale;
+    int base_aligned;                 // y / y_lo are 32-byte aligned (256-bit stores allowed)
+    float pre_gain, post_gain;        // gain folded into scale/bias/noise (lrelu is positively homogeneous) or applied last
 };
 
-template <int kStages>
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+
+// kAct: 0 linear, 1 leaky-relu with 0 <= alpha <= 1 (max form), 2 leaky-relu, any alpha (select form)
+template <int kAct, bool kClamp>
+__device__ __forceinline__ float conv_epilogue_act(float x, float alpha, float post_gain, float clamp) {
+    if (kAct == 1) x = fmaxf(x, x * alpha);
+    if (kAct == 2) x = x > 0.f ? x : x * alpha;
+    x *= post_gain;                                   // 1.0 when the gain was folded (always, for gain > 0)
+    if (kClamp) x = fminf(fmaxf(x, -clamp), clamp);
+    return x;
+}
+
+template <int kStages, int kAct, bool kClamp>
 __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const ConvKernelArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages][A 16 KB][B BN*128 B] | barriers | tmem ptr
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = (uint32_t)a.MT * kBM * 128, b_bytes = (uint32_t)a.NT * a.BN * 128;
+    // carve: [stages][A 16 KB][B BN*128 B] | barriers | tmem ptr | per-channel scale, bias
+    // round up inside the shared window (pointer arithmetic on smem_raw keeps the address space known to the compiler)
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t a_bytes = (uint32_t)kBM * 128, b_bytes = (uint32_t)a.BN * 128;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* s_scale = reinterpret_cast<float*>(smem + kStages * stage_bytes + (((2 * kStages + 1) * 8 + 4 + 15) & ~15));
+    float* s_bias = s_scale + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x, tile_n = blockIdx.y, b = blockIdx.z;
     const int ty = tile_m / a.tiles_x, tx = tile_m % a.tiles_x;
-    const int n0 = tile_n * a.BN * a.NT;
+    const int n0 = tile_n * a.BN;
     const int total_k = a.n_groups * a.kc_steps;
 
     if (warp == 0 && lane == 0) {
@@ -71,6 +98,22 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, a.tmem_cols);
+    if (warp >= 2) {
+        // per-channel epilogue constants: accumulator scale (1/weight scale x demodulation x gain) and bias x gain; channels
+        // beyond Cout get zeros so the hot loop needs no channel predicate
+        const int i = threadIdx.x - 64;
+        if (i < a.BN) {
+            const int ch = n0 + i;
+            float sc = 0.f, bi = 0.f;
+            if (ch < a.Cout) {
+                sc = a.acc_scale * a.pre_gain;
+                if (a.dscale) sc *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
+                if (a.bias) bi = __ldg(a.bias + ch) * a.pre_gain;
+            }
+            s_scale[i] = sc;
+            s_bias[i] = bi;
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -81,7 +124,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int g = 0; g < a.n_groups; ++g) {
-                const int x0 = tx * a.BW + a.dx[g], y0 = ty * a.BH * a.MT + a.dy[g];
+                const int x0 = tx * a.BW + a.dx[g], y0 = ty * a.BH + a.dy[g];
                 const int kb = a.tap[g] * a.Cin;
                 for (int kc = 0; kc < a.kc_steps; ++kc) {
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -103,101 +146,106 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
                 tc::tc_fence_after();
                 const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
                 const uint64_t da = tc::umma_desc_k128(sa), db = tc::umma_desc_k128(sa + a_bytes);
-                // every (pixel sub-tile, channel sub-tile) pair has its own 128-column accumulator; operands are shared
-                for (int mt = 0; mt < a.MT; ++mt)
-                    for (int nt = 0; nt < a.NT; ++nt) {
-                        const uint64_t dam = da + (uint64_t)(mt * (kBM * 128 >> 4)), dbn = db + (uint64_t)(nt * (a.BN * 128 >> 4));
-                        const uint32_t acc = tmem_base + (uint32_t)((mt * a.NT + nt) * 128);
 #pragma unroll
-                        for (int j = 0; j < kBK / 16; ++j)   // 4 MMAs of K=16: advance 32 bytes inside the swizzle span
-                            tc::umma_f16(acc, dam + (uint64_t)(j * 2), dbn + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
-                    }
+                for (int j = 0; j < kBK / 16; ++j)   // 4 MMAs of K=16: advance 32 bytes inside the swizzle span
+                    tc::umma_f16(tmem_base, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
                 tc::umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
                 if (k == total_k - 1) tc::umma_commit(tmem_full_bar);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4); thread = pixel, 32 channels per TMEM load =====
         const int q = warp & 3;
         const int m = q * 32 + lane;                    // tile row = TMEM lane
-        tc::mbar_wait(tmem_full_bar, 0);
-        tc::tc_fence_after();
-        for (int mt = 0; mt < a.MT; ++mt) {
-        const int gy = (ty * a.MT + mt) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
+        const int gy = ty * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
         const bool pix_ok = (gy < a.gH) && (gx < a.gW);
         const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
         const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
-        const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) : 0.f;
-        for (int nt = 0; nt < a.NT; ++nt)
+        const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+        const float alpha = a.alpha, post_gain = a.post_gain, clampv = a.clamp;
+        const int out_mode = a.out_mode;
+        // vector path: every 32-channel chunk of this CTA is full and its stores are 32-byte aligned
+        const bool vec_ok = a.base_aligned && ((n0 + a.BN) <= a.Cout) && (a.BN % 32 == 0) &&
+                            (out_mode <= 1 ? ((a.y_cstride % 16) == 0 && ((a.y_coff + n0) % 16) == 0)
+                                           : ((a.y_cstride % 8) == 0 && ((a.y_coff + n0) % 8) == 0));
+        tc::mbar_wait(tmem_full_bar, 0);
+        tc::tc_fence_after();
         for (int c0 = 0; c0 < a.BN; c0 += 32) {
             uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((mt * a.NT + nt) * 128 + c0), v);
+            tc::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tc::tmem_ld_wait();
             if (!pix_ok) continue;
-            const int ch0 = n0 + nt * a.BN + c0;
+            const int ch0 = n0 + c0;
             if (ch0 >= a.Cout) continue;
-            float r[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int ch = ch0 + i;
-                float x = __uint_as_float(v[i]) * a.acc_scale;
-                if (ch < a.Cout) {
-                    if (a.dscale) x *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
-                    x += nz;
-                    if (a.bias) x += __ldg(a.bias + ch);
-                    if (a.act == 3) x = x > 0.f ? x : x * a.alpha;
-                    x *= a.gain;
-                    if (a.clamp >= 0.f) x = fminf(fmaxf(x, -a.clamp), a.clamp);
-                } else {
-                    x = 0.f;
-                }
-                r[i] = x;
-            }
-            const int nvalid = min(32, a.Cout - ch0);
             const size_t off = pix * a.y_cstride + a.y_coff + ch0;
-            if (a.out_mode == 0 || a.out_mode == 1) {
-                __half* yh = reinterpret_cast<__half*>(a.y) + off;
-                __half* yl = a.out_mode == 1 ? reinterpret_cast<__half*>(a.y_lo) + off : nullptr;
-                if (nvalid == 32) {
+            if (vec_ok) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        __align__(16) __half2 hv[4], lv[4];
+                for (int j = 0; j < 2; ++j) {           // 16 channels per step
+                    float r[16];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            float f0 = r[j * 8 + 2 * t], f1 = r[j * 8 + 2 * t + 1];
-                            __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
-                            hv[t] = __halves2half2(h0, h1);
-                            lv[t] = __halves2half2(__float2half_rn(f0 - __half2float(h0)), __float2half_rn(f1 - __half2float(h1)));
-                        }
-                        *reinterpret_cast<uint4*>(yh + j * 8) = *reinterpret_cast<uint4*>(hv);
-                        if (yl) *reinterpret_cast<uint4*>(yl + j * 8) = *reinterpret_cast<uint4*>(lv);
+                    for (int t4 = 0; t4 < 4; ++t4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 16 * j + 4 * t4);
+                        const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + 16 * j + 4 * t4);
+                        const uint32_t* vv = v + 16 * j + 4 * t4;
+                        r[4 * t4 + 0] = fmaf(__uint_as_float(vv[0]), sc.x, bi.x) + nz;
+                        r[4 * t4 + 1] = fmaf(__uint_as_float(vv[1]), sc.y, bi.y) + nz;
+                        r[4 * t4 + 2] = fmaf(__uint_as_float(vv[2]), sc.z, bi.z) + nz;
+                        r[4 * t4 + 3] = fmaf(__uint_as_float(vv[3]), sc.w, bi.w) + nz;
                     }
-                } else {
-                    for (int i = 0; i < nvalid; ++i) {
-                        __half h = __float2half_rn(r[i]);
-                        yh[i] = h;
-                        if (yl) yl[i] = __float2half_rn(r[i] - __half2float(h));
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) r[t] = conv_epilogue_act<kAct, kClamp>(r[t], alpha, post_gain, clampv);
+                    if (out_mode >= 2) {
+                        float* yp = reinterpret_cast<float*>(a.y) + off + 16 * j;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t o[8];
+                            if (out_mode == 3) {
+                                ld_global_256(yp + 8 * h, o);
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) + r[8 * h + t]);
+                            } else {
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(r[8 * h + t]);
+                            }
+                            st_global_256(yp + 8 * h, o);
+                        }
+                    } else {
+                        uint32_t oh[8], ol[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const __half2 hv = __floats2half2_rn(r[2 * t], r[2 * t + 1]);
+                            oh[t] = *reinterpret_cast<const uint32_t*>(&hv);
+                            if (out_mode == 1) {
+                                const float2 back = __half22float2(hv);
+                                const __half2 lv = __floats2half2_rn(r[2 * t] - back.x, r[2 * t + 1] - back.y);
+                                ol[t] = *reinterpret_cast<const uint32_t*>(&lv);
+                            }
+                        }
+                        st_global_256(reinterpret_cast<__half*>(a.y) + off + 16 * j, oh);
+                        if (out_mode == 1) st_global_256(reinterpret_cast<__half*>(a.y_lo) + off + 16 * j, ol);
                     }
                 }
             } else {
-                float* yf = reinterpret_cast<float*>(a.y) + off;
-                if (nvalid == 32 && (a.y_cstride & 3) == 0 && ((a.y_coff + ch0) & 3) == 0) {
+                // ragged chunk (ToRGB's 3 channels, channel tails, unaligned concat offsets): scalar stores
+                const int nvalid = min(32, a.Cout - ch0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-                        if (a.out_mode == 3) {
-                            float4 p = *reinterpret_cast<float4*>(yf + 4 * j);
-                            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+                for (int i = 0; i < 32; ++i) {
+                    if (i < nvalid) {
+                        const float x = conv_epilogue_act<kAct, kClamp>(
+                            fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_bias[c0 + i]) + nz, alpha, post_gain, clampv);
+                        if (out_mode <= 1) {
+                            const __half h = __float2half_rn(x);
+                            reinterpret_cast<__half*>(a.y)[off + i] = h;
+                            if (out_mode == 1) reinterpret_cast<__half*>(a.y_lo)[off + i] = __float2half_rn(x - __half2float(h));
+                        } else {
+                            float* yf = reinterpret_cast<float*>(a.y) + off + i;
+                            *yf = (out_mode == 3 ? *yf : 0.f) + x;
                         }
-                        *reinterpret_cast<float4*>(yf + 4 * j) = o;
                     }
-                } else {
-                    for (int i = 0; i < nvalid; ++i) yf[i] = (a.out_mode == 3 ? yf[i] : 0.f) + r[i];
                 }
             }
         }
-        }   // mt
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -263,20 +311,6 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     }
     const int BH = kBM / BW;
     const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
-    // operand reuse: up to 2 x 2 sub-tiles per CTA (A and B stages are shared by the accumulators), as long as the
-    // grid still fills the machine; it halves the L2 -> shared-memory traffic per FLOP, which is what bounds this kernel
-    // (measured on B200, profiles/r01_conv_subtiles.md: 1x1 with two co-resident CTAs per SM beats 2x1 / 2x2 with one
-    //  CTA per SM by ~1.5x, because the second CTA hides the epilogue and the TMA latency; so 1x1 is the default and the
-    //  larger shapes stay selectable through P3D_CONV_MT / P3D_CONV_NT for experiments.)
-    int MT = 1, NT = 1;
-    {
-        const char* emt = getenv("P3D_CONV_MT");
-        const char* ent = getenv("P3D_CONV_NT");
-        const long ctas1 = (long)ceil_div(p->gW, BW) * ceil_div(p->gH, BH) * ceil_div(p->Cout_padded, BN) * p->B;
-        const int nsm = sm_count();
-        if (ent && atoi(ent) == 2 && BN == 128 && p->Cout_padded >= 256 && ctas1 / 2 >= nsm) NT = 2;
-        if (emt && atoi(emt) == 2 && 2 * BH <= 256 && p->gH >= 2 * BH && ctas1 / (2 * NT) >= nsm) MT = 2;
-    }
     const int K = p->n_kblocks * p->C;
     if (p->n_kblocks < 1) return P3D_BAD_ARG;
 
@@ -285,14 +319,14 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)p->x_planes};
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
-        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)(BH * MT), 1, 1};
+        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)BH, 1, 1};
         int rc = make_tmap(&tmA, p->x, 5, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)p->Cout_padded, (uint64_t)p->Bw, (uint64_t)p->w_planes};
         uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)p->Cout_padded * K * 2, (uint64_t)p->Bw * p->Cout_padded * K * 2};
-        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(BN * NT), 1, 1};
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
         int rc = make_tmap(&tmB, p->w, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
@@ -312,23 +346,39 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.kc_steps = p->C / kBK;
     a.Cin = p->C;
     a.BW = BW; a.BH = BH;
-    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, BH * MT);
-    a.MT = MT; a.NT = NT;
+    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, BH);
     a.BN = BN; a.w_per_sample = p->Bw > 1 ? 1 : 0;
     a.idesc = tc::umma_idesc_f16(kBM, BN, 0);
-    a.tmem_cols = (MT * NT > 1) ? (uint32_t)(MT * NT * 128) : (BN <= 32 ? 32u : BN <= 64 ? 64u : 128u);
-    if (a.tmem_cols == 384) a.tmem_cols = 512;
+    a.tmem_cols = BN <= 32 ? 32u : BN <= 64 ? 64u : 128u;
     a.gH = p->gH; a.gW = p->gW; a.oH = p->oH; a.oW = p->oW; a.sy = p->sy; a.oy = p->oy; a.sx = p->sx; a.ox = p->ox;
     a.Cout = p->Cout; a.y_cstride = p->y_cstride; a.y_coff = p->y_coff;
     a.y = p->y; a.y_lo = p->y_lo; a.out_mode = p->out_mode;
     a.bias = p->bias; a.noise = p->noise; a.dscale = p->dscale;
-    a.act = p->act; a.alpha = p->alpha; a.gain = p->gain; a.clamp = p->clamp; a.acc_scale = p->acc_scale;
+    a.alpha = p->alpha; a.clamp = p->clamp; a.acc_scale = p->acc_scale;
+    a.base_aligned = ((((uintptr_t)p->y) | ((uintptr_t)p->y_lo)) & 31) == 0;
+    // act(x) * gain == act(x * gain) for gain > 0 (linear and leaky-relu are positively homogeneous): fold the gain into the
+    // per-channel scale / bias / noise so the per-element epilogue is fma + add + max (+ clamp)
+    const bool fold = p->gain > 0.f;
+    a.pre_gain = fold ? p->gain : 1.f;
+    a.post_gain = fold ? 1.f : p->gain;
+    if (p->act != 1 && p->act != 3) return P3D_UNSUPPORTED;
+    const int act = p->act == 1 ? 0 : (p->alpha >= 0.f && p->alpha <= 1.f ? 1 : 2);
+    const bool clamp = p->clamp >= 0.f;
 
-    constexpr int kStages = 3;   // 3 stages: with 1x1 sub-tiles (96 KB) two CTAs per SM overlap epilogue and MMA phases
-    const size_t smem = (size_t)kStages * ((size_t)MT * kBM * 128 + (size_t)NT * BN * 128) + (2 * kStages + 1) * 8 + 16 + 1024;
-    P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN * NT), p->B);
-    conv_gemm_kernel<kStages><<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, a);
+    // 3 stages (96 KB at BN = 128): two CTAs per SM, so one tile's epilogue / TMA latency hides behind the other's MMAs
+    constexpr int kStages = 3;
+    const size_t smem = (size_t)kStages * ((size_t)kBM * 128 + (size_t)BN * 128) + 64 + 2 * 128 * sizeof(float) + 1024;
+    dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
+#define P3D_LAUNCH_CONV(ACT, CL)                                                                                              \
+    do {                                                                                                                      \
+        P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kStages, ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                          (int)smem));                                                                        \
+        conv_gemm_kernel<kStages, ACT, CL><<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, a);                           \
+    } while (0)
+    if (act == 0) { if (clamp) P3D_LAUNCH_CONV(0, true); else P3D_LAUNCH_CONV(0, false); }
+    else if (act == 1) { if (clamp) P3D_LAUNCH_CONV(1, true); else P3D_LAUNCH_CONV(1, false); }
+    else { if (clamp) P3D_LAUNCH_CONV(2, true); else P3D_LAUNCH_CONV(2, false); }
+#undef P3D_LAUNCH_CONV
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

@@ -117,7 +117,8 @@ constexpr int kTcColsPerGroup = 160;   // D1: [0,128)  D2: [128,160)
 
 __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRenderParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // round up inside the shared window (pointer arithmetic on smem_raw keeps the address space known to the compiler)
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const p3d_render_args_t& a = P.a;
     const TcLayout& L = P.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kTcThreads >> 5;
