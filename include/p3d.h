@@ -77,7 +77,7 @@ int p3d_pack_decoder(const p3d_decoder_t* dec, float* packed, p3d_stream_t strea
 
 typedef struct {
     /* inputs */
-    const float* planes_nhwc;    /* [B,3,H,W,32] fp32 */
+    const float* planes_nhwc;    /* [B,3,H,W,32] fp32 (dense), or any layout with 32 contiguous channels described by plane_strides */
     const float* ray_origins;    /* [B,R,3] */
     const float* ray_dirs;       /* [B,R,3] */
     const float* depths_coarse;  /* [B,R,Sc]  (sample_stratified output, renderer.py:169-192) */
@@ -100,6 +100,10 @@ typedef struct {
     float*   dbg_weights_final;  /* [B,R,Sc+Sf-1] */
     /* scratch: 4 x uint32, zeroed by the callee on the stream before launch */
     uint32_t* workspace;
+    /* element strides {image, plane, pixel} of planes_nhwc; rows are W pixels apart. All zero = dense [B,3,H,W,32].
+     * {H*W*96, 32, 96} reads the backbone's NHWC [B,H,W,96] output in place (p3d_render_fwd_tc only; p3d_render_fwd
+     * returns P3D_UNSUPPORTED for non-dense planes). */
+    int64_t plane_strides[3];
 } p3d_render_args_t;
 
 /* ImportanceRenderer.forward for scalar ray limits -- training/volumetric_rendering/renderer.py:88-140:
@@ -209,6 +213,14 @@ int p3d_conv_gemm(const p3d_conv_args_t* args, p3d_stream_t stream);
 int p3d_modulate_weights(const float* weight, const float* styles, int B, int Cout, int Cin, int ktaps,
                          int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
                          float out_scale, int planes, void* out, p3d_stream_t stream);
+
+/* Every style affine of a synthesis stack in one launch (layer.affine(w) of SynthesisLayer.forward / ToRGBLayer.forward,
+ * networks_stylegan2.py:313-315, 354-355; FullyConnectedLayer.forward :111-123 with the weight and bias gains already
+ * applied by the caller): for each row r of weight [rows, w_dim],
+ *   out[meta[r].out_off + b * meta[r].out_stride] = bias[r] + dot(ws[b, meta[r].ws_index, :], weight[r, :]).
+ * meta: int32 [rows][4] = {ws_index, out_off, out_stride, 0}; ws: [B, num_ws, w_dim] fp32. */
+int p3d_affine_batch(const float* ws, const float* weight, const float* bias, const int32_t* meta, float* out,
+                     int B, int num_ws, int w_dim, int rows, p3d_stream_t stream);
 
 /* Layout / precision converters between the reference's NCHW tensors and the NHWC fp16 tensors of this path. */
 int p3d_nchw_to_nhwc_f16(const void* x, int src_dtype, int N, int C, int H, int W, int C_padded, int planes,

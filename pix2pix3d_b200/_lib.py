@@ -40,6 +40,7 @@ class RenderArgs(ctypes.Structure):  # p3d_render_args_t
         ('dbg_weights_coarse', c_void_p), ('dbg_depths_fine', c_void_p), ('dbg_inds', c_void_p),
         ('dbg_perm', c_void_p), ('dbg_weights_final', c_void_p),
         ('workspace', c_void_p),
+        ('plane_strides', ctypes.c_int64 * 3),
     ]
 
 
@@ -68,6 +69,7 @@ _SIGNATURES = {
                                  ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), c_int, c_int, c_int, c_int, c_float,
                                  c_int, c_float, c_float, c_float, c_int64, c_void_p]),
     'p3d_conv_gemm': (c_int, [c_void_p, c_void_p]),
+    'p3d_affine_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'p3d_modulate_weights': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                      c_int, c_void_p, c_void_p]),
     'p3d_nchw_to_nhwc_f16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -17,6 +17,7 @@
 #include <string.h>
 #include "p3d_common.cuh"
 #include "tc05.cuh"
+#include "tmap.cuh"
 
 namespace p3d {
 
@@ -258,32 +259,9 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-static int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return P3D_UNSUPPORTED;
-    cuuint64_t gdim[5], gstr[4];
-    cuuint32_t bx[5], es[5];
-    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
-    for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? P3D_OK : P3D_BAD_ARG;
+static int make_tmap_f16_sw128(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                               const uint32_t* box) {
+    return make_tmap(tm, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, rank, dims, strides_bytes, box);
 }
 
 }  // namespace p3d
@@ -320,14 +298,14 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
         uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)BH, 1, 1};
-        int rc = make_tmap(&tmA, p->x, 5, dims, str, box);
+        int rc = make_tmap_f16_sw128(&tmA, p->x, 5, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)p->Cout_padded, (uint64_t)p->Bw, (uint64_t)p->w_planes};
         uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)p->Cout_padded * K * 2, (uint64_t)p->Bw * p->Cout_padded * K * 2};
         uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
-        int rc = make_tmap(&tmB, p->w, 4, dims, str, box);
+        int rc = make_tmap_f16_sw128(&tmB, p->w, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
 
@@ -365,19 +343,25 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     const int act = p->act == 1 ? 0 : (p->alpha >= 0.f && p->alpha <= 1.f ? 1 : 2);
     const bool clamp = p->clamp >= 0.f;
 
-    // 3 stages (96 KB at BN = 128): two CTAs per SM, so one tile's epilogue / TMA latency hides behind the other's MMAs
-    constexpr int kStages = 3;
-    const size_t smem = (size_t)kStages * ((size_t)kBM * 128 + (size_t)BN * 128) + 64 + 2 * 128 * sizeof(float) + 1024;
+    // 3 stages (96 KB at BN = 128): two CTAs per SM, so one tile's epilogue / TMA latency hides behind the other's MMAs.
+    // Grids that leave at most one CTA per SM anyway (the 4^2..32^2 backbone layers: 16-128 CTAs with 200+ k-steps each)
+    // are bound by TMA latency x bytes in flight instead; they get a 6-stage ring (192 KB).
     dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
-#define P3D_LAUNCH_CONV(ACT, CL)                                                                                              \
+    const bool deep = (long)grid.x * grid.y * grid.z <= sm_count() && a.n_groups * a.kc_steps > 6;
+    const size_t stage_bytes = (size_t)kBM * 128 + (size_t)BN * 128;
+    const size_t smem = (deep ? 6 : 3) * stage_bytes + 64 + 2 * 128 * sizeof(float) + 1024 + (deep ? 64 : 0);
+#define P3D_LAUNCH_CONV_S(ST, ACT, CL)                                                                                        \
     do {                                                                                                                      \
-        P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<kStages, ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+        P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<ST, ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                           (int)smem));                                                                        \
-        conv_gemm_kernel<kStages, ACT, CL><<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, a);                           \
+        conv_gemm_kernel<ST, ACT, CL><<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, a);                                \
     } while (0)
+#define P3D_LAUNCH_CONV(ACT, CL)                                                                                              \
+    do { if (deep) P3D_LAUNCH_CONV_S(6, ACT, CL); else P3D_LAUNCH_CONV_S(3, ACT, CL); } while (0)
     if (act == 0) { if (clamp) P3D_LAUNCH_CONV(0, true); else P3D_LAUNCH_CONV(0, false); }
     else if (act == 1) { if (clamp) P3D_LAUNCH_CONV(1, true); else P3D_LAUNCH_CONV(1, false); }
     else { if (clamp) P3D_LAUNCH_CONV(2, true); else P3D_LAUNCH_CONV(2, false); }
+#undef P3D_LAUNCH_CONV_S
 #undef P3D_LAUNCH_CONV
     P3D_LAUNCH_CHECK();
     return P3D_OK;

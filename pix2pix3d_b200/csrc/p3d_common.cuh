@@ -43,15 +43,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// log(1 + exp(x)); agrees with F.softplus(beta=1, threshold=20) to ~1.5e-7 absolute.
+// MUFU approximations without the denormal pre/post-scaling nvcc wraps around __expf/__logf/__fdividef (their
+// arguments here never need it: exp(-|x|) <= 1 may flush to 0, 1+u is in [1,2], 1+exp(-x) >= 1)
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// log(1 + exp(x)) = max(x,0) + ln2 * log2(1 + 2^(-|x| log2 e)); agrees with F.softplus(beta=1, threshold=20) to
+// ~1.5e-7 absolute.
 __device__ __forceinline__ float softplus_f(float x) {
-    float u = __expf(-fabsf(x));
-    return fmaxf(x, 0.f) + __logf(1.f + u);
+    const float u = ex2_ftz(-fabsf(x) * 1.4426950408889634f);
+    return fmaf(lg2_ftz(1.f + u), 0.6931471805599453f, fmaxf(x, 0.f));
 }
 
 // sigmoid(x) * (1 + 2*0.001) - 0.001  (training/triplane.py:133)
 __device__ __forceinline__ float sigmoid_clamp_f(float x) {
-    float s = __fdividef(1.f, 1.f + __expf(-x));
+    const float s = rcp_ftz(1.f + ex2_ftz(x * -1.4426950408889634f));
     return fmaf(s, 1.002f, -0.001f);
 }
 

@@ -758,6 +758,10 @@ int p3d_render_fwd(const p3d_render_args_t* args, p3d_stream_t stream) {
     if (!a.planes_nhwc || !a.ray_origins || !a.ray_dirs || !a.depths_coarse || !a.decoder_packed || !a.out_feat ||
         !a.out_depth || !a.out_wsum || !a.workspace)
         return P3D_BAD_ARG;
+    if (a.plane_strides[0] || a.plane_strides[1] || a.plane_strides[2]) {
+        const int64_t psz = (int64_t)a.H * a.W * kC;
+        if (a.plane_strides[0] != 3 * psz || a.plane_strides[1] != psz || a.plane_strides[2] != kC) return P3D_UNSUPPORTED;
+    }
     if (a.B <= 0 || a.R <= 0 || a.H <= 0 || a.W <= 0 || a.Sc < 2 || a.Sf < 0) return P3D_BAD_ARG;
     if (a.Sf > 0 && (!a.u_importance || a.Sc < 4)) return P3D_BAD_ARG;
     if (a.n_nets < 1 || a.n_nets > 2 || a.sigma_net < 0 || a.sigma_net >= a.n_nets) return P3D_BAD_ARG;

@@ -40,7 +40,7 @@ __global__ void pack_decoder_tc_kernel(PackTcArgs a, uint8_t* __restrict__ out) 
     // layer 1: row n = net*64 + j, k = 0..31
     for (int i = tid; i < 128 * 32; i += nth) {
         int n = i / 32, k = i % 32, net = n / 64, j = n % 64;
-        float v = net < a.n_nets ? __fmul_rn(a.w1[net][j * 32 + k], a.w1g[net]) : 0.f;
+        float v = net < a.n_nets ? __fmul_rn(a.w1[net][j * 32 + k], a.w1g[net]) * (1.f / 3.f) : 0.f;   // x = mean of 3 planes
         __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
         *reinterpret_cast<__half*>(out + kTcW1A + sw128(n, k * 2)) = hi;
         *reinterpret_cast<__half*>(out + kTcW1A + sw128(n, 64 + k * 2)) = hi;
@@ -110,7 +110,17 @@ struct TcRenderParams {
     p3d_render_args_t a;
     TcLayout L;
     int total_rays, n_tiles, cout;
+    uint32_t img_stride, plane_stride, pix_stride;     // element strides of the planes tensor
 };
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
 
 constexpr int kTcThreads = 384;
 constexpr int kTcColsPerGroup = 160;   // D1: [0,128)  D2: [128,160)
@@ -196,50 +206,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
     // per row and overwrites the row with the fp16 (hi | lo) features.
     auto gather_rows = [&](int tile, bool valid, int b, float px, float py, float pz) {
         uint8_t* tb = feat + tile * 16384;
+        const uint32_t tb32 = tc::smem_u32(tb);
         const int myrow = q * 32 + lane;
         if (valid) {
             const Taps t0 = make_taps(px, py, a.H, a.W), t1 = make_taps(px, pz, a.H, a.W), t2 = make_taps(pz, px, a.H, a.W);
+            // element offsets from the planes base (host guarantees they fit 32 bits)
+            const uint32_t ps = P.pix_stride;
+            const uint32_t e0 = (uint32_t)b * P.img_stride, e1 = e0 + P.plane_stride, e2 = e1 + P.plane_stride;
             uint8_t* r = tb + myrow * 128;
             const int sw = myrow & 7;
-            *reinterpret_cast<int4*>(r + ((0 ^ sw) << 4)) = make_int4(t0.o00, t0.o01, t0.o10, t0.o11);
-            *reinterpret_cast<int4*>(r + ((1 ^ sw) << 4)) = make_int4(t1.o00, t1.o01, t1.o10, t1.o11);
-            *reinterpret_cast<int4*>(r + ((2 ^ sw) << 4)) = make_int4(t2.o00, t2.o01, t2.o10, t2.o11);
+            *reinterpret_cast<uint4*>(r + ((0 ^ sw) << 4)) = make_uint4(e0 + t0.o00 * ps, e0 + t0.o01 * ps, e0 + t0.o10 * ps, e0 + t0.o11 * ps);
+            *reinterpret_cast<uint4*>(r + ((1 ^ sw) << 4)) = make_uint4(e1 + t1.o00 * ps, e1 + t1.o01 * ps, e1 + t1.o10 * ps, e1 + t1.o11 * ps);
+            *reinterpret_cast<uint4*>(r + ((2 ^ sw) << 4)) = make_uint4(e2 + t2.o00 * ps, e2 + t2.o01 * ps, e2 + t2.o10 * ps, e2 + t2.o11 * ps);
             *reinterpret_cast<float4*>(r + ((3 ^ sw) << 4)) = make_float4(t0.w00, t0.w01, t0.w10, t0.w11);
             *reinterpret_cast<float4*>(r + ((4 ^ sw) << 4)) = make_float4(t1.w00, t1.w01, t1.w10, t1.w11);
             *reinterpret_cast<float4*>(r + ((5 ^ sw) << 4)) = make_float4(t2.w00, t2.w01, t2.w10, t2.w11);
-            *reinterpret_cast<int4*>(r + ((6 ^ sw) << 4)) = make_int4(b, 0, 0, 0);
         }
         __syncwarp();
         unsigned active = __ballot_sync(0xffffffffu, valid);
-        const size_t psz = (size_t)a.H * a.W * kC, isz = 3 * psz;
+        const float* pl = a.planes_nhwc + lane;
         auto fetch = [&](int row, float& f) {
-            const uint8_t* r = tb + row * 128;
-            const int sw = row & 7;
-            const int4 o0 = *reinterpret_cast<const int4*>(r + ((0 ^ sw) << 4));
-            const int4 o1 = *reinterpret_cast<const int4*>(r + ((1 ^ sw) << 4));
-            const int4 o2 = *reinterpret_cast<const int4*>(r + ((2 ^ sw) << 4));
-            const float4 w0 = *reinterpret_cast<const float4*>(r + ((3 ^ sw) << 4));
-            const float4 w1 = *reinterpret_cast<const float4*>(r + ((4 ^ sw) << 4));
-            const float4 w2 = *reinterpret_cast<const float4*>(r + ((5 ^ sw) << 4));
-            const int bs = reinterpret_cast<const int4*>(r + ((6 ^ sw) << 4))->x;
-            const float* p0 = a.planes_nhwc + (size_t)bs * isz + lane;
-            const float* p1 = p0 + psz;
-            const float* p2 = p1 + psz;
-            const float v00 = __ldg(p0 + (size_t)o0.x * kC), v01 = __ldg(p0 + (size_t)o0.y * kC);
-            const float v02 = __ldg(p0 + (size_t)o0.z * kC), v03 = __ldg(p0 + (size_t)o0.w * kC);
-            const float v10 = __ldg(p1 + (size_t)o1.x * kC), v11 = __ldg(p1 + (size_t)o1.y * kC);
-            const float v12 = __ldg(p1 + (size_t)o1.z * kC), v13 = __ldg(p1 + (size_t)o1.w * kC);
-            const float v20 = __ldg(p2 + (size_t)o2.x * kC), v21 = __ldg(p2 + (size_t)o2.y * kC);
-            const float v22 = __ldg(p2 + (size_t)o2.z * kC), v23 = __ldg(p2 + (size_t)o2.w * kC);
-            const float f0 = fmaf(v03, w0.w, fmaf(v02, w0.z, fmaf(v01, w0.y, __fmul_rn(v00, w0.x))));
-            const float f1 = fmaf(v13, w1.w, fmaf(v12, w1.z, fmaf(v11, w1.y, __fmul_rn(v10, w1.x))));
-            const float f2 = fmaf(v23, w2.w, fmaf(v22, w2.z, fmaf(v21, w2.y, __fmul_rn(v20, w2.x))));
-            f = plane_mean(f0, f1, f2);
+            // the row base is 128-byte aligned, so base | ((chunk << 4) ^ (swizzle << 4)) is one LOP3 per 16-byte chunk
+            const uint32_t rb = tb32 + row * 128, swx = (uint32_t)(row & 7) << 4;
+            const uint4 o0 = lds_u4(rb | (0x00u ^ swx)), o1 = lds_u4(rb | (0x10u ^ swx)), o2 = lds_u4(rb | (0x20u ^ swx));
+            const uint4 x0 = lds_u4(rb | (0x30u ^ swx)), x1 = lds_u4(rb | (0x40u ^ swx)), x2 = lds_u4(rb | (0x50u ^ swx));
+            const float v00 = __ldg(pl + o0.x), v01 = __ldg(pl + o0.y), v02 = __ldg(pl + o0.z), v03 = __ldg(pl + o0.w);
+            const float v10 = __ldg(pl + o1.x), v11 = __ldg(pl + o1.y), v12 = __ldg(pl + o1.z), v13 = __ldg(pl + o1.w);
+            const float v20 = __ldg(pl + o2.x), v21 = __ldg(pl + o2.y), v22 = __ldg(pl + o2.z), v23 = __ldg(pl + o2.w);
+            const float f0 = fmaf(v03, __uint_as_float(x0.w), fmaf(v02, __uint_as_float(x0.z), fmaf(v01, __uint_as_float(x0.y), __fmul_rn(v00, __uint_as_float(x0.x)))));
+            const float f1 = fmaf(v13, __uint_as_float(x1.w), fmaf(v12, __uint_as_float(x1.z), fmaf(v11, __uint_as_float(x1.y), __fmul_rn(v10, __uint_as_float(x1.x)))));
+            const float f2 = fmaf(v23, __uint_as_float(x2.w), fmaf(v22, __uint_as_float(x2.z), fmaf(v21, __uint_as_float(x2.y), __fmul_rn(v20, __uint_as_float(x2.x)))));
+            f = __fadd_rn(__fadd_rn(f0, f1), f2);      // the mean's 1/3 lives in the packed layer-1 weights
         };
         auto store = [&](int row, float f) {
             const __half hi = __float2half_rn(f), lo = __float2half_rn(f - __half2float(hi));
-            *reinterpret_cast<__half*>(tb + sw128(row, lane * 2)) = hi;
-            *reinterpret_cast<__half*>(tb + sw128(row, 64 + lane * 2)) = lo;
+            const uint32_t rb = tb32 + row * 128, swx = (uint32_t)(row & 7) << 4;
+            // lane's hi at k-byte 2*lane, lo at 64 + 2*lane: chunks (lane >> 3) and 4 + (lane >> 3), byte (lane & 7) * 2
+            const uint32_t c = ((uint32_t)(lane >> 3) << 4), inb = (uint32_t)(lane & 7) * 2;
+            sts_u16((rb | (c ^ swx)) + inb, __half_as_ushort(hi));
+            sts_u16((rb | ((c + 0x40u) ^ swx)) + inb, __half_as_ushort(lo));
         };
         while (active) {
             const int s0 = __ffs(active) - 1;
@@ -569,6 +574,16 @@ extern "C" int p3d_render_fwd_tc(const p3d_render_args_t* args, p3d_stream_t str
     P.total_rays = a.B * a.R;
     P.n_tiles = ceil_div(P.total_rays, RT);
     P.cout = kOut * a.n_nets;
+    {
+        const int64_t psz = (int64_t)a.H * a.W * kC;
+        const bool dense = !(a.plane_strides[0] || a.plane_strides[1] || a.plane_strides[2]);
+        const int64_t is = dense ? 3 * psz : a.plane_strides[0], pls = dense ? psz : a.plane_strides[1], pxs = dense ? kC : a.plane_strides[2];
+        if (is <= 0 || pls <= 0 || pxs < kC) return P3D_BAD_ARG;
+        // largest element offset the kernel forms must fit 32 bits
+        const int64_t max_off = (int64_t)(a.B - 1) * is + 2 * pls + ((int64_t)a.H * a.W - 1) * pxs + kC;
+        if (max_off >= ((int64_t)1 << 32)) return P3D_UNSUPPORTED;
+        P.img_stride = (uint32_t)is; P.plane_stride = (uint32_t)pls; P.pix_stride = (uint32_t)pxs;
+    }
     P3D_CUDA_TRY(cudaMemsetAsync(a.workspace, 0, 4 * sizeof(uint32_t), (cudaStream_t)stream));
     P3D_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = sm_count();

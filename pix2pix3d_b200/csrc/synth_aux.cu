@@ -2,6 +2,8 @@
 // NCHW<->NHWC converters, the NHWC FIR + noise + bias + lrelu tail of an up=2 layer and the skip-image upsampler.
 // All are HBM-streaming kernels with 8/16-byte vector accesses along the (contiguous) channel axis.
 #include "p3d_common.cuh"
+#include "tc05.cuh"
+#include "tmap.cuh"
 
 namespace p3d {
 
@@ -13,50 +15,86 @@ __device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
 // ---------------------------------------------------------------------------------------------
 // modulated_conv2d weight preparation (networks_stylegan2.py:58-67)
 // ---------------------------------------------------------------------------------------------
+// One CTA per output channel: the fp32 weight row [Cin][ktaps] is read once (coalesced) and kept in shared memory as
+// [ktaps][Cin]; every sample of the batch then costs one pass for the demodulation sum and one pass that writes the
+// K-major fp16 row(s) with 16-byte stores.
 __global__ void __launch_bounds__(256) modulate_weights_kernel(const float* __restrict__ weight, const float* __restrict__ styles,
                                                                int Cout, int Cin, int ktaps, int Cout_p, int Cin_p, int cin_off, int demod,
                                                                float pre_scale, float out_scale, int planes, int B,
                                                                __half* __restrict__ out) {
-    const int o = blockIdx.x, b = blockIdx.y;
-    const size_t row = ((size_t)b * Cout_p + o) * (size_t)ktaps * Cin_p;
-    const size_t plane_stride = (size_t)B * Cout_p * ktaps * Cin_p;
+    extern __shared__ float wsm[];                 // [ktaps][Cin + 1] weights (odd row pitch: conflict-free transposed
+                                                   // staging), then [Cin] styles of the current sample
+    const int Cs = Cin + 1;
+    float* ssm = wsm + (size_t)ktaps * Cs;
     __shared__ float red[8];
-    __shared__ float dcoef;
+    const int o = blockIdx.x;
+    const size_t row_elems = (size_t)ktaps * Cin_p;
+    const size_t plane_stride = (size_t)B * Cout_p * row_elems;
     const int n = Cin * ktaps;
-    if (o >= Cout) {
-        for (int idx = threadIdx.x; idx < ktaps * Cin_p; idx += blockDim.x) {
-            out[row + idx] = __float2half_rn(0.f);
-            if (planes == 2) out[plane_stride + row + idx] = __float2half_rn(0.f);
+    const bool vec8 = (Cin_p % 8) == 0;
+    if (o >= Cout) {                               // channel padding rows
+        for (int b = 0; b < B; ++b) {
+            __half* dst = out + ((size_t)b * Cout_p + o) * row_elems;
+            for (int idx = threadIdx.x; idx < (int)row_elems; idx += blockDim.x) {
+                dst[idx] = __float2half_rn(0.f);
+                if (planes == 2) dst[plane_stride + idx] = __float2half_rn(0.f);
+            }
         }
         return;
     }
-    const float* w = weight + (size_t)o * n;   // [Cin][ktaps]
-    const float* s = styles + (size_t)b * Cin;
-    float acc = 0.f;
-    if (demod) {
-        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-            float v = __ldg(w + idx) * (__ldg(s + idx / ktaps) * pre_scale);
-            acc = fmaf(v, v, acc);
-        }
-        acc = warp_sum(acc);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-            dcoef = rsqrtf(t + 1e-8f);
-        }
-        __syncthreads();
+    const float* w = weight + (size_t)o * n;       // [Cin][ktaps]
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int i = idx / ktaps, t = idx - i * ktaps;
+        wsm[t * Cs + i] = __ldg(w + idx);
     }
-    const float d = demod ? dcoef : 1.f;
-    for (int idx = threadIdx.x; idx < ktaps * Cin_p; idx += blockDim.x) {
-        const int t = idx / Cin_p, i = idx % Cin_p - cin_off;
-        float v = 0.f;
-        if (i >= 0 && i < Cin) v = __ldg(w + (size_t)i * ktaps + t) * (__ldg(s + i) * pre_scale) * d * out_scale;
-        __half hi, lo;
-        split_half(v, hi, lo);
-        out[row + idx] = hi;
-        if (planes == 2) out[plane_stride + row + idx] = lo;
+    for (int b = 0; b < B; ++b) {
+        __syncthreads();                           // weights staged / previous sample done with ssm
+        for (int i = threadIdx.x; i < Cin; i += blockDim.x) ssm[i] = __ldg(styles + (size_t)b * Cin + i) * pre_scale;
+        __syncthreads();
+        float d = 1.f;
+        if (demod) {
+            float acc = 0.f;
+            for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+                const int t = idx / Cin, i = idx - t * Cin;
+                const float v = wsm[t * Cs + i] * ssm[i];
+                acc = fmaf(v, v, acc);
+            }
+            acc = warp_sum(acc);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            float tsum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tsum += red[i];
+            d = rsqrtf(tsum + 1e-8f);
+        }
+        const float ds = d * out_scale;
+        __half* dst = out + ((size_t)b * Cout_p + o) * row_elems;
+        if (vec8) {
+            const int nv = (int)(row_elems / 8);
+            for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+                const int e0 = v * 8, t = e0 / Cin_p, ip = e0 - t * Cin_p;
+                __align__(16) __half hv[8], lv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = ip + k - cin_off;
+                    float val = 0.f;
+                    if (i >= 0 && i < Cin) val = wsm[t * Cs + i] * ssm[i] * ds;
+                    split_half(val, hv[k], lv[k]);
+                }
+                *reinterpret_cast<uint4*>(dst + e0) = *reinterpret_cast<const uint4*>(hv);
+                if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride + e0) = *reinterpret_cast<const uint4*>(lv);
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < (int)row_elems; idx += blockDim.x) {
+                const int t = idx / Cin_p, i = idx - t * Cin_p - cin_off;
+                float val = 0.f;
+                if (i >= 0 && i < Cin) val = wsm[t * Cs + i] * ssm[i] * ds;
+                __half hi, lo;
+                split_half(val, hi, lo);
+                dst[idx] = hi;
+                if (planes == 2) dst[plane_stride + idx] = lo;
+            }
+        }
     }
 }
 
@@ -122,43 +160,45 @@ __device__ __forceinline__ void load_vec<__half, 8>(const __half* p, float (&v)[
     for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
 }
 
-// Shared-memory tiled version: a CTA produces an 8 x 16 pixel tile for a 128-byte channel block (64 fp16 or 32 fp32
-// channels). The (8+3) x (16+3) input halo is staged once with fully coalesced 16-byte loads (all issued up front),
-// then every thread computes a 2x2 output block for one 16-byte channel vector from 25 conflict-free LDS.128.
+// A CTA produces an 8 x 16 pixel tile for a 128-byte channel block (64 fp16 or 32 fp32 channels). The (8+3) x (16+3)
+// input halo is one TMA box (out-of-bounds rows / columns arrive as zeros = the FIR padding), so staging costs no
+// address arithmetic and no register round trip; every thread then computes a 2x2 output block for one 16-byte channel
+// vector from 25 conflict-free LDS.128. The filter gain is folded into the taps (as upfirdn2d.py:186 scales f).
 constexpr int kFirTH = 8, kFirTW = 16, kFirIH = kFirTH + 3, kFirIW = kFirTW + 3;
 
 template <class TIn, int VEC>
-__global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict__ x, const float* __restrict__ f,
+__global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ f,
                                                            const float* __restrict__ noise, const float* __restrict__ bias,
                                                            __half* __restrict__ y, int out_planes, size_t out_plane_stride,
-                                                           int B, int inH, int inW, int outH, int outW, int C, int padx0,
-                                                           int pady0, float fir_gain, int act, float alpha, float act_gain,
-                                                           float clamp) {
-    __shared__ uint4 tile[kFirIH * kFirIW * 8];      // 209 pixels x 128 bytes
-    float ft[4][4];                                  // mirrored taps: true convolution (flip_filter=False)
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ft[j][i] = __ldg(f + (3 - j) * 4 + (3 - i));
+                                                           int outH, int outW, int C, int padx0, int pady0, float fir_gain,
+                                                           int act, float alpha, float act_gain, float clamp) {
+    __shared__ __align__(128) uint4 tile[kFirIH * kFirIW * 8];      // 209 pixels x 128 bytes
+    __shared__ __align__(8) uint64_t bar;
     constexpr int CB = 8 * VEC;                      // channels per block (8 vectors of 16 bytes)
     const int tiles_x = (outW + kFirTW - 1) / kFirTW;
     const int tx0 = (blockIdx.x % tiles_x) * kFirTW, ty0 = (blockIdx.x / tiles_x) * kFirTH;
     const int c0 = blockIdx.y * CB, b = blockIdx.z;
-    const bool round16 = (sizeof(TIn) == 2);
-    // ---- stage the input halo (zero outside the image) ----
-    const TIn* xb = x + (size_t)b * inH * inW * C + c0;
-    for (int i = threadIdx.x; i < kFirIH * kFirIW * 8; i += 256) {
-        const int v = i & 7, p = i >> 3;
-        const int iy = ty0 - pady0 + p / kFirIW, ix = tx0 - padx0 + p % kFirIW;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (iy >= 0 && iy < inH && ix >= 0 && ix < inW)
-            val = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)iy * inW + ix) * C) + v);
-        tile[i] = val;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::fence_barrier_init();
+        tc::mbar_expect_tx(&bar, (uint32_t)sizeof(tile));
+        tc::tma_load_4d(tile, &tmX, &bar, c0, tx0 - padx0, ty0 - pady0, b);
     }
-    __syncthreads();
-    // ---- 2x2 outputs per thread ----
+    float ft[4][4];                                  // mirrored taps: true convolution (flip_filter=False)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ft[j][i] = __ldg(f + (3 - j) * 4 + (3 - i)) * fir_gain;
+    const bool round16 = (sizeof(TIn) == 2);
     const int v = threadIdx.x & 7, blk = threadIdx.x >> 3;          // 32 blocks: 4 rows x 8 cols of 2x2
     const int by = (blk >> 3) * 2, bx = (blk & 7) * 2;
+    const int c = c0 + v * VEC;
+    float bv[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) bv[k] = bias ? __ldg(bias + c + k) : 0.f;
+    __syncthreads();                                 // barrier init visible to the waiters
+    tc::mbar_wait(&bar, 0);
+    // ---- 2x2 outputs per thread ----
     float acc[2][2][VEC];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -194,7 +234,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
                     for (int k = 0; k < VEC; ++k) acc[i][j][k] = fmaf(ft[ty][tx], win[tx + j][k], acc[i][j][k]);
         }
     }
-    const int c = c0 + v * VEC;
+    const bool fast_lrelu = alpha >= 0.f && alpha <= 1.f;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
 #pragma unroll
@@ -203,18 +243,31 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
             if (py >= outH || px >= outW) continue;
             const float nz = noise ? __ldg(noise + (size_t)py * outW + px) : 0.f;
             const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
-            __align__(16) __half hv[VEC], lv[VEC];
+            __align__(16) __half2 hv[VEC / 2], lv[VEC / 2];
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                float val = acc[i][j][k] * fir_gain;
-                if (round16) val = __half2float(__float2half_rn(val));
-                val += nz;
-                if (round16 && noise) val = __half2float(__float2half_rn(val));
-                if (bias) val += __ldg(bias + c + k);
-                if (act == 3) val = val > 0.f ? val : val * alpha;
-                val *= act_gain;
-                if (clamp >= 0.f) val = fminf(fmaxf(val, -clamp), clamp);
-                split_half(val, hv[k], lv[k]);
+            for (int k = 0; k < VEC; k += 2) {
+                float v0 = acc[i][j][k], v1 = acc[i][j][k + 1];
+                if (round16) {   // the fp16 reference rounds the FIR output, and again after the in-place noise add
+                    float2 t = __half22float2(__floats2half2_rn(v0, v1));
+                    v0 = t.x + nz; v1 = t.y + nz;
+                    if (noise) { t = __half22float2(__floats2half2_rn(v0, v1)); v0 = t.x; v1 = t.y; }
+                } else {
+                    v0 += nz; v1 += nz;
+                }
+                v0 += bv[k]; v1 += bv[k + 1];
+                if (act == 3) {
+                    const float m0 = v0 * alpha, m1 = v1 * alpha;
+                    if (fast_lrelu) { v0 = fmaxf(v0, m0); v1 = fmaxf(v1, m1); }
+                    else { v0 = v0 > 0.f ? v0 : m0; v1 = v1 > 0.f ? v1 : m1; }
+                }
+                v0 *= act_gain; v1 *= act_gain;
+                if (clamp >= 0.f) { v0 = fminf(fmaxf(v0, -clamp), clamp); v1 = fminf(fmaxf(v1, -clamp), clamp); }
+                const __half2 h = __floats2half2_rn(v0, v1);
+                hv[k / 2] = h;
+                if (out_planes == 2) {
+                    const float2 back = __half22float2(h);
+                    lv[k / 2] = __floats2half2_rn(v0 - back.x, v1 - back.y);
+                }
             }
             if (VEC == 8) {
                 *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
@@ -227,31 +280,92 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const TIn* __restrict
     }
 }
 
-// upsample2d(img, [1,3,3,1]) on fp32 NHWC: zero-insert x2, pad (2,1), 4x4 FIR, gain 4 (upfirdn2d.py:344-350)
+// upsample2d(img, [1,3,3,1]) on fp32 NHWC: zero-insert x2, pad (2,1), 4x4 FIR, gain 4 (upfirdn2d.py:344-350).
+// Polyphase form: one thread owns an input pixel (x VEC channels) and writes its 2x2 output quad from the 3x3 input
+// neighbourhood; output (2y+py, 2x+px) only sees filter taps of parity (py, px), i.e. 2x2 of the 16 taps.
+template <int VEC>
 __global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ f,
                                                               float* __restrict__ y, int B, int H, int W, int C) {
-    const int64_t total = (int64_t)B * 2 * H * 2 * W * C;
+    __shared__ float fs[16];
+    if (threadIdx.x < 16) fs[threadIdx.x] = __ldg(f + threadIdx.x) * 4.f;
+    __syncthreads();
+    const int CV = C / VEC;
+    const int64_t total = (int64_t)B * H * W * CV;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C);
-        int64_t t = idx / C;
-        const int ox = (int)(t % (2 * W)); t /= 2 * W;
-        const int oy = (int)(t % (2 * H));
-        const int b = (int)(t / (2 * H));
-        const float* xb = x + (size_t)b * H * W * C + c;
-        float acc = 0.f;
-        // padded/upsampled position p = o + tap - 2 holds x[p/2] when p is even
+        const int cv = (int)(idx % CV);
+        int64_t t = idx / CV;
+        const int ix = (int)(t % W); t /= W;
+        const int iy = (int)(t % H);
+        const int b = (int)(t / H);
+        float v[3][3][VEC];
 #pragma unroll
-        for (int ty = 0; ty < 4; ++ty) {
-            const int py = oy + ty - 2;
-            if (py < 0 || (py & 1) || (py >> 1) >= H) continue;
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-            for (int tx = 0; tx < 4; ++tx) {
-                const int px = ox + tx - 2;
-                if (px < 0 || (px & 1) || (px >> 1) >= W) continue;
-                acc = fmaf(__ldg(f + (3 - ty) * 4 + (3 - tx)), __ldg(xb + ((size_t)(py >> 1) * W + (px >> 1)) * C), acc);
+            for (int dx = 0; dx < 3; ++dx) {
+                const int yy = iy + dy - 1, xx = ix + dx - 1;
+                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+                const float* src = x + (((size_t)b * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * C + (size_t)cv * VEC;
+                if (VEC == 4) {
+                    const float4 q = ok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[dy][dx][0] = q.x; v[dy][dx][1 % VEC] = q.y; v[dy][dx][2 % VEC] = q.z; v[dy][dx][3 % VEC] = q.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) v[dy][dx][k] = ok ? __ldg(src + k) : 0.f;
+                }
             }
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                // output row 2*iy+py reads padded rows p = o + ty - 2 (even only): ty in {py, py+2} -> input rows iy-1+py, iy+py
+                float acc[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const int ty = py + 2 * a, tx = px + 2 * c;
+                        const float w = fs[(3 - ty) * 4 + (3 - tx)];
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w, v[py + a][px + c][k], acc[k]);
+                    }
+                float* dst = y + (((size_t)b * 2 * H + 2 * iy + py) * 2 * W + 2 * ix + px) * C + (size_t)cv * VEC;
+                if (VEC == 4) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) dst[k] = acc[k];
+                }
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// every style affine of a synthesis stack in one launch (FullyConnectedLayer.forward, networks_stylegan2.py:111-123)
+// ---------------------------------------------------------------------------------------------
+// one warp per output row r: out[meta.out_off + b * meta.out_stride] = bias[r] + <ws[b, meta.ws_index, :], weight[r, :]>
+__global__ void __launch_bounds__(256) affine_batch_kernel(const float* __restrict__ ws, const float* __restrict__ weight,
+                                                           const float* __restrict__ bias, const int4* __restrict__ meta,
+                                                           float* __restrict__ out, int B, int num_ws, int w_dim, int rows) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int4 m = __ldg(meta + r);
+    const float* wr = weight + (size_t)r * w_dim;
+    const float bv = __ldg(bias + r);
+    for (int b = 0; b < B; ++b) {
+        const float* x = ws + ((size_t)b * num_ws + m.x) * w_dim;
+        float acc = 0.f;
+        if ((w_dim & 3) == 0) {
+            for (int k = lane * 4; k < w_dim; k += 128) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(wr + k)), v = __ldg(reinterpret_cast<const float4*>(x + k));
+                acc = fmaf(a.x, v.x, fmaf(a.y, v.y, fmaf(a.z, v.z, fmaf(a.w, v.w, acc))));
+            }
+        } else {
+            for (int k = lane; k < w_dim; k += 32) acc = fmaf(__ldg(wr + k), __ldg(x + k), acc);
         }
-        y[idx] = acc * 4.f;
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)m.y + (size_t)b * m.z] = acc + bv;
     }
 }
 
@@ -270,9 +384,22 @@ extern "C" int p3d_modulate_weights(const float* weight, const float* styles, in
                                     float out_scale, int planes, void* out, p3d_stream_t stream) {
     if (!weight || !styles || !out || B <= 0 || Cout <= 0 || Cin <= 0 || ktaps <= 0) return P3D_BAD_ARG;
     if (Cout_padded < Cout || cin_offset < 0 || Cin_padded < Cin + cin_offset || planes < 1 || planes > 2 || B > 65535) return P3D_BAD_ARG;
-    dim3 grid(Cout_padded, B);
-    modulate_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(weight, styles, Cout, Cin, ktaps, Cout_padded, Cin_padded,
+    const size_t smem = ((size_t)ktaps * (Cin + 1) + Cin) * sizeof(float);
+    if (smem > 200 * 1024) return P3D_UNSUPPORTED;
+    if (smem > 48 * 1024)
+        P3D_CUDA_TRY(cudaFuncSetAttribute(modulate_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    modulate_weights_kernel<<<Cout_padded, 256, smem, (cudaStream_t)stream>>>(weight, styles, Cout, Cin, ktaps, Cout_padded, Cin_padded,
                                                                     cin_offset, demodulate, pre_scale, out_scale, planes, B, (__half*)out);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+extern "C" int p3d_affine_batch(const float* ws, const float* weight, const float* bias, const int32_t* meta, float* out,
+                                int B, int num_ws, int w_dim, int rows, p3d_stream_t stream) {
+    if (!ws || !weight || !bias || !meta || !out || B <= 0 || num_ws <= 0 || w_dim <= 0 || rows <= 0) return P3D_BAD_ARG;
+    if ((((uintptr_t)ws | (uintptr_t)weight) & 15) != 0 || (((uintptr_t)meta) & 15) != 0) return P3D_BAD_ARG;
+    affine_batch_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(ws, weight, bias, reinterpret_cast<const int4*>(meta), out, B,
+                                                                             num_ws, w_dim, rows);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
@@ -310,29 +437,40 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
     const size_t ps = (size_t)B * outH * outW * C;
     const int tiles = ceil_div(outW, kFirTW) * ceil_div(outH, kFirTH);
     if (B > 65535) return P3D_UNSUPPORTED;
-    if (in_dtype == P3D_F32) {
-        if (C % 32) return P3D_UNSUPPORTED;
-        dim3 grid(tiles, C / 32, B);
-        fir_act_nhwc_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
-            (const float*)x, f, noise, bias, (__half*)y, out_planes, ps, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
-            alpha, act_gain, clamp);
-    } else if (in_dtype == P3D_F16) {
-        if (C % 64) return P3D_UNSUPPORTED;
-        dim3 grid(tiles, C / 64, B);
-        fir_act_nhwc_kernel<__half, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(
-            (const __half*)x, f, noise, bias, (__half*)y, out_planes, ps, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
-            alpha, act_gain, clamp);
-    } else {
-        return P3D_BAD_ARG;
+    if (in_dtype != P3D_F32 && in_dtype != P3D_F16) return P3D_BAD_ARG;
+    const int es = in_dtype == P3D_F32 ? 4 : 2, cb = 128 / es;
+    if (C % cb) return P3D_UNSUPPORTED;
+    if (((uintptr_t)x & 15) != 0) return P3D_BAD_ARG;
+    CUtensorMap tm;
+    {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)inW, (uint64_t)inH, (uint64_t)B};
+        uint64_t str[3] = {(uint64_t)C * es, (uint64_t)inW * C * es, (uint64_t)inH * inW * C * es};
+        uint32_t box[4] = {(uint32_t)cb, (uint32_t)kFirIW, (uint32_t)kFirIH, 1};
+        int rc = make_tmap(&tm, x, in_dtype == P3D_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, 4, dims, str, box);
+        if (rc != P3D_OK) return rc;
     }
+    dim3 grid(tiles, C / cb, B);
+    if (in_dtype == P3D_F32)
+        fir_act_nhwc_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW,
+                                                                              C, padx0, pady0, fir_gain, act, alpha, act_gain, clamp);
+    else
+        fir_act_nhwc_kernel<__half, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH,
+                                                                               outW, C, padx0, pady0, fir_gain, act, alpha, act_gain,
+                                                                               clamp);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
 
 extern "C" int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream) {
     if (!x || !f || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0) return P3D_BAD_ARG;
-    int64_t items = (int64_t)B * 4 * H * W * C;
-    upsample2x_nhwc_kernel<<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(x, f, y, B, H, W, C);
+    if (C % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0) {
+        int64_t items = (int64_t)B * H * W * (C / 4);
+        upsample2x_nhwc_kernel<4><<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(x, f, y, B, H, W, C);
+    } else {
+        int64_t items = (int64_t)B * H * W * C;
+        upsample2x_nhwc_kernel<1><<<grid1d(items, 256), 256, 0, (cudaStream_t)stream>>>(x, f, y, B, H, W, C);
+    }
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

@@ -11,6 +11,8 @@ tensor-core passes (fp32-level accuracy); fp16 blocks run single pass, rounding 
 The module classes call into this when the inputs are CUDA tensors, no gradient is required and the noise mode is
 'const' or 'none'; every other case keeps the generic op-by-op formulation.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -48,6 +50,22 @@ def grad_needed(*modules_and_tensors):
     return False
 
 
+# Tensors derived from parameters only (gain-scaled affine weights, padded biases, const noise x strength, the NHWC image
+# of the learned constant) are computed once per parameter version instead of once per step.
+_derived = weakref.WeakKeyDictionary()
+
+
+def _cached(module, key, params, fn):
+    ver = tuple((p.data_ptr(), p._version, p.device) for p in params)
+    slot = _derived.setdefault(module, {})
+    hit = slot.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = fn()
+    slot[key] = (ver, val)
+    return val
+
+
 def _pad_vec(v, n):
     v = v.detach().float()
     if v.numel() == n:
@@ -57,10 +75,74 @@ def _pad_vec(v, n):
     return out
 
 
+def _bias(layer, n):
+    return _cached(layer, ('bias', n), [layer.bias], lambda: _pad_vec(layer.bias, n))
+
+
 def _noise(layer, noise_mode):
     if noise_mode == 'const' and layer.use_noise:
-        return (layer.noise_const * layer.noise_strength).detach().float().contiguous()
+        return _cached(layer, 'noise', [layer.noise_const, layer.noise_strength],
+                       lambda: (layer.noise_const * layer.noise_strength).detach().float().contiguous())
     return None
+
+
+class StylePlan:
+    """All `layer.affine(w)` of a list of layers as one `p3d_affine_batch` launch.
+
+    layers: [(layer, ws_index)] in execution order; `run(ws)` returns the styles in that order, each [B, in_channels]
+    (contiguous slices of one buffer)."""
+
+    def __init__(self, layers):
+        affs = [l.affine for l, _ in layers]
+        dev = affs[0].weight.device
+        self.key = tuple((a.weight.data_ptr(), a.weight._version, a.bias.data_ptr(), a.bias._version) for a in affs) + \
+            tuple(i for _, i in layers)
+        with torch.no_grad():
+            self.weight = torch.cat([a.weight.detach().float() * a.weight_gain for a in affs]).contiguous()
+            self.bias = torch.cat([a.bias.detach().float() * a.bias_gain for a in affs]).contiguous()
+        self.sizes = [a.out_features for a in affs]
+        self.index = [i for _, i in layers]
+        self.device = dev
+        self._meta = {}
+
+    def meta(self, b):
+        m = self._meta.get(b)
+        if m is None:
+            rows, off = [], 0
+            for n, wi in zip(self.sizes, self.index):
+                j = np.arange(n, dtype=np.int64)
+                rows.append(np.stack([np.full(n, wi, np.int64), off + j, np.full(n, n, np.int64), np.zeros(n, np.int64)], 1))
+                off += b * n
+            m = (torch.from_numpy(np.concatenate(rows).astype(np.int32)).to(self.device), off)
+            self._meta[b] = m
+        return m
+
+    def run(self, ws):
+        b = ws.shape[0]
+        meta, total = self.meta(b)
+        flat = tcconv.affine_batch(ws, self.weight, self.bias, meta, total)
+        out, off = [], 0
+        for n in self.sizes:
+            out.append(flat[off:off + b * n].view(b, n))
+            off += b * n
+        return out
+
+
+def _block_layers(block):
+    names = (['conv1'] if block.in_channels == 0 else ['conv0', 'conv1']) + ['torgb']
+    return [getattr(block, n) for n in names]
+
+
+def style_plan(owner, tag, layers):
+    """Cached StylePlan for `layers` ([(layer, ws_index)]), stored against `owner`."""
+    slot = _derived.setdefault(owner, {})
+    key = tuple((l.affine.weight.data_ptr(), l.affine.weight._version, l.affine.bias.data_ptr(), l.affine.bias._version)
+                for l, _ in layers) + tuple(i for _, i in layers)
+    plan = slot.get(('styles', tag))
+    if plan is None or plan.key != key:
+        plan = StylePlan(layers)
+        slot[('styles', tag)] = plan
+    return plan
 
 
 def _alloc(planes, b, h, w, c, cp, device):
@@ -68,17 +150,16 @@ def _alloc(planes, b, h, w, c, cp, device):
     return torch.zeros(shape, device=device, dtype=torch.float16) if cp != c else torch.empty(shape, device=device, dtype=torch.float16)
 
 
-def synthesis_layer(layer, x, w_lat, noise_mode, split, gain=1.0, cin_offset=0):
-    """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]."""
+def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0):
+    """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]; styles = layer.affine(w)."""
     planes = 2 if split else 1
-    styles = layer.affine(w_lat.float())
     b = styles.shape[0]
     cin_p = x.shape[-1]
     cout = layer.out_channels
     cout_p = tcconv.pad_to(cout, 64)
     wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset)
     noise = _noise(layer, noise_mode)
-    bias = _pad_vec(layer.bias, cout_p)
+    bias = _bias(layer, cout_p)
     act_gain = layer.act_gain * gain
     clamp = float(layer.conv_clamp * gain) if layer.conv_clamp is not None else -1.0
     dev = x.device
@@ -100,16 +181,15 @@ def synthesis_layer(layer, x, w_lat, noise_mode, split, gain=1.0, cin_offset=0):
                                alpha=0.2, act_gain=act_gain, clamp=clamp)
 
 
-def torgb_layer(layer, x, w_lat, img, split):
+def torgb_layer(layer, x, styles, img, split):
     """ToRGBLayer.forward (:354-359) accumulated into the fp32 NHWC skip image (or creating it)."""
     planes = 2 if split else 1
-    styles = layer.affine(w_lat.float())
     b = styles.shape[0]
     cout = layer.out_channels
     wk = tcconv.modulate_weights(layer.weight, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes,
                                  cin_padded=x.shape[-1])
     h, w = x.shape[2], x.shape[3]
-    bias = layer.bias.detach().float().contiguous()
+    bias = _bias(layer, cout)
     clamp = float(layer.conv_clamp) if layer.conv_clamp is not None else -1.0
     if img is None:
         img = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float32)
@@ -129,52 +209,80 @@ def torgb_layer(layer, x, w_lat, img, split):
     return img
 
 
-def synthesis_block(block, x, img, ws, noise_mode='const', force_fp32=False, upsample=True, cin_offset=0):
-    """One block on NHWC tensors. x: [planes,B,h,w,Cp] fp16 or None (first block); img: [B,h,w,Ci] fp32 or None.
+def _const_input(block, b, planes):
+    def make():
+        c = block.const.shape[0]
+        return tcconv.to_nhwc_f16(block.const.detach().float().unsqueeze(0).expand(b, -1, -1, -1).contiguous(),
+                                  c_padded=tcconv.pad_to(c, 64), planes=planes)
+    return _cached(block, ('const', b, planes), [block.const], make)
+
+
+def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False, upsample=True, cin_offset=0):
+    """One block on NHWC tensors. x: [planes,B,h,w,Cp] fp16 or None (first block); img: [B,h,w,Ci] fp32 or None;
+    styles: the affine outputs of this block's layers in execution order (conv0, conv1, torgb).
     Returns (x, img) in the same representation. The precision of x switches at block boundaries as
     `x.to(dtype)` does in the reference (:438)."""
     split = not (block.use_fp16 and not force_fp32)
     planes = 2 if split else 1
-    w_iter = iter(ws.unbind(dim=1))
-    b = ws.shape[0]
+    s_iter = iter(styles)
     if block.in_channels == 0:
-        c = block.const.shape[0]
-        x = tcconv.to_nhwc_f16(block.const.detach().float().unsqueeze(0).expand(b, -1, -1, -1).contiguous(),
-                               c_padded=tcconv.pad_to(c, 64), planes=planes)
-        x = synthesis_layer(block.conv1, x, next(w_iter), noise_mode, split)
+        x = _const_input(block, styles[0].shape[0], planes)
+        x = synthesis_layer(block.conv1, x, next(s_iter), noise_mode, split)
     else:
         if x.shape[0] != planes:   # precision change between blocks
             x = x[:1].contiguous() if planes == 1 else torch.stack([x[0], torch.zeros_like(x[0])])
-        x = synthesis_layer(block.conv0, x, next(w_iter), noise_mode, split, cin_offset=cin_offset)
-        x = synthesis_layer(block.conv1, x, next(w_iter), noise_mode, split)
+        x = synthesis_layer(block.conv0, x, next(s_iter), noise_mode, split, cin_offset=cin_offset)
+        x = synthesis_layer(block.conv1, x, next(s_iter), noise_mode, split)
     if upsample and img is not None:
         img = tcconv.upsample2x_nhwc(img, block.resample_filter)
-    img = torgb_layer(block.torgb, x, next(w_iter), img, split)
+    img = torgb_layer(block.torgb, x, next(s_iter), img, split)
     return x, img
+
+
+def _network_layers(net):
+    """[(layer, ws_index)] of a SynthesisNetwork in execution order (ws slicing of :505-516)."""
+    out, w_idx = [], 0
+    for res in net.block_resolutions:
+        block = getattr(net, f'b{res}')
+        for k, layer in enumerate(_block_layers(block)):
+            out.append((layer, w_idx + k))
+        w_idx += block.num_conv
+    return out
+
+
+def _run_network(net, styles, noise_mode, force_fp32):
+    x = img = None
+    pos = 0
+    for res in net.block_resolutions:
+        block = getattr(net, f'b{res}')
+        n = len(_block_layers(block))
+        x, img = synthesis_block(block, x, img, styles[pos:pos + n], noise_mode=noise_mode, force_fp32=force_fp32)
+        pos += n
+    return img
 
 
 def synthesis_network(net, ws, noise_mode='const', force_fp32=False):
     """SynthesisNetwork.forward (:505-520) -> fp32 NHWC image [B,R,R,img_channels]."""
-    ws = ws.to(torch.float32)
-    x = img = None
-    w_idx = 0
-    for res in net.block_resolutions:
-        block = getattr(net, f'b{res}')
-        cur = ws.narrow(1, w_idx, block.num_conv + block.num_torgb)
-        w_idx += block.num_conv
-        x, img = synthesis_block(block, x, img, cur, noise_mode=noise_mode, force_fp32=force_fp32)
-    return img
+    styles = style_plan(net, 'net', _network_layers(net)).run(ws.to(torch.float32))
+    return _run_network(net, styles, noise_mode, force_fp32)
+
+
+def _sr_layers(sr, ws_index):
+    """Both SR blocks read the same latent three times (superresolution.py:49: ws[:, -1:].repeat(1, 3, 1))."""
+    return [(layer, ws_index) for block in (sr.block0, sr.block1) for layer in _block_layers(block)]
 
 
 def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=False):
     """Superresolution*.forward (superresolution.py:48-57) with the feature image as NCHW fp32 and the low-res image as
     fp32 NHWC; returns the fp32 NHWC output image."""
-    ws = ws[:, -1:, :].repeat(1, 3, 1).to(torch.float32)
+    ws = ws.to(torch.float32)
+    styles = style_plan(sr, 'sr', _sr_layers(sr, ws.shape[1] - 1)).run(ws)
     split0 = not (sr.block0.use_fp16 and not force_fp32)
     x = tcconv.to_nhwc_f16(feat_nchw, c_padded=tcconv.pad_to(feat_nchw.shape[1], 64), planes=2 if split0 else 1)
     up0 = sr.block0.conv0.up == 2
-    x, img = synthesis_block(sr.block0, x, rgb_nhwc, ws, noise_mode=noise_mode, force_fp32=force_fp32, upsample=up0)
-    x, img = synthesis_block(sr.block1, x, img, ws, noise_mode=noise_mode, force_fp32=force_fp32, upsample=True)
+    n0 = len(_block_layers(sr.block0))
+    x, img = synthesis_block(sr.block0, x, rgb_nhwc, styles[:n0], noise_mode=noise_mode, force_fp32=force_fp32, upsample=up0)
+    x, img = synthesis_block(sr.block1, x, img, styles[n0:], noise_mode=noise_mode, force_fp32=force_fp32, upsample=True)
     return img
 
 
@@ -219,13 +327,21 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
     cam2world = c[:, :16].view(-1, 4, 4)
     intrinsics = c[:, 16:25].view(-1, 3, 3)
     ray_origins, ray_directions = gen.ray_sampler(cam2world, intrinsics, nrr)
+    # every style affine of the step (backbone + both SR stacks) in one launch
+    net = gen.backbone.synthesis
+    semantic = hasattr(gen, 'superresolution_semantic')
+    srs = [gen.superresolution] + ([gen.superresolution_semantic] if semantic else [])
+    net_layers = _network_layers(net)
+    n_net = len(net_layers)
+    all_layers = net_layers + [lw for sr in srs for lw in _sr_layers(sr, ws.shape[1] - 1)]
+    styles = style_plan(gen, 'gen', all_layers).run(ws.to(torch.float32))
     if use_cached_backbone and gen._last_planes is not None:
         planes_nchw = gen._last_planes
         planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
     else:
-        img = synthesis_network(gen.backbone.synthesis, ws, noise_mode=noise_mode, force_fp32=force_fp32)   # [B,H,W,96]
+        img = _run_network(net, styles[:n_net], noise_mode, force_fp32)                                      # [B,H,W,96]
         h, w = img.shape[1], img.shape[2]
-        planes_cl = img.view(b, h, w, 3, 32).permute(0, 3, 1, 2, 4).contiguous()
+        planes_cl = img.view(b, h, w, 3, 32).permute(0, 3, 1, 2, 4)     # strided view, read in place by the renderer
         if cache_backbone:
             gen._last_planes = tcconv.nhwc_to_nchw_f32(img)
     feats, depth, wsum = gen.renderer(None, gen.decoder, ray_origins, ray_directions, gen.rendering_kwargs,
@@ -234,10 +350,10 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
     fimg = feats.view(b, nrr, nrr, nch)                     # [B,R,C] is already NHWC
     depth_image = depth.permute(0, 2, 1).reshape(b, 1, nrr, nrr)
     sr_noise = gen.rendering_kwargs['superresolution_noise_mode']
-    semantic = hasattr(gen, 'superresolution_semantic')
     half = nch // 2 if semantic else nch
+    n_sr = len(_sr_layers(gen.superresolution, 0))
 
-    def run_sr(sr, c_off, n_img):
+    def run_sr(sr, c_off, n_img, st):
         split0 = not (sr.block0.use_fp16 and not force_fp32)
         if split0:
             hi = fimg.half()
@@ -248,21 +364,21 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
             x = torch.nn.functional.pad(x, (0, tcconv.pad_to(nch, 64) - nch))
         x = x.contiguous()
         rgb = fimg[..., c_off:c_off + n_img].contiguous()
-        w3 = ws[:, -1:, :].repeat(1, 3, 1).to(torch.float32)
         up0 = sr.block0.conv0.up == 2
+        n0 = len(_block_layers(sr.block0))
         # reference quirk kept: a NoUp block0 accumulates its ToRGB into the very tensor it was handed
         # (superresolution.py:283 `img.add_(y)` on the `feature_image[:, :3]` view), so the raw image returned by
         # synthesis includes that term whenever no resize happened; with an upsampling block0 it does not.
         raw = rgb if up0 else rgb.clone()
-        x, im = synthesis_block(sr.block0, x, rgb, w3, noise_mode=sr_noise, force_fp32=force_fp32, upsample=up0, cin_offset=c_off)
+        x, im = synthesis_block(sr.block0, x, rgb, st[:n0], noise_mode=sr_noise, force_fp32=force_fp32, upsample=up0, cin_offset=c_off)
         if not up0:
             raw = im
-        x, im = synthesis_block(sr.block1, x, im, w3, noise_mode=sr_noise, force_fp32=force_fp32, upsample=True)
+        x, im = synthesis_block(sr.block1, x, im, st[n0:], noise_mode=sr_noise, force_fp32=force_fp32, upsample=True)
         return tcconv.nhwc_to_nchw_f32(im), raw.permute(0, 3, 1, 2).contiguous()
 
-    image, image_raw = run_sr(gen.superresolution, 0, 3)
+    image, image_raw = run_sr(gen.superresolution, 0, 3, styles[n_net:n_net + n_sr])
     out = {'image': image, 'image_raw': image_raw, 'image_depth': depth_image}
     if semantic:
         cs = gen.semantic_channels
-        out['semantic'], out['semantic_raw'] = run_sr(gen.superresolution_semantic, half, cs)
+        out['semantic'], out['semantic_raw'] = run_sr(gen.superresolution_semantic, half, cs, styles[n_net + n_sr:])
     return out

@@ -133,7 +133,15 @@ def pack_decoder(decoder):
 def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_warp, white_back=False, debug=False, impl=None):
     """Fused ImportanceRenderer.forward. Returns (feat [B,R,C], depth [B,R,1], wsum [B,R,1][, debug dict])."""
     B, _, H, W, C = planes_nhwc.shape
-    assert C == 32
+    assert C == 32 and planes_nhwc.dtype == torch.float32
+    impl = impl or render_impl
+    # a strided view is read in place by the tensor-core kernel as long as channels are contiguous and rows are W pixels
+    # apart (e.g. the backbone's NHWC [B,H,W,96] output viewed as [B,3,H,W,32]); everything else is made dense first
+    st_img, st_plane, st_row, st_pix, st_ch = planes_nhwc.stride()
+    strided = not planes_nhwc.is_contiguous()
+    if strided and not (st_ch == 1 and st_row == W * st_pix and st_pix >= 32 and st_plane > 0 and st_img > 0 and impl != 'simt'):
+        planes_nhwc = planes_nhwc.contiguous()
+        strided = False
     R = ray_origins.shape[1]
     o, d = _f32c(ray_origins), _f32c(ray_dirs)
     dc = _f32c(depths_coarse).reshape(B, R, -1)
@@ -169,11 +177,12 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
             a.dbg_weights_coarse = dbg['weights_coarse'].data_ptr()
             a.dbg_depths_fine, a.dbg_inds = dbg['depths_fine'].data_ptr(), dbg['inds'].data_ptr()
     a.workspace = ws.data_ptr()
+    if strided:
+        a.plane_strides[0], a.plane_strides[1], a.plane_strides[2] = st_img, st_plane, st_pix
     ev = None
     if kernel_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    impl = impl or render_impl
     use_tc = impl in ('auto', 'tc') and Sc % 8 == 0 and Sf % 8 == 0 and Sc <= 128 and Sf <= 128 and dec.packed_tc is not None
     if impl == 'tc' and not use_tc:
         raise ValueError('tensor-core renderer needs sample counts that are multiples of 8')
@@ -182,6 +191,10 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
             a.decoder_packed = dec.packed_tc.data_ptr()
             st = _lib.lib().p3d_render_fwd_tc(ctypes.byref(a), _lib.stream_ptr())
         else:
+            if strided:   # the SIMT kernel reads dense planes only
+                dense = planes_nhwc.contiguous()
+                a.planes_nhwc = dense.data_ptr()
+                a.plane_strides[0] = a.plane_strides[1] = a.plane_strides[2] = 0
             st = _lib.lib().p3d_render_fwd(ctypes.byref(a), _lib.stream_ptr())
     if ev is not None:
         ev[1].record()

@@ -80,6 +80,19 @@ def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, c
     return out
 
 
+def affine_batch(ws, weight, bias, meta, out_numel):
+    """ws [B,num_ws,w_dim] fp32; weight [rows,w_dim] (gains applied), bias [rows], meta int32 [rows,4] -> flat fp32 buffer."""
+    ws = ws.detach().float().contiguous()
+    b, num_ws, w_dim = ws.shape
+    out = torch.empty(out_numel, device=ws.device, dtype=torch.float32)
+    with torch.cuda.device(ws.device):
+        st = _lib.lib().p3d_affine_batch(_lib.ptr(ws), _lib.ptr(weight), _lib.ptr(bias), _lib.ptr(meta), _lib.ptr(out), b, num_ws, w_dim,
+                                         weight.shape[0], _lib.stream_ptr())
+    _lib.check(st, 'p3d_affine_batch')
+    _lib.bump()
+    return out
+
+
 def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
               noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE):
     """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;

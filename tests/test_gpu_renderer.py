@@ -178,6 +178,12 @@ def test_full_size_properties_config2(impl):
     f1, d1, w1 = native.render_fwd(pcl[2:3].contiguous(), dec, o[2:3].contiguous(), d[2:3].contiguous(), dc[2:3].contiguous(),
                                    u[2 * R:3 * R].contiguous(), 1.0, impl=impl)
     assert torch.equal(f1[0], feat[2]) and torch.equal(w1[0], wsum[2])
+    # the backbone's NHWC [B,H,W,96] output read in place as a strided [B,3,H,W,32] view (plane_strides of the C-ABI)
+    inter = pcl.permute(0, 2, 3, 1, 4).contiguous()
+    view = inter.permute(0, 3, 1, 2, 4)
+    assert not view.is_contiguous()
+    fs, dsx, wsx = native.render_fwd(view, dec, o, d, dc, u, 1.0, impl=impl)
+    assert torch.equal(fs, feat) and torch.equal(dsx, depth) and torch.equal(wsx, wsum)
     # sampled check of full-size output against the oracle on 64 rays
     idx = torch.randperm(R, device=dev)[:64]
     pl = planes[1:2].cpu().numpy()

@@ -26,19 +26,23 @@ def sass_rows(rep, kernel, launch):
     return [(r[iS].strip(), int(r[iW] or 0), int(r[iE] or 0)) for r in rows[1:] if len(r) > iE]
 
 
-def line_table(lib, kernel):
+def line_table(lib, kernel, n_expected=None):
+    """Line table of the function whose name contains `kernel`; with several template instantiations, the one whose
+    instruction count equals n_expected."""
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    res = []
+    tables = {}
     for cub in glob.glob(os.path.join(tmp, '*.cubin')):
         txt = subprocess.run(['nvdisasm', '-g', cub], capture_output=True, text=True).stdout
         if kernel not in txt:
             continue
-        in_fn, cur = False, ('?', 0, None)
+        in_fn, cur, res = False, ('?', 0, None), None
         for line in txt.splitlines():
             m = re.match(r'\s*\.section\s+\.text\.(\S+?),', line)
             if m:
                 in_fn = kernel in m.group(1)
+                if in_fn:
+                    res = tables.setdefault(m.group(1), [])
                 continue
             if not in_fn:
                 continue
@@ -50,9 +54,13 @@ def line_table(lib, kernel):
             m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);', line)
             if m:
                 res.append((m.group(2).strip(), cur))
-        if res:
-            break
-    return res
+    if not tables:
+        return []
+    if n_expected is not None:
+        for name, t in tables.items():
+            if len(t) == n_expected:
+                return t
+    return max(tables.values(), key=len) if n_expected is None else min(tables.values(), key=lambda t: abs(len(t) - n_expected))
 
 
 def main():
@@ -60,7 +68,7 @@ def main():
     launch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     topn = int(sys.argv[5]) if len(sys.argv) > 5 else 40
     rows = sass_rows(rep, kernel, launch)
-    table = line_table(lib, kernel)
+    table = line_table(lib, kernel, len(rows))
     if len(rows) != len(table):
         print(f'WARNING: {len(rows)} profiled instructions vs {len(table)} in the cubin: different builds?')
     n = min(len(rows), len(table))
