@@ -199,6 +199,8 @@ typedef struct {
     int32_t act;              /* 1 linear, 3 lrelu */
     float alpha, gain, clamp; /* activation slope, output gain, clamp (<0: none) */
     float acc_scale;          /* multiplies the accumulator first (undoes the power-of-two weight scaling) */
+    void* splitk_scratch;     /* optional fp32 scratch (32-byte aligned): lets launches much smaller than the machine split */
+    int64_t splitk_scratch_bytes; /* their K range over up to 16 CTAs each (deterministic two-kernel reduction); NULL/0 = never */
 } p3d_conv_args_t;
 
 /* One implicit-GEMM convolution launch (tcgen05 + TMA): 3x3 / 1x1 convolutions and the four phases of a stride-2
@@ -213,6 +215,16 @@ int p3d_conv_gemm(const p3d_conv_args_t* args, p3d_stream_t stream);
 int p3d_modulate_weights(const float* weight, const float* styles, int B, int Cout, int Cin, int ktaps,
                          int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
                          float out_scale, int planes, void* out, p3d_stream_t stream);
+
+/* Two-step form of p3d_modulate_weights for weights that change rarely (inference): p3d_prepare_weights runs once
+ * per parameter version and writes weight_t [Cout][ktaps][Cin] (K-major copy) and wsq [Cout][Cin] = sum_k w^2;
+ * p3d_modulate_weights_t then streams weight_t * styles * d with d[b,o] = rsqrt(sum_i styles[b,i]^2 wsq[o,i] + 1e-8)
+ * (the same sum as :62 factored over taps). Same output layout and arguments as p3d_modulate_weights; needs
+ * Cin_padded % 8 == 0 and 256 % (Cin_padded / 8) == 0, else P3D_UNSUPPORTED. */
+int p3d_prepare_weights(const float* weight, int Cout, int Cin, int ktaps, float* weight_t, float* wsq, p3d_stream_t stream);
+int p3d_modulate_weights_t(const float* weight_t, const float* wsq, const float* styles, int B, int Cout, int Cin, int ktaps,
+                           int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
+                           float out_scale, int planes, void* out, p3d_stream_t stream);
 
 /* Every style affine of a synthesis stack in one launch (layer.affine(w) of SynthesisLayer.forward / ToRGBLayer.forward,
  * networks_stylegan2.py:313-315, 354-355; FullyConnectedLayer.forward :111-123 with the weight and bias gains already

@@ -69,6 +69,9 @@ _SIGNATURES = {
                                  ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), c_int, c_int, c_int, c_int, c_float,
                                  c_int, c_float, c_float, c_float, c_int64, c_void_p]),
     'p3d_conv_gemm': (c_int, [c_void_p, c_void_p]),
+    'p3d_prepare_weights': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'p3d_modulate_weights_t': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                       c_float, c_int, c_void_p, c_void_p]),
     'p3d_affine_batch': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'p3d_modulate_weights': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                      c_int, c_void_p, c_void_p]),

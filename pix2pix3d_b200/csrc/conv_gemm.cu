@@ -42,6 +42,9 @@ struct ConvKernelArgs {
     const float* bias; const float* noise; const float* dscale;
     float alpha, clamp, acc_scale;
     int base_aligned;                 // y / y_lo are 32-byte aligned (256-bit stores allowed)
+    int splits;                       // split-K: blockIdx.z = b * splits + s; s covers k-steps [s*total/splits, (s+1)*total/splits)
+    float* partial;                   // split-K: raw fp32 accumulators [splits][B][gH][gW][Cout_pad] (finished by a second kernel)
+    int Cout_pad;
     float pre_gain, post_gain;        // gain folded into scale/bias/noise (lrelu is positively homogeneous) or applied last
 };
 
@@ -86,10 +89,13 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
     float* s_bias = s_scale + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y, b = blockIdx.z;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int b = blockIdx.z / a.splits, ksplit = blockIdx.z - b * a.splits;
     const int ty = tile_m / a.tiles_x, tx = tile_m % a.tiles_x;
     const int n0 = tile_n * a.BN;
-    const int total_k = a.n_groups * a.kc_steps;
+    const int all_k = a.n_groups * a.kc_steps;
+    const int k_begin = (int)((long long)all_k * ksplit / a.splits), k_end = (int)((long long)all_k * (ksplit + 1) / a.splits);
+    const int total_k = k_end - k_begin;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -124,18 +130,18 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int g = 0; g < a.n_groups; ++g) {
+            int g = k_begin / a.kc_steps, kc = k_begin - g * a.kc_steps;
+            for (int k = 0; k < total_k; ++k) {
                 const int x0 = tx * a.BW + a.dx[g], y0 = ty * a.BH + a.dy[g];
                 const int kb = a.tap[g] * a.Cin;
-                for (int kc = 0; kc < a.kc_steps; ++kc) {
-                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    tc::mbar_expect_tx(&full_bar[stage], stage_bytes);
-                    tc::tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, x0, y0, b, a.a_plane[g]);
-                    tc::tma_load_4d(sb, &tmB, &full_bar[stage], kb + kc * kBK, n0, a.w_per_sample ? b : 0, a.b_plane[g]);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
-                }
+                tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                tc::mbar_expect_tx(&full_bar[stage], stage_bytes);
+                tc::tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, x0, y0, b, a.a_plane[g]);
+                tc::tma_load_4d(sb, &tmB, &full_bar[stage], kb + kc * kBK, n0, a.w_per_sample ? b : 0, a.b_plane[g]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++kc == a.kc_steps) { kc = 0; ++g; }
             }
         }
     } else if (warp == 1) {
@@ -178,6 +184,18 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
             tc::tmem_ld_wait();
             if (!pix_ok) continue;
             const int ch0 = n0 + c0;
+            if (a.partial) {
+                // split-K: raw accumulators of this k-range; conv_splitk_finish_kernel sums the ranges and applies the epilogue
+                float* pp = a.partial + ((((size_t)ksplit * gridDim.z / a.splits + b) * a.gH + gy) * a.gW + gx) * a.Cout_pad + ch0;
+                const int ncols = min(32, a.BN - c0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (8 * j < ncols) {
+                        const uint32_t o[8] = {v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]};
+                        st_global_256(pp + 8 * j, o);
+                    }
+                continue;
+            }
             if (ch0 >= a.Cout) continue;
             const size_t off = pix * a.y_cstride + a.y_coff + ch0;
             if (vec_ok) {
@@ -253,6 +271,54 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// Second half of a split-K convolution: sums the k-range partials in a fixed order (deterministic) and applies the same
+// epilogue as the fused path. One thread per (pixel, 4 channels).
+__global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const ConvKernelArgs a, int B, int act) {
+    const int cq = a.Cout_pad >> 2;
+    const size_t total = (size_t)B * a.gH * a.gW * cq;
+    const size_t split_stride = (size_t)B * a.gH * a.gW * a.Cout_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % cq) * 4;
+        size_t t = idx / cq;
+        const int gx = (int)(t % a.gW); t /= a.gW;
+        const int gy = (int)(t % a.gH);
+        const int b = (int)(t / a.gH);
+        if (c4 >= a.Cout) continue;
+        const float* pp = a.partial + (((size_t)b * a.gH + gy) * a.gW + gx) * a.Cout_pad + c4;
+        float4 acc = *reinterpret_cast<const float4*>(pp);
+        for (int s = 1; s < a.splits; ++s) {
+            const float4 q = *reinterpret_cast<const float4*>(pp + s * split_stride);
+            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+        }
+        const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
+        const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
+        const float nz = a.noise ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+        const float accv[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ch = c4 + k;
+            if (ch >= a.Cout) break;
+            float sc = a.acc_scale * a.pre_gain;
+            if (a.dscale) sc *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
+            const float bi = a.bias ? __ldg(a.bias + ch) * a.pre_gain : 0.f;
+            float x = fmaf(accv[k], sc, bi) + nz;
+            if (act == 1) x = fmaxf(x, x * a.alpha);
+            if (act == 2) x = x > 0.f ? x : x * a.alpha;
+            x *= a.post_gain;
+            if (a.clamp >= 0.f) x = fminf(fmaxf(x, -a.clamp), a.clamp);
+            const size_t off = pix * a.y_cstride + a.y_coff + ch;
+            if (a.out_mode <= 1) {
+                const __half h = __float2half_rn(x);
+                reinterpret_cast<__half*>(a.y)[off] = h;
+                if (a.out_mode == 1) reinterpret_cast<__half*>(a.y_lo)[off] = __float2half_rn(x - __half2float(h));
+            } else {
+                float* yf = reinterpret_cast<float*>(a.y) + off;
+                *yf = (a.out_mode == 3 ? *yf : 0.f) + x;
+            }
+        }
     }
 }
 
@@ -347,7 +413,25 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     // Grids that leave at most one CTA per SM anyway (the 4^2..32^2 backbone layers: 16-128 CTAs with 200+ k-steps each)
     // are bound by TMA latency x bytes in flight instead; they get a 6-stage ring (192 KB).
     dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
-    const bool deep = (long)grid.x * grid.y * grid.z <= sm_count() && a.n_groups * a.kc_steps > 6;
+    const int total_k = a.n_groups * a.kc_steps;
+    const long base_ctas = (long)grid.x * grid.y * grid.z;
+    // split-K for grids far smaller than the machine (4^2..16^2 layers: 16-32 CTAs each streaming 100-200 k-steps at
+    // the per-SM L2 ingest rate): every k-range becomes its own CTA writing raw fp32 partials into the caller's scratch
+    // buffer; conv_splitk_finish_kernel adds them in a fixed order and applies the epilogue.
+    a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
+    if (p->splitk_scratch && base_ctas * 2 <= sm_count() && total_k >= 8) {
+        int splits = (int)(sm_count() / base_ctas);
+        if (splits > total_k / 4) splits = total_k / 4;
+        if (splits > 16) splits = 16;
+        const size_t per_split = (size_t)p->B * p->gH * p->gW * p->Cout_padded * sizeof(float);
+        while (splits > 1 && per_split * splits > (size_t)p->splitk_scratch_bytes) --splits;
+        if (splits > 1 && (((uintptr_t)p->splitk_scratch) & 31) == 0) {
+            a.splits = splits;
+            a.partial = reinterpret_cast<float*>(p->splitk_scratch);
+            grid.z = p->B * splits;
+        }
+    }
+    const bool deep = (long)grid.x * grid.y * grid.z <= sm_count() && total_k / a.splits > 6;
     const size_t stage_bytes = (size_t)kBM * 128 + (size_t)BN * 128;
     const size_t smem = (deep ? 6 : 3) * stage_bytes + 64 + 2 * 128 * sizeof(float) + 1024 + (deep ? 64 : 0);
 #define P3D_LAUNCH_CONV_S(ST, ACT, CL)                                                                                        \
@@ -364,5 +448,13 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
 #undef P3D_LAUNCH_CONV_S
 #undef P3D_LAUNCH_CONV
     P3D_LAUNCH_CHECK();
+    if (a.splits > 1) {
+        const size_t items = (size_t)p->B * p->gH * p->gW * (p->Cout_padded / 4);
+        size_t blocks = (items + 255) / 256;
+        const size_t cap = (size_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        conv_splitk_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, p->B, act);
+        P3D_LAUNCH_CHECK();
+    }
     return P3D_OK;
 }

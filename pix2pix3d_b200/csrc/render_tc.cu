@@ -118,6 +118,15 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+// base (already offset by the lane) + 32-bit element offset in ONE IMAD.WIDE.U32; written in PTX because nvcc otherwise
+// reassociates (base + lane) + offset into a 64-bit add chain (IADD3, IADD3.X, LEA, LEA.HI.X per load)
+__device__ __forceinline__ float ldg_f32_off(const float* base, uint32_t elem_off) {
+    uint64_t addr;
+    float v;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(elem_off), "l"(base));
+    asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -230,9 +239,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             const uint32_t rb = tb32 + row * 128, swx = (uint32_t)(row & 7) << 4;
             const uint4 o0 = lds_u4(rb | (0x00u ^ swx)), o1 = lds_u4(rb | (0x10u ^ swx)), o2 = lds_u4(rb | (0x20u ^ swx));
             const uint4 x0 = lds_u4(rb | (0x30u ^ swx)), x1 = lds_u4(rb | (0x40u ^ swx)), x2 = lds_u4(rb | (0x50u ^ swx));
-            const float v00 = __ldg(pl + o0.x), v01 = __ldg(pl + o0.y), v02 = __ldg(pl + o0.z), v03 = __ldg(pl + o0.w);
-            const float v10 = __ldg(pl + o1.x), v11 = __ldg(pl + o1.y), v12 = __ldg(pl + o1.z), v13 = __ldg(pl + o1.w);
-            const float v20 = __ldg(pl + o2.x), v21 = __ldg(pl + o2.y), v22 = __ldg(pl + o2.z), v23 = __ldg(pl + o2.w);
+            const float v00 = ldg_f32_off(pl, o0.x), v01 = ldg_f32_off(pl, o0.y), v02 = ldg_f32_off(pl, o0.z), v03 = ldg_f32_off(pl, o0.w);
+            const float v10 = ldg_f32_off(pl, o1.x), v11 = ldg_f32_off(pl, o1.y), v12 = ldg_f32_off(pl, o1.z), v13 = ldg_f32_off(pl, o1.w);
+            const float v20 = ldg_f32_off(pl, o2.x), v21 = ldg_f32_off(pl, o2.y), v22 = ldg_f32_off(pl, o2.z), v23 = ldg_f32_off(pl, o2.w);
             const float f0 = fmaf(v03, __uint_as_float(x0.w), fmaf(v02, __uint_as_float(x0.z), fmaf(v01, __uint_as_float(x0.y), __fmul_rn(v00, __uint_as_float(x0.x)))));
             const float f1 = fmaf(v13, __uint_as_float(x1.w), fmaf(v12, __uint_as_float(x1.z), fmaf(v11, __uint_as_float(x1.y), __fmul_rn(v10, __uint_as_float(x1.x)))));
             const float f2 = fmaf(v23, __uint_as_float(x2.w), fmaf(v22, __uint_as_float(x2.z), fmaf(v21, __uint_as_float(x2.y), __fmul_rn(v20, __uint_as_float(x2.x)))));

@@ -98,6 +98,86 @@ __global__ void __launch_bounds__(256) modulate_weights_kernel(const float* __re
     }
 }
 
+// Static part of the weight preparation, once per parameter version: wt[o][t][i] = w[o][i][t] (K-major like the output)
+// and wsq[o][i] = sum_t w[o][i][t]^2, so that the per-step kernel below is a pure stream and the demodulation
+// coefficient is a dot product: d[b,o] = rsqrt(sum_i styles[b,i]^2 * wsq[o,i] + 1e-8).
+__global__ void __launch_bounds__(256) prepare_weights_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                                              float* __restrict__ wsq, int Cin, int ktaps) {
+    const int o = blockIdx.x;
+    for (int i = threadIdx.x; i < Cin; i += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < ktaps; ++t) {
+            const float v = __ldg(w + ((size_t)o * Cin + i) * ktaps + t);
+            wt[((size_t)o * ktaps + t) * Cin + i] = v;
+            acc = fmaf(v, v, acc);
+        }
+        wsq[(size_t)o * Cin + i] = acc;
+    }
+}
+
+// One CTA per output channel, all samples. Thread = (8-channel chunk, tap row); no integer division in the loops.
+__global__ void __launch_bounds__(256) modulate_weights_t_kernel(const float* __restrict__ wt, const float* __restrict__ wsq,
+                                                                 const float* __restrict__ styles, int Cout, int Cin, int ktaps,
+                                                                 int Cout_p, int Cin_p, int cin_off, int demod, float pre_scale,
+                                                                 float out_scale, int planes, int B, __half* __restrict__ out) {
+    __shared__ float dsm[64];
+    const int o = blockIdx.x;
+    const size_t row_elems = (size_t)ktaps * Cin_p;
+    const size_t plane_stride = (size_t)B * Cout_p * row_elems;
+    const int nchunk = Cin_p >> 3;                 // host guarantees Cin_p % 8 == 0 and 256 % nchunk == 0
+    const int chunk = threadIdx.x % nchunk, trow = threadIdx.x / nchunk, tstep = 256 / nchunk;
+    const int ip = chunk * 8;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    if (o >= Cout) {                               // channel padding rows
+        for (int b = 0; b < B; ++b) {
+            __half* dst = out + ((size_t)b * Cout_p + o) * row_elems;
+            for (int t = trow; t < ktaps; t += tstep) {
+                *reinterpret_cast<uint4*>(dst + (size_t)t * Cin_p + ip) = zero4;
+                if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride + (size_t)t * Cin_p + ip) = zero4;
+            }
+        }
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b0 = 0; b0 < B; b0 += 64) {
+        __syncthreads();
+        const int nb = min(64, B - b0);
+        for (int b = warp; b < nb; b += 8) {       // one warp per sample: demodulation coefficient
+            float acc = 0.f;
+            if (demod)
+                for (int i = lane; i < Cin; i += 32) {
+                    const float sv = __ldg(styles + (size_t)(b0 + b) * Cin + i) * pre_scale;
+                    acc = fmaf(sv * sv, __ldg(wsq + (size_t)o * Cin + i), acc);
+                }
+            acc = warp_sum(acc);
+            if (lane == 0) dsm[b] = (demod ? rsqrtf(acc + 1e-8f) : 1.f) * out_scale;
+        }
+        __syncthreads();
+        for (int b = 0; b < nb; ++b) {
+            const float ds = dsm[b];
+            float sv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = ip + k - cin_off;
+                sv[k] = (i >= 0 && i < Cin) ? __ldg(styles + (size_t)(b0 + b) * Cin + i) * pre_scale * ds : 0.f;
+            }
+            __half* dst = out + ((size_t)(b0 + b) * Cout_p + o) * row_elems;
+            for (int t = trow; t < ktaps; t += tstep) {
+                const float* wr = wt + ((size_t)o * ktaps + t) * Cin;
+                __align__(16) __half hv[8], lv[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = ip + k - cin_off;
+                    const float val = (i >= 0 && i < Cin) ? __ldg(wr + i) * sv[k] : 0.f;
+                    split_half(val, hv[k], lv[k]);
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)t * Cin_p + ip) = *reinterpret_cast<const uint4*>(hv);
+                if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride + (size_t)t * Cin_p + ip) = *reinterpret_cast<const uint4*>(lv);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCHW (fp32 / fp16) -> NHWC fp16 (1 or 2 planes, channel-padded); NHWC fp32 -> NCHW fp32
 // ---------------------------------------------------------------------------------------------
@@ -390,6 +470,27 @@ extern "C" int p3d_modulate_weights(const float* weight, const float* styles, in
         P3D_CUDA_TRY(cudaFuncSetAttribute(modulate_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     modulate_weights_kernel<<<Cout_padded, 256, smem, (cudaStream_t)stream>>>(weight, styles, Cout, Cin, ktaps, Cout_padded, Cin_padded,
                                                                     cin_offset, demodulate, pre_scale, out_scale, planes, B, (__half*)out);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+extern "C" int p3d_prepare_weights(const float* weight, int Cout, int Cin, int ktaps, float* weight_t, float* wsq, p3d_stream_t stream) {
+    if (!weight || !weight_t || !wsq || Cout <= 0 || Cin <= 0 || ktaps <= 0) return P3D_BAD_ARG;
+    prepare_weights_kernel<<<Cout, 256, 0, (cudaStream_t)stream>>>(weight, weight_t, wsq, Cin, ktaps);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+extern "C" int p3d_modulate_weights_t(const float* weight_t, const float* wsq, const float* styles, int B, int Cout, int Cin, int ktaps,
+                                      int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
+                                      float out_scale, int planes, void* out, p3d_stream_t stream) {
+    if (!weight_t || !wsq || !styles || !out || B <= 0 || Cout <= 0 || Cin <= 0 || ktaps <= 0) return P3D_BAD_ARG;
+    if (Cout_padded < Cout || cin_offset < 0 || Cin_padded < Cin + cin_offset || planes < 1 || planes > 2) return P3D_BAD_ARG;
+    const int nchunk = Cin_padded / 8;
+    if (Cin_padded % 8 != 0 || nchunk > 256 || 256 % nchunk != 0) return P3D_UNSUPPORTED;
+    modulate_weights_t_kernel<<<Cout_padded, 256, 0, (cudaStream_t)stream>>>(weight_t, wsq, styles, Cout, Cin, ktaps, Cout_padded,
+                                                                             Cin_padded, cin_offset, demodulate, pre_scale, out_scale,
+                                                                             planes, B, (__half*)out);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

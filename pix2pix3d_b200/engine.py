@@ -79,6 +79,10 @@ def _bias(layer, n):
     return _cached(layer, ('bias', n), [layer.bias], lambda: _pad_vec(layer.bias, n))
 
 
+def _prepared(layer):
+    return _cached(layer, 'wprep', [layer.weight], lambda: tcconv.prepare_weights(layer.weight))
+
+
 def _noise(layer, noise_mode):
     if noise_mode == 'const' and layer.use_noise:
         return _cached(layer, 'noise', [layer.noise_const, layer.noise_strength],
@@ -157,7 +161,8 @@ def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0)
     cin_p = x.shape[-1]
     cout = layer.out_channels
     cout_p = tcconv.pad_to(cout, 64)
-    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset)
+    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset,
+                                 prepared=_prepared(layer))
     noise = _noise(layer, noise_mode)
     bias = _bias(layer, cout_p)
     act_gain = layer.act_gain * gain
@@ -187,7 +192,7 @@ def torgb_layer(layer, x, styles, img, split):
     b = styles.shape[0]
     cout = layer.out_channels
     wk = tcconv.modulate_weights(layer.weight, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes,
-                                 cin_padded=x.shape[-1])
+                                 cin_padded=x.shape[-1], prepared=_prepared(layer))
     h, w = x.shape[2], x.shape[3]
     bias = _bias(layer, cout)
     clamp = float(layer.conv_clamp) if layer.conv_clamp is not None else -1.0

@@ -28,6 +28,7 @@ class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
         ('bias', ctypes.c_void_p), ('noise', ctypes.c_void_p), ('dscale', ctypes.c_void_p),
         ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
         ('acc_scale', ctypes.c_float),
+        ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64),
     ]
 
 
@@ -63,15 +64,39 @@ def nhwc_to_nchw_f32(x, channels=None, c_offset=0):
     return out
 
 
-def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, cin_padded=None, out_scale=WEIGHT_SCALE,
-                     cin_offset=0):
-    """weight [O,I,kh,kw] fp32, styles [B,I] fp32 -> [planes,B,Op,kh*kw*Ip] fp16, K-major (tap-major, then channel)."""
+def prepare_weights(weight):
+    """weight [O,I,kh,kw] fp32 -> (weight_t [O,kh*kw,I], wsq [O,I]): the parameter-only part of modulate_weights."""
     w = weight.detach().float().contiguous()
-    s = styles.detach().float().contiguous()
     o, i, kh, kw = w.shape
+    wt = torch.empty(o, kh * kw, i, device=w.device, dtype=torch.float32)
+    wsq = torch.empty(o, i, device=w.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        st = _lib.lib().p3d_prepare_weights(_lib.ptr(w), o, i, kh * kw, _lib.ptr(wt), _lib.ptr(wsq), _lib.stream_ptr())
+    _lib.check(st, 'p3d_prepare_weights')
+    _lib.bump()
+    return wt, wsq
+
+
+def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, cin_padded=None, out_scale=WEIGHT_SCALE,
+                     cin_offset=0, prepared=None):
+    """weight [O,I,kh,kw] fp32, styles [B,I] fp32 -> [planes,B,Op,kh*kw*Ip] fp16, K-major (tap-major, then channel).
+    `prepared` = prepare_weights(weight) selects the streaming two-step kernel."""
+    s = styles.detach().float().contiguous()
+    o, i, kh, kw = weight.shape
     b = s.shape[0]
     op, ip = pad_to(o, 16), (cin_padded or pad_to(i, 64))
-    out = torch.empty(planes, b, op, kh * kw * ip, device=w.device, dtype=torch.float16)
+    out = torch.empty(planes, b, op, kh * kw * ip, device=s.device, dtype=torch.float16)
+    nchunk = ip // 8
+    if prepared is not None and ip % 8 == 0 and nchunk <= 256 and 256 % nchunk == 0:
+        wt, wsq = prepared
+        with torch.cuda.device(s.device):
+            st = _lib.lib().p3d_modulate_weights_t(_lib.ptr(wt), _lib.ptr(wsq), _lib.ptr(s), b, o, i, kh * kw, op, ip, cin_offset,
+                                                   1 if demodulate else 0, float(pre_scale), float(out_scale), planes, _lib.ptr(out),
+                                                   _lib.stream_ptr())
+        _lib.check(st, 'p3d_modulate_weights_t')
+        _lib.bump()
+        return out
+    w = weight.detach().float().contiguous()
     with torch.cuda.device(w.device):
         st = _lib.lib().p3d_modulate_weights(_lib.ptr(w), _lib.ptr(s), b, o, i, kh * kw, op, ip, cin_offset, 1 if demodulate else 0,
                                              float(pre_scale), float(out_scale), planes, _lib.ptr(out), _lib.stream_ptr())
@@ -93,8 +118,22 @@ def affine_batch(ws, weight, bias, meta, out_numel):
     return out
 
 
+_SPLITK_SCRATCH = {}
+
+
+def _splitk_scratch(device):
+    """One fp32 scratch buffer per (device, stream) for split-K partial sums (launches on a stream are ordered, so consecutive
+    convolutions can share it)."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _SPLITK_SCRATCH.get(key)
+    if buf is None:
+        buf = torch.empty(8 << 20, device=device, dtype=torch.float32)      # 32 MB
+        _SPLITK_SCRATCH[key] = buf
+    return buf
+
+
 def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
-              noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE):
+              noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True):
     """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;
     out: NHWC tensor [B,oH,oW,Cs] (fp16 or fp32); out_map = (sy, oy, sx, ox)."""
     xp, b, h, wd, c = x.shape
@@ -126,6 +165,9 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
     for t in (bias, noise, dscale):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     a.act, a.alpha, a.gain, a.clamp, a.acc_scale = act, alpha, gain, clamp, acc_scale
+    if split_k:
+        scratch = _splitk_scratch(x.device)
+        a.splitk_scratch, a.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
     with torch.cuda.device(x.device):
         st = _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr())
     _lib.check(st, 'p3d_conv_gemm')

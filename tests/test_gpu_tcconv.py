@@ -120,14 +120,41 @@ def test_epilogue_noise_bias_lrelu_clamp_and_output_modes():
     assert rel_err((acc - 1).permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 3e-6
 
 
+def test_split_k_small_grids_match_single_pass_order():
+    """4^2..16^2 backbone layers: the K range is split over up to 16 CTAs and reduced by a second kernel (deterministic)."""
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(11)
+    b, c, h, w, cout = 2, 512, 8, 8, 512
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    bias = torch.randn(cout, device='cuda')
+    noise = torch.randn(h, w, device='cuda') * 0.5
+    xn = tcconv.to_nhwc_f16(x, planes=2)
+    wk = _weights_kmajor(wt, planes=2, scale=tcconv.WEIGHT_SCALE)
+    kw = dict(split=True, bias=bias, noise=noise, act=3, alpha=0.2, gain=float(np.sqrt(2)))
+    outs = []
+    for split_k in (False, True, True):
+        hi = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float16)
+        lo = torch.zeros_like(hi)
+        tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), hi, out_lo=lo, out_mode=1, split_k=split_k, **kw)
+        outs.append(hi.float() + lo.float())
+    assert torch.equal(outs[1], outs[2])                                   # fixed reduction order
+    ref = F.conv2d(x.double().cpu(), wt.double().cpu(), padding=1) + noise.double().cpu() + bias.double().cpu()[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) * np.sqrt(2)
+    for o in outs:
+        assert rel_err(o.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < 2e-5
+    assert rel_err(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 2e-6
+
+
 def test_modulate_weights_matches_modulated_conv2d_formula():
     from pix2pix3d_b200 import tcconv
     torch.manual_seed(5)
     b, o, i = 3, 40, 100
     wt = torch.randn(o, i, 3, 3, device='cuda')
     st = torch.randn(b, i, device='cuda') + 1
-    for demod in (True, False):
-        wk = tcconv.modulate_weights(wt, st, demodulate=demod, pre_scale=0.7, planes=2, out_scale=4.0)
+    prep = tcconv.prepare_weights(wt)
+    for demod, prepared in ((True, None), (False, None), (True, prep), (False, prep)):
+        wk = tcconv.modulate_weights(wt, st, demodulate=demod, pre_scale=0.7, planes=2, out_scale=4.0, prepared=prepared)
         assert wk.shape == (2, b, 48, 9 * 128)
         w = wt.double()[None] * (st.double() * 0.7)[:, None, :, None, None]
         if demod:
@@ -136,6 +163,15 @@ def test_modulate_weights_matches_modulated_conv2d_formula():
         ref[:, :o, :, :i] = (w * 4.0).permute(0, 1, 3, 4, 2).reshape(b, o, 9, i)
         got = (wk[0].double() + wk[1].double()).reshape(b, 48, 9, 128)
         assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    # channel-slice form (cin_offset) through both kernels
+    for prepared in (None, prep):
+        wk = tcconv.modulate_weights(wt, st, demodulate=True, planes=1, cin_padded=256, cin_offset=128, prepared=prepared)
+        got = wk[0].double().reshape(b, 48, 9, 256)
+        assert float(got[..., :128].abs().max()) == 0 and float(got[..., 228:].abs().max()) == 0
+        w = wt.double()[None] * st.double()[:, None, :, None, None]
+        w = w * (w.square().sum(dim=[2, 3, 4], keepdim=True) + 1e-8).rsqrt() * tcconv.WEIGHT_SCALE
+        ref = w.permute(0, 1, 3, 4, 2).reshape(b, o, 9, i)
+        assert rel_err(got[:, :o, :, 128:228].cpu().numpy(), ref.cpu().numpy()) < 2e-3     # single fp16 plane
 
 
 def test_layout_converters_roundtrip():
