@@ -247,7 +247,8 @@ def main():
     launches = graphed.native_launches if graphed is not None else (_lib.launch_count - launches0) / args.steps
     kev = native.kernel_events
     native.kernel_events = None
-    render_ms = [a.elapsed_time(b) for (name, a, b) in kev if name == 'render_fwd']
+    render_ms = [e[1].elapsed_time(e[2]) for e in kev if e[0] == 'render_fwd']
+    conv_ev = [e for e in kev if e[0] == 'conv_gemm']
     if not render_ms:
         # graph replay hides individual launches: time the render kernel inside eager steps of the same workload
         native.kernel_events = []
@@ -255,7 +256,8 @@ def main():
             for _ in range(max(3, args.steps)):
                 G.synthesis(ws, c, **syn_kw)
         torch.cuda.synchronize()
-        render_ms = [a.elapsed_time(b) for (name, a, b) in native.kernel_events if name == 'render_fwd'][1:]
+        render_ms = [e[1].elapsed_time(e[2]) for e in native.kernel_events if e[0] == 'render_fwd'][1:]
+        conv_ev = [e for e in native.kernel_events if e[0] == 'conv_gemm']
         native.kernel_events = None
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1000.0)
@@ -298,9 +300,27 @@ def main():
         t_k = sum(render_ms) / len(render_ms) / 1000.0
         achieved = alg_bytes / t_k / 1e9
         roofline = {'kernel': 'render_fwd_tc_kernel' if native.render_impl in ('auto', 'tc') else 'render_fwd_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
+                    'frac': achieved / peaks['hbm_gbs'],
+                    # dram__bytes_read + write of this kernel at this workload from the ncu --set full capture summarised in
+                    # profiles/r01_render_fwd_tc_ncu.md (config 2, B=4); not re-measured here
+                    'traffic': 100.1e6 if (WORKLOAD == 'seg2cat_512' and B == 4) else None, 'peak_source': peak_src,
                     'kernel_ms': t_k * 1000, 'algorithmic_bytes': alg_bytes, 'share_of_step': t_k * 1000 / (ms / args.steps),
                     'rays_per_s': B * nrr * nrr / t_k}
+
+    # second bound: the tensor-core convolutions (62 launches per step), algorithmic FLOPs / summed launch time
+    roofline_tensor = None
+    if conv_ev:
+        per_step = len(conv_ev) // max(1, len(render_ms) + 1)
+        use = conv_ev[per_step:] if per_step and len(conv_ev) > per_step else conv_ev      # drop the first (cold) step
+        t_c = sum(e[1].elapsed_time(e[2]) for e in use) / 1000.0
+        fl_alg, fl_exec = sum(e[3] for e in use), sum(e[4] for e in use)
+        n_steps = max(1, len(use) // max(1, per_step))
+        roofline_tensor = {'kernel': 'conv_gemm_kernel', 'bound': 'tensor', 'achieved': fl_alg / t_c / 1e12, 'peak': peaks['bf16_tflops'],
+                           'unit': 'TFLOP/s', 'frac': fl_alg / t_c / 1e12 / peaks['bf16_tflops'],
+                           'executed_tflops': fl_exec / t_c / 1e12, 'launches_per_step': per_step,
+                           'ms_per_step': t_c * 1000 / n_steps,
+                           'note': 'fp32 backbone layers execute 3 fp16 passes per algorithmic FLOP (hi/lo split); '
+                                   'event pairs around single launches in eager steps'}
 
     # ---- CPU baseline: the oracle port on the host cores, one image ----------------------------
     cpu_baseline = None
@@ -326,7 +346,7 @@ def main():
         'gpu_launches': launches,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
-        'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+        'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor, 'cpu_baseline': cpu_baseline,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -240,6 +240,16 @@ SYNTH_CASES = {
 }
 
 
+# TriPlaneSemanticGenerator (two backbones + ImportanceSemanticRenderer, triplane_cond.py:724-849)
+SEMGEN_CASES = {
+    'semgen_tiny': dict(seed=31, cls='TriPlaneSemanticGenerator', img_resolution=128, semantic_channels=6, nrr=16, Sc=12, Sf=12,
+                        B=2, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask_plain', in_res=32, w_dim=64),
+    'semgen_edge': dict(seed=32, cls='TriPlaneSemanticGenerator', img_resolution=128, semantic_channels=1, nrr=16, Sc=8, Sf=8,
+                        B=1, channel_base=1024, channel_max=16, ray=(0.1, 2.6, 1.6), white_back=True, mapping='edge_plain',
+                        in_res=32, w_dim=64),
+}
+
+
 def synth_kwargs(case):
     sem = case['semantic_channels']
     rk = dict(image_resolution=case['img_resolution'], disparity_space_sampling=False, clamp_mode='softplus',
@@ -251,12 +261,14 @@ def synth_kwargs(case):
               ray_end=case['ray'][1], box_warp=case['ray'][2], avg_camera_radius=2.7, avg_camera_pivot=[0, 0, -0.06])
     if case.get('white_back'):
         rk['white_back'] = True
-    mk = dict(class_name='training.triplane_cond.' + ('MaskMappingNetwork_disentangle' if case['mapping'] == 'mask'
-                                                      else 'EdgeMappingNetwork_disentangle'),
-              num_layers=2, in_resolution=case['in_res'], in_channels=max(sem, 1) if case['mapping'] == 'mask' else 1)
-    if case['mapping'] == 'mask' and sem == 0:
+    mclass = {'mask': 'MaskMappingNetwork_disentangle', 'edge': 'EdgeMappingNetwork_disentangle',
+              'mask_plain': 'MaskMappingNetwork', 'edge_plain': 'EdgeMappingNetwork'}[case['mapping']]
+    is_mask = case['mapping'].startswith('mask')
+    mk = dict(class_name='training.triplane_cond.' + mclass,
+              num_layers=2, in_resolution=case['in_res'], in_channels=max(sem, 1) if is_mask else 1)
+    if is_mask and sem == 0:
         mk['in_channels'] = 6
-    kw = dict(z_dim=32, c_dim=25, w_dim=512, img_resolution=case['img_resolution'], img_channels=3, mapping_kwargs=mk,
+    kw = dict(z_dim=32, c_dim=25, w_dim=case.get('w_dim', 512), img_resolution=case['img_resolution'], img_channels=3, mapping_kwargs=mk,
               rendering_kwargs=rk, channel_base=case['channel_base'], channel_max=case['channel_max'],
               fused_modconv_default='inference_only', num_fp16_res=0, sr_num_fp16_res=4, conv_clamp=None,
               sr_kwargs=dict(channel_base=case['channel_base'], channel_max=case['channel_max'],
@@ -285,7 +297,7 @@ def synth_inputs(case):
     B = case['B']
     z = torch.randn(B, 32, generator=g)
     c = poses(B, case['seed'])
-    if case['mapping'] == 'mask':
+    if case['mapping'].startswith('mask'):
         nclass = max(case['semantic_channels'], 1) if case['semantic_channels'] else 6
         blocks = torch.randint(0, nclass, (B, 1, 4, 4), generator=g)
         mask = blocks.repeat_interleave(case['in_res'] // 4, 2).repeat_interleave(case['in_res'] // 4, 3)
@@ -318,15 +330,45 @@ def golden_synthesis():
         print('synthesis', name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def golden_semgen():
+    import training.triplane_cond as ref_tc
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 else None
+    for name, case in SEMGEN_CASES.items():
+        if only is not None and name not in only:
+            continue
+        G = build_generator(ref_tc, case)
+        z, c, mask = synth_inputs(case)
+        draws = []
+        with torch.no_grad():
+            ws = G.mapping(z, c, {'mask': mask, 'pose': c})
+            with capture_rand(draws):
+                out = G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=case['nrr'])
+            wd = case['w_dim']
+            pt = G.backbone.synthesis(ws[..., :wd], noise_mode='const')
+            ps = G.backbone_semantic.synthesis(ws[..., wd:], noise_mode='const')
+            pts = torch.rand(case['B'], 50, 3, generator=torch.Generator().manual_seed(9)) - 0.5
+            smp = G.sample_mixed(pts, None, ws, noise_mode='const')
+        save = dict(z=z, c=c, mask=mask, ws=ws, jitter=draws[0][1], u=draws[1][1],
+                    planes_texture_sub=pt[:, :, 3::16, 5::16].contiguous(), planes_semantic_sub=ps[:, :, 3::16, 5::16].contiguous(),
+                    pts=pts, sample_rgb=smp['rgb'], sample_sigma=smp['sigma'], sample_semantic=smp['semantic'],
+                    **{'out_' + k: v for k, v in out.items()})
+        arrays = {k: v.detach().numpy() for k, v in save.items()}
+        arrays['state_digest'] = np.frombuffer(state_digest(G).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, f'synthesis_{name}.npz'), **arrays)
+        print('semgen', name, {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == '__main__':
     assert os.path.isdir(REF), 'the reference checkout is only available in the authoring container'
     sys.path.insert(0, REF)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['renderer', 'ops', 'synthesis']
+    which = sys.argv[1:] or ['renderer', 'ops', 'synthesis', 'semgen']
     if 'renderer' in which:
         golden_renderer()
     if 'ops' in which:
         golden_ops()
     if 'synthesis' in which:
         golden_synthesis()
+    if 'semgen' in which:
+        golden_semgen()

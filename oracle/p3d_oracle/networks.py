@@ -197,3 +197,43 @@ def generator_synthesis(ws, c, sd, cfg, jitter, u, noise_mode='const'):
                                                          noise_mode=sr_noise, fused_modconv=fused,
                                                          use_fp16_clamp=cfg.get('sr_fp16', True), return_raw=True)
     return out
+
+
+def generator_synthesis_semantic(ws, c, sd, cfg, jitter, u, noise_mode='const'):
+    """TriPlaneSemanticGenerator.synthesis (triplane_cond.py:772-822): ws[..., :w_dim] drives the texture backbone and the
+    colour super-resolution, ws[..., w_dim:] the semantic backbone and the semantic super-resolution."""
+    ws = np.asarray(ws, f32)
+    c = np.asarray(c, f32)
+    rk = cfg['rendering_kwargs']
+    nrr, wd, cs = cfg['nrr'], cfg['w_dim'], cfg['semantic_channels']
+    n = ws.shape[0]
+    ws_t, ws_s = np.ascontiguousarray(ws[..., :wd]), np.ascontiguousarray(ws[..., wd:])
+    origins, dirs = R.ray_sampler(c[:, :16].reshape(-1, 4, 4), c[:, 16:25].reshape(-1, 3, 3), nrr)
+    fused = cfg.get('fused_modconv', True)
+    res = cfg.get('plane_res', 256)
+    pt = synthesis_network(ws_t, sd, 'backbone.synthesis', res, noise_mode=noise_mode, fused_modconv=fused,
+                           conv_clamp=cfg.get('conv_clamp', None))
+    ps = synthesis_network(ws_s, sd, 'backbone_semantic.synthesis', res, noise_mode=noise_mode, fused_modconv=fused,
+                           conv_clamp=cfg.get('conv_clamp', None))
+    pt = pt.reshape(n, 3, 32, pt.shape[-2], pt.shape[-1])
+    ps = ps.reshape(n, 3, 32, ps.shape[-2], ps.shape[-1])
+    lr = rk.get('decoder_lr_mul', 1)
+    dec_t = decoder_from_state_dict(sd, 'decoder', 'OSGDecoder', lr_mul=lr)
+    dec_s = decoder_from_state_dict(sd, 'decoder_semantic', 'OSGDecoder_semantic', semantic_sigmoid=(cs == 1), lr_mul=lr)
+    m = nrr * nrr
+    depths_coarse = R.sample_stratified(n, m, rk['ray_start'], rk['ray_end'], rk['depth_resolution'], jitter,
+                                        rk.get('disparity_space_sampling', False))
+    feats, depth, _ = R.importance_semantic_renderer(pt, ps, dec_t, dec_s, origins, dirs, depths_coarse, u, rk)
+    fimg = np.ascontiguousarray(feats.transpose(0, 2, 1).reshape(n, feats.shape[-1], nrr, nrr))
+    dimg = depth.transpose(0, 2, 1).reshape(n, 1, nrr, nrr)
+    sr_noise = rk['superresolution_noise_mode']
+    half = fimg.shape[1] // 2
+    rgb_f, sem_f = fimg[:, :half], fimg[:, half:]
+    out = {'image_depth': dimg, 'planes_texture': pt, 'planes_semantic': ps}
+    out['image'], out['image_raw'] = superresolution(rgb_f[:, :3], rgb_f, ws_t, sd, 'superresolution', cfg['sr_kind'],
+                                                     noise_mode=sr_noise, fused_modconv=fused,
+                                                     use_fp16_clamp=cfg.get('sr_fp16', True), return_raw=True)
+    out['semantic'], out['semantic_raw'] = superresolution(sem_f[:, :cs], sem_f, ws_s, sd, 'superresolution_semantic',
+                                                           cfg['sr_kind_semantic'], noise_mode=sr_noise, fused_modconv=fused,
+                                                           use_fp16_clamp=cfg.get('sr_fp16', True), return_raw=True)
+    return out

@@ -283,3 +283,50 @@ def importance_renderer(planes, dec, ray_origins, ray_directions, depths_coarse,
     if return_debug:
         return rgb, depth, wsum.astype(f32), dbg
     return rgb, depth, wsum.astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------
+# renderer.py:256-337  ImportanceSemanticRenderer (two plane sets, two decoders)
+# ---------------------------------------------------------------------------------------------
+def run_model_semantic(planes_texture, planes_semantic, dec_texture, dec_semantic, coords, box_warp):
+    """renderer.py:324-337: sigma and semantics from the semantic decoder (semantic planes), colour from the texture
+    decoder on cat(texture, semantic) features. Returns (rgb, sigma, semantic)."""
+    f_tex = sample_from_planes(planes_texture, coords, box_warp)
+    f_sem = sample_from_planes(planes_semantic, coords, box_warp)
+    sem, sigma = decoder_forward(dec_semantic, f_sem)
+    rgb, _ = decoder_forward(dec_texture, np.concatenate([f_tex, f_sem], -1))
+    return rgb, sigma, sem
+
+
+def importance_semantic_renderer(planes_texture, planes_semantic, dec_texture, dec_semantic, ray_origins, ray_directions,
+                                 depths_coarse, u, opts):
+    """ImportanceSemanticRenderer.forward (:262-322) with the two random draws supplied explicitly; the coarse weights
+    come from the colours (:296), the composited feature is cat(colour, semantic) (:292, :314)."""
+    pt, ps = np.asarray(planes_texture, f32), np.asarray(planes_semantic, f32)
+    o = np.asarray(ray_origins, f32)
+    d = np.asarray(ray_directions, f32)
+    dc = np.asarray(depths_coarse, f32)
+    b, r, sc, _ = dc.shape
+    bw = opts['box_warp']
+    wb = bool(opts.get('white_back', False))
+
+    def shade(depths, count):
+        coords = (o[:, :, None, :] + depths * d[:, :, None, :]).reshape(b, -1, 3)
+        rgb, sigma, sem = run_model_semantic(pt, ps, dec_texture, dec_semantic, coords, bw)
+        rgb = rgb.reshape(b, r, count, -1)
+        return rgb, sigma.reshape(b, r, count, 1), np.concatenate([rgb, sem.reshape(b, r, count, -1)], -1)
+
+    colors_c, dens_c, feats_c = shade(dc, sc)
+    sf = 0 if u is None else u.shape[-1]
+    if sf > 0:
+        _, _, w_c = ray_march(colors_c, dens_c, dc, wb)
+        dfine = sample_importance(dc.reshape(b * r, sc), w_c.reshape(b * r, -1), u).reshape(b, r, sf, 1)
+        _, dens_f, feats_f = shade(dfine, sf)
+        all_d, all_f, all_s, _ = unify_samples(dc, feats_c, dens_c, dfine, feats_f, dens_f)
+        feat, depth, w = ray_march(all_f, all_s, all_d, wb)
+    else:
+        feat, depth, w = ray_march(feats_c, dens_c, dc, wb)
+    wsum = np.zeros_like(w[:, :, 0])
+    for i in range(w.shape[2]):
+        wsum = wsum + w[:, :, i]
+    return feat, depth, wsum.astype(f32)

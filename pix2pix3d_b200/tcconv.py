@@ -168,8 +168,19 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
     if split_k:
         scratch = _splitk_scratch(x.device)
         a.splitk_scratch, a.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
+    from . import native
+    ev = None
+    if native.kernel_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     with torch.cuda.device(x.device):
         st = _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr())
+    if ev is not None:
+        ev[1].record()
+        # algorithmic FLOPs of the convolution this launch implements (one pass); the fp32 layers execute 3x that on the
+        # tensor pipe (hi*hi + hi*lo + lo*hi)
+        flops = 2.0 * b * grid_hw[0] * grid_hw[1] * cout * len(taps) * c
+        native.kernel_events.append(('conv_gemm', ev[0], ev[1], flops, flops * (3 if split else 1)))
     _lib.check(st, 'p3d_conv_gemm')
     _lib.bump()
     return out

@@ -18,7 +18,7 @@ from .networks_stylegan2 import DiscriminatorBlock, FullyConnectedLayer, Synthes
 from .networks_stylegan2 import Generator as StyleGAN2Backbone
 from .triplane import OSGDecoder, _decoder_mlp, _mipnerf_sigmoid, _sr_kwargs, fast_synthesis, query_points, render_to_images
 from .volumetric_rendering.ray_sampler import RaySampler
-from .volumetric_rendering.renderer import ImportanceRenderer
+from .volumetric_rendering.renderer import ImportanceRenderer, ImportanceSemanticRenderer
 
 # ----------------------------------------------------------------------------------------------
 # Label-map encoder and mapping networks
@@ -423,6 +423,108 @@ def _semantic_heads(gen, feature_image, ws, synthesis_kwargs):
     sem_image = sem_feat[:, :gen.semantic_channels]
     sr_sem = gen.superresolution_semantic(sem_image, sem_feat, ws, noise_mode=noise_mode, **_sr_kwargs(synthesis_kwargs))
     return rgb_image, sr_image, sem_image, sr_sem
+
+
+@persistence.persistent_class
+class TriPlaneSemanticGenerator(torch.nn.Module):
+    """Separate texture and semantic tri-plane backbones rendered together by ImportanceSemanticRenderer (:724-849).
+    `ws` carries both latents side by side: [..., :w_dim] texture, [..., w_dim:] semantic."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, semantic_channels, sr_num_fp16_res=0,
+                 mapping_kwargs={}, rendering_kwargs={}, sr_kwargs={}, data_type=None, **synthesis_kwargs):
+        super().__init__()
+        self.z_dim = z_dim
+        self.c_dim = c_dim
+        self.w_dim = w_dim
+        self.img_resolution = img_resolution
+        self.img_channels = img_channels
+        self.semantic_channels = semantic_channels
+        self.data_type = data_type
+        self.renderer = ImportanceSemanticRenderer()
+        self.ray_sampler = RaySampler()
+        self.backbone = StyleGAN2Backbone(z_dim, c_dim, w_dim, img_resolution=256, img_channels=32 * 3,
+                                          mapping_kwargs=mapping_kwargs, **synthesis_kwargs)
+        self.backbone_semantic = Generator_cond(0, c_dim, w_dim, img_resolution=256, img_channels=32 * 3,
+                                                mapping_kwargs=mapping_kwargs, **synthesis_kwargs)
+        self.superresolution = dnnlib.util.construct_class_by_name(
+            class_name=rendering_kwargs['superresolution_module'], channels=32, img_resolution=img_resolution,
+            sr_num_fp16_res=sr_num_fp16_res, sr_antialias=rendering_kwargs['sr_antialias'], **sr_kwargs)
+        self.superresolution_semantic = dnnlib.util.construct_class_by_name(
+            class_name=rendering_kwargs['superresolution_module_semantic'], channels=32, img_resolution=img_resolution,
+            sr_num_fp16_res=sr_num_fp16_res, sr_antialias=rendering_kwargs['sr_antialias'],
+            semantic_channels=semantic_channels, **sr_kwargs)
+        lr_mul = rendering_kwargs.get('decoder_lr_mul', 1)
+        self.decoder = OSGDecoder(64, {'decoder_lr_mul': lr_mul, 'decoder_output_dim': 32, 'sigmoid': True})
+        self.decoder_semantic = OSGDecoder_semantic(32, {'decoder_lr_mul': lr_mul, 'decoder_output_dim': 32,
+                                                         'sigmoid': True if semantic_channels == 1 else False})
+        self.neural_rendering_resolution = 64
+        self.rendering_kwargs = rendering_kwargs
+        self._last_planes = None
+
+    def mapping(self, z, c, batch, truncation_psi=1, truncation_cutoff=None, update_emas=False):
+        if self.rendering_kwargs['c_gen_conditioning_zero']:
+            c = torch.zeros_like(c)
+        cs = c * self.rendering_kwargs.get('c_scale', 0)
+        ws_texture = self.backbone.mapping(z, cs, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff,
+                                           update_emas=update_emas)
+        ws_semantic = self.backbone_semantic.mapping(None, cs, batch, truncation_psi=truncation_psi,
+                                                     truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return torch.cat([ws_texture, ws_semantic], dim=-1)
+
+    def _planes(self, ws, update_emas, synthesis_kwargs):
+        assert ws.shape[-1] == self.w_dim * 2
+        ws_texture, ws_semantic = ws[..., :self.w_dim], ws[..., self.w_dim:]
+        pt = self.backbone.synthesis(ws_texture, update_emas=update_emas, **synthesis_kwargs)
+        ps = self.backbone_semantic.synthesis(ws_semantic, update_emas=update_emas, **synthesis_kwargs)
+        pt = pt.view(len(pt), 3, 32, pt.shape[-2], pt.shape[-1])
+        ps = ps.view(len(ps), 3, 32, ps.shape[-2], ps.shape[-1])
+        return ws_texture, ws_semantic, pt, ps
+
+    def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
+                  use_cached_backbone=False, **synthesis_kwargs):
+        cam2world = c[:, :16].view(-1, 4, 4)
+        intrinsics = c[:, 16:25].view(-1, 3, 3)
+        if neural_rendering_resolution is None:
+            neural_rendering_resolution = self.neural_rendering_resolution
+        else:
+            self.neural_rendering_resolution = neural_rendering_resolution
+        ray_origins, ray_directions = self.ray_sampler(cam2world, intrinsics, neural_rendering_resolution)
+        n = ray_origins.shape[0]
+        ws_texture, ws_semantic, planes_texture, planes_semantic = self._planes(ws, update_emas, synthesis_kwargs)
+        feats, depth, _ = self.renderer(planes_texture, planes_semantic, self.decoder, self.decoder_semantic, ray_origins,
+                                        ray_directions, self.rendering_kwargs)
+        h = w = self.neural_rendering_resolution
+        feature_image = feats.permute(0, 2, 1).reshape(n, feats.shape[-1], h, w).contiguous()
+        depth_image = depth.permute(0, 2, 1).reshape(n, 1, h, w)
+        half = feature_image.shape[1] // 2
+        rgb_feat, sem_feat = feature_image[:, :half], feature_image[:, half:]
+        noise_mode = self.rendering_kwargs['superresolution_noise_mode']
+        rgb_image = rgb_feat[:, :3]
+        sr_image = self.superresolution(rgb_image, rgb_feat, ws_texture, noise_mode=noise_mode, **_sr_kwargs(synthesis_kwargs))
+        sem_image = sem_feat[:, :self.semantic_channels]
+        sr_sem = self.superresolution_semantic(sem_image, sem_feat, ws_semantic, noise_mode=noise_mode,
+                                               **_sr_kwargs(synthesis_kwargs))
+        return {'image': sr_image, 'image_raw': rgb_image, 'image_depth': depth_image, 'semantic': sr_sem,
+                'semantic_raw': sem_image}
+
+    def sample(self, coordinates, directions, z, c, batch, truncation_psi=1, truncation_cutoff=None, update_emas=False,
+               **synthesis_kwargs):
+        ws = self.mapping(z, batch['pose'], batch, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff,
+                          update_emas=update_emas)
+        return self.sample_mixed(coordinates, directions, ws, update_emas=update_emas, **synthesis_kwargs)
+
+    def sample_mixed(self, coordinates, directions, ws, truncation_psi=1, truncation_cutoff=None, update_emas=False,
+                     **synthesis_kwargs):
+        _, _, planes_texture, planes_semantic = self._planes(ws, update_emas, synthesis_kwargs)
+        return self.renderer.run_model(planes_texture, planes_semantic, self.decoder, self.decoder_semantic, coordinates,
+                                       directions, self.rendering_kwargs)
+
+    def forward(self, z, c, batch, truncation_psi=1, truncation_cutoff=None, neural_rendering_resolution=None,
+                update_emas=False, cache_backbone=False, use_cached_backbone=False, **synthesis_kwargs):
+        ws = self.mapping(z, batch['pose'], batch, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff,
+                          update_emas=update_emas)
+        return self.synthesis(ws, c, update_emas=update_emas, neural_rendering_resolution=neural_rendering_resolution,
+                              cache_backbone=cache_backbone, use_cached_backbone=use_cached_backbone, **synthesis_kwargs)
 
 
 @persistence.persistent_class

@@ -241,3 +241,63 @@ class ImportanceRenderer(torch.nn.Module):
         denom = cdf_g[..., 1] - cdf_g[..., 0]
         denom[denom < eps] = 1
         return bins_g[..., 0] + (u - cdf_g[..., 0]) / denom * (bins_g[..., 1] - bins_g[..., 0])
+
+
+class ImportanceSemanticRenderer(ImportanceRenderer):
+    """Two tri-plane sets and two decoders (:256-438): the semantic decoder sees the semantic planes and provides the
+    density; the texture decoder sees cat(texture, semantic) features. Same two-pass sampling as ImportanceRenderer;
+    features are cat(colour, semantic). Runs stage by stage (on CUDA each stage is a libp3d kernel: tri-plane gather,
+    ray marcher, importance sampling; the decoders are two small GEMMs)."""
+
+    def forward(self, planes_texture, planes_semantic, decoder_texture, decoder_semantic, ray_origins, ray_directions,
+                rendering_options):
+        self.plane_axes = self.plane_axes.to(ray_origins.device)
+        opts = rendering_options
+        if opts['ray_start'] == opts['ray_end'] == 'auto':
+            ray_start, ray_end = math_utils.get_ray_limits_box(ray_origins, ray_directions, box_side_length=opts['box_warp'])
+            is_ray_valid = ray_end > ray_start
+            if torch.any(is_ray_valid).item():
+                ray_start[~is_ray_valid] = ray_start[is_ray_valid].min()
+                ray_end[~is_ray_valid] = ray_start[is_ray_valid].max()
+            depths_coarse = self.sample_stratified(ray_origins, ray_start, ray_end, opts['depth_resolution'],
+                                                   opts['disparity_space_sampling'])
+        else:
+            depths_coarse = self.sample_stratified(ray_origins, opts['ray_start'], opts['ray_end'], opts['depth_resolution'],
+                                                   opts['disparity_space_sampling'])
+        b, r, s, _ = depths_coarse.shape
+
+        def shade(depths, count):
+            coords = (ray_origins.unsqueeze(-2) + depths * ray_directions.unsqueeze(-2)).reshape(b, -1, 3)
+            dirs = ray_directions.unsqueeze(-2).expand(-1, -1, count, -1).reshape(b, -1, 3)
+            out = self.run_model(planes_texture, planes_semantic, decoder_texture, decoder_semantic, coords, dirs, opts)
+            colors = out['rgb'].reshape(b, r, count, out['rgb'].shape[-1])
+            sem = out['semantic'].reshape(b, r, count, out['semantic'].shape[-1])
+            return colors, out['sigma'].reshape(b, r, count, 1), torch.cat([colors, sem], -1)
+
+        colors_coarse, dens_coarse, feats_coarse = shade(depths_coarse, s)
+        n_importance = opts['depth_resolution_importance']
+        if n_importance > 0:
+            _, _, weights = self.ray_marcher(colors_coarse, dens_coarse, depths_coarse, opts)
+            depths_fine = self.sample_importance(depths_coarse, weights, n_importance)
+            _, dens_fine, feats_fine = shade(depths_fine, n_importance)
+            all_depths, all_feats, all_dens = self.unify_samples(depths_coarse, feats_coarse, dens_coarse,
+                                                                 depths_fine, feats_fine, dens_fine)
+            feat, depth, weights = self.ray_marcher(all_feats, all_dens, all_depths, opts)
+        else:
+            feat, depth, weights = self.ray_marcher(feats_coarse, dens_coarse, depths_coarse, opts)
+        return feat, depth, weights.sum(2)
+
+    def run_model(self, planes_texture, planes_semantic, decoder_texture, decoder_semantic, sample_coordinates,
+                  sample_directions, options):
+        """(:324-337) sigma and semantics from the semantic decoder, colour from the texture decoder."""
+        self.plane_axes = self.plane_axes.to(sample_coordinates.device)
+        f_tex = sample_from_planes(self.plane_axes, planes_texture, sample_coordinates, padding_mode='zeros',
+                                   box_warp=options['box_warp'])
+        f_sem = sample_from_planes(self.plane_axes, planes_semantic, sample_coordinates, padding_mode='zeros',
+                                   box_warp=options['box_warp'])
+        out_sem = decoder_semantic(f_sem, sample_directions)
+        out_tex = decoder_texture(torch.cat([f_tex, f_sem], dim=-1), sample_directions)
+        out = {'sigma': out_sem['sigma'], 'rgb': out_tex['rgb'], 'semantic': out_sem['rgb']}
+        if options.get('density_noise', 0) > 0:
+            out['sigma'] += torch.randn_like(out['sigma']) * options['density_noise']
+        return out
