@@ -243,10 +243,10 @@ SYNTH_CASES = {
 # TriPlaneSemanticGenerator (two backbones + ImportanceSemanticRenderer, triplane_cond.py:724-849)
 SEMGEN_CASES = {
     'semgen_tiny': dict(seed=31, cls='TriPlaneSemanticGenerator', img_resolution=128, semantic_channels=6, nrr=16, Sc=12, Sf=12,
-                        B=2, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask_plain', in_res=32, w_dim=64),
+                        B=2, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask_plain', in_res=32, w_dim=512),
     'semgen_edge': dict(seed=32, cls='TriPlaneSemanticGenerator', img_resolution=128, semantic_channels=1, nrr=16, Sc=8, Sf=8,
                         B=1, channel_base=1024, channel_max=16, ray=(0.1, 2.6, 1.6), white_back=True, mapping='edge_plain',
-                        in_res=32, w_dim=64),
+                        in_res=32, w_dim=512),
 }
 
 

@@ -71,6 +71,81 @@ __device__ __forceinline__ float conv_epilogue_act(float x, float alpha, float p
     return x;
 }
 
+// Epilogue of one 32-channel chunk held by a thread (= one pixel): per-channel constants from shared memory, noise,
+// activation, clamp, and the store in the requested output mode.
+template <int kAct, bool kClamp>
+__device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32_t (&v)[32], const float* s_scale,
+                                                 const float* s_bias, int c0, int ch0, size_t off, float nz, bool vec_ok) {
+    const float alpha = a.alpha, post_gain = a.post_gain, clampv = a.clamp;
+    const int out_mode = a.out_mode;
+                if (vec_ok) {
+    #pragma unroll
+                    for (int j = 0; j < 2; ++j) {           // 16 channels per step
+                        float r[16];
+    #pragma unroll
+                        for (int t4 = 0; t4 < 4; ++t4) {
+                            const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 16 * j + 4 * t4);
+                            const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + 16 * j + 4 * t4);
+                            const uint32_t* vv = v + 16 * j + 4 * t4;
+                            r[4 * t4 + 0] = fmaf(__uint_as_float(vv[0]), sc.x, bi.x) + nz;
+                            r[4 * t4 + 1] = fmaf(__uint_as_float(vv[1]), sc.y, bi.y) + nz;
+                            r[4 * t4 + 2] = fmaf(__uint_as_float(vv[2]), sc.z, bi.z) + nz;
+                            r[4 * t4 + 3] = fmaf(__uint_as_float(vv[3]), sc.w, bi.w) + nz;
+                        }
+    #pragma unroll
+                        for (int t = 0; t < 16; ++t) r[t] = conv_epilogue_act<kAct, kClamp>(r[t], alpha, post_gain, clampv);
+                        if (out_mode >= 2) {
+                            float* yp = reinterpret_cast<float*>(a.y) + off + 16 * j;
+    #pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t o[8];
+                                if (out_mode == 3) {
+                                    ld_global_256(yp + 8 * h, o);
+    #pragma unroll
+                                    for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) + r[8 * h + t]);
+                                } else {
+    #pragma unroll
+                                    for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(r[8 * h + t]);
+                                }
+                                st_global_256(yp + 8 * h, o);
+                            }
+                        } else {
+                            uint32_t oh[8], ol[8];
+    #pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const __half2 hv = __floats2half2_rn(r[2 * t], r[2 * t + 1]);
+                                oh[t] = *reinterpret_cast<const uint32_t*>(&hv);
+                                if (out_mode == 1) {
+                                    const float2 back = __half22float2(hv);
+                                    const __half2 lv = __floats2half2_rn(r[2 * t] - back.x, r[2 * t + 1] - back.y);
+                                    ol[t] = *reinterpret_cast<const uint32_t*>(&lv);
+                                }
+                            }
+                            st_global_256(reinterpret_cast<__half*>(a.y) + off + 16 * j, oh);
+                            if (out_mode == 1) st_global_256(reinterpret_cast<__half*>(a.y_lo) + off + 16 * j, ol);
+                        }
+                    }
+                } else {
+                    // ragged chunk (ToRGB's 3 channels, channel tails, unaligned concat offsets): scalar stores
+                    const int nvalid = min(32, a.Cout - ch0);
+    #pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < nvalid) {
+                            const float x = conv_epilogue_act<kAct, kClamp>(
+                                fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_bias[c0 + i]) + nz, alpha, post_gain, clampv);
+                            if (out_mode <= 1) {
+                                const __half h = __float2half_rn(x);
+                                reinterpret_cast<__half*>(a.y)[off + i] = h;
+                                if (out_mode == 1) reinterpret_cast<__half*>(a.y_lo)[off + i] = __float2half_rn(x - __half2float(h));
+                            } else {
+                                float* yf = reinterpret_cast<float*>(a.y) + off + i;
+                                *yf = (out_mode == 3 ? *yf : 0.f) + x;
+                            }
+                        }
+                    }
+                }
+}
+
 template <int kStages, int kAct, bool kClamp>
 __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
@@ -170,7 +245,6 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
         const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
         const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
-        const float alpha = a.alpha, post_gain = a.post_gain, clampv = a.clamp;
         const int out_mode = a.out_mode;
         // vector path: every 32-channel chunk of this CTA is full and its stores are 32-byte aligned
         const bool vec_ok = a.base_aligned && ((n0 + a.BN) <= a.Cout) && (a.BN % 32 == 0) &&
@@ -198,72 +272,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
             }
             if (ch0 >= a.Cout) continue;
             const size_t off = pix * a.y_cstride + a.y_coff + ch0;
-            if (vec_ok) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {           // 16 channels per step
-                    float r[16];
-#pragma unroll
-                    for (int t4 = 0; t4 < 4; ++t4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + 16 * j + 4 * t4);
-                        const float4 bi = *reinterpret_cast<const float4*>(s_bias + c0 + 16 * j + 4 * t4);
-                        const uint32_t* vv = v + 16 * j + 4 * t4;
-                        r[4 * t4 + 0] = fmaf(__uint_as_float(vv[0]), sc.x, bi.x) + nz;
-                        r[4 * t4 + 1] = fmaf(__uint_as_float(vv[1]), sc.y, bi.y) + nz;
-                        r[4 * t4 + 2] = fmaf(__uint_as_float(vv[2]), sc.z, bi.z) + nz;
-                        r[4 * t4 + 3] = fmaf(__uint_as_float(vv[3]), sc.w, bi.w) + nz;
-                    }
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) r[t] = conv_epilogue_act<kAct, kClamp>(r[t], alpha, post_gain, clampv);
-                    if (out_mode >= 2) {
-                        float* yp = reinterpret_cast<float*>(a.y) + off + 16 * j;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint32_t o[8];
-                            if (out_mode == 3) {
-                                ld_global_256(yp + 8 * h, o);
-#pragma unroll
-                                for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) + r[8 * h + t]);
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < 8; ++t) o[t] = __float_as_uint(r[8 * h + t]);
-                            }
-                            st_global_256(yp + 8 * h, o);
-                        }
-                    } else {
-                        uint32_t oh[8], ol[8];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            const __half2 hv = __floats2half2_rn(r[2 * t], r[2 * t + 1]);
-                            oh[t] = *reinterpret_cast<const uint32_t*>(&hv);
-                            if (out_mode == 1) {
-                                const float2 back = __half22float2(hv);
-                                const __half2 lv = __floats2half2_rn(r[2 * t] - back.x, r[2 * t + 1] - back.y);
-                                ol[t] = *reinterpret_cast<const uint32_t*>(&lv);
-                            }
-                        }
-                        st_global_256(reinterpret_cast<__half*>(a.y) + off + 16 * j, oh);
-                        if (out_mode == 1) st_global_256(reinterpret_cast<__half*>(a.y_lo) + off + 16 * j, ol);
-                    }
-                }
-            } else {
-                // ragged chunk (ToRGB's 3 channels, channel tails, unaligned concat offsets): scalar stores
-                const int nvalid = min(32, a.Cout - ch0);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (i < nvalid) {
-                        const float x = conv_epilogue_act<kAct, kClamp>(
-                            fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_bias[c0 + i]) + nz, alpha, post_gain, clampv);
-                        if (out_mode <= 1) {
-                            const __half h = __float2half_rn(x);
-                            reinterpret_cast<__half*>(a.y)[off + i] = h;
-                            if (out_mode == 1) reinterpret_cast<__half*>(a.y_lo)[off + i] = __float2half_rn(x - __half2float(h));
-                        } else {
-                            float* yf = reinterpret_cast<float*>(a.y) + off + i;
-                            *yf = (out_mode == 3 ? *yf : 0.f) + x;
-                        }
-                    }
-                }
-            }
+            conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, off, nz, vec_ok);
         }
     }
     tc::tc_fence_before();
@@ -271,6 +280,156 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, a.tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for launches with many tiles: one CTA per SM walks a static tile schedule. A tile is 256 pixels
+// (two stacked 128-row sub-tiles that share every B stage) x BN channels, so a k-step moves 32 KB + BN*128 B for twice the
+// FLOPs of the kernel above (the mainloop is bound by the per-SM L2 -> shared-memory ingest rate, ~50 B/clk). The four
+// 128-column accumulators are double-buffered in TMEM (2 tiles x 2 sub-tiles = 512 columns), so the epilogue of tile i
+// (warps 2-9, one warp per sub-tile and lane quarter) runs under the MMAs of tile i+1.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPStages = 4;
+
+template <int kAct, bool kClamp>
+__global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                    const ConvKernelArgs a, int n_tiles, int tiles_n) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t a_bytes = 2u * kBM * 128, b_bytes = (uint32_t)a.BN * 128;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPStages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kPStages;
+    uint64_t* tmem_full_bar = empty_bar + kPStages;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_const = reinterpret_cast<float*>(smem + kPStages * stage_bytes + 128);     // [2 parities][scale 128 | bias 128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_k = a.n_groups * a.kc_steps;
+    const int tiles_m = a.tiles_x * a.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kPStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 8); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr_smem, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
+                const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+                const int n0 = tn * a.BN;
+                int g = 0, kc = 0;
+                for (int k = 0; k < total_k; ++k) {
+                    const int x0 = tx * a.BW + a.dx[g], y0 = ty * 2 * a.BH + a.dy[g];
+                    const int kb = a.tap[g] * a.Cin;
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    tc::mbar_expect_tx(&full_bar[stage], stage_bytes);
+                    tc::tma_load_5d(sa, &tmA, &full_bar[stage], kc * kBK, x0, y0, b, a.a_plane[g]);
+                    tc::tma_load_4d(sa + a_bytes, &tmB, &full_bar[stage], kb + kc * kBK, n0, a.w_per_sample ? b : 0, a.b_plane[g]);
+                    if (++stage == kPStages) { stage = 0; phase ^= 1; }
+                    if (++kc == a.kc_steps) { kc = 0; ++g; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                tc::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);        // the epilogue drained this accumulator pair
+                tc::tc_fence_after();
+                const uint32_t acc0 = tmem_base + (uint32_t)(as * 256);
+                for (int k = 0; k < total_k; ++k) {
+                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
+                    const uint64_t da = tc::umma_desc_k128(sa), db = tc::umma_desc_k128(sa + a_bytes);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const uint64_t dam = da + (uint64_t)(mt * (kBM * 128 >> 4));
+#pragma unroll
+                        for (int j = 0; j < kBK / 16; ++j)
+                            tc::umma_f16(acc0 + (uint32_t)(mt * 128), dam + (uint64_t)(j * 2), db + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
+                    }
+                    tc::umma_commit(&empty_bar[stage]);
+                    if (k == total_k - 1) tc::umma_commit(&tmem_full_bar[as]);
+                    if (++stage == kPStages) { stage = 0; phase ^= 1; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..9; sub-tile = (warp - 2) / 4, TMEM lane quarter = warp % 4 =====
+        const int e = warp - 2, mt = e >> 2, q = warp & 3;
+        const int m = q * 32 + lane;                    // row inside the 128-row sub-tile = TMEM lane
+        const int et = threadIdx.x - 64;                // 0..255 among the epilogue threads
+        int as = 0; uint32_t aphase = 0;
+        int parity = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
+            const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+            const int n0 = tn * a.BN;
+            float* s_scale = s_const + parity * 256;
+            float* s_bias = s_scale + 128;
+            if (et < a.BN) {
+                const int ch = n0 + et;
+                float sc = 0.f, bi = 0.f;
+                if (ch < a.Cout) {
+                    sc = a.acc_scale * a.pre_gain;
+                    if (a.dscale) sc *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
+                    if (a.bias) bi = __ldg(a.bias + ch) * a.pre_gain;
+                }
+                s_scale[et] = sc;
+                s_bias[et] = bi;
+            }
+            tc::named_bar_sync(1, 256);                 // constants of this tile visible to all epilogue warps
+            const int gy = (ty * 2 + mt) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
+            const bool pix_ok = (gy < a.gH) && (gx < a.gW);
+            const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
+            const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
+            const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+            const bool vec_ok = a.base_aligned && ((n0 + a.BN) <= a.Cout) && (a.BN % 32 == 0) &&
+                                (a.out_mode <= 1 ? ((a.y_cstride % 16) == 0 && ((a.y_coff + n0) % 16) == 0)
+                                                 : ((a.y_cstride % 8) == 0 && ((a.y_coff + n0) % 8) == 0));
+            tc::mbar_wait(&tmem_full_bar[as], aphase);
+            tc::tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + mt * 128);
+            for (int c0 = 0; c0 < a.BN; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(acc + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+                const int ch0 = n0 + c0;
+                if (!pix_ok || ch0 >= a.Cout) continue;
+                conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok);
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[as]);      // 8 warps -> accumulator pair free for the MMA warp
+            if (++as == 2) { as = 0; aphase ^= 1; }
+            parity ^= 1;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -343,18 +502,32 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     if (p->Cout_padded % 16 != 0 || p->Cout_padded < p->Cout) return P3D_BAD_ARG;
     if (p->gH <= 0 || p->gW <= 0 || p->B <= 0) return P3D_BAD_ARG;
 
-    // spatial tile BW x BH = 128 pixels: the power-of-two split with the least padded area (ties -> wider rows)
-    int BW = 1;
-    {
+    const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
+    // spatial tile BW x BH = 128 pixels: the power-of-two split with the least padded area (ties -> wider rows);
+    // `rows` = sub-tiles stacked in y per CTA tile (2 for the persistent kernel)
+    auto pick_bw = [&](int rows, long* area_out) {
+        int bw_best = 1;
         long best = -1;
         for (int bw = 1; bw <= 64; bw *= 2) {
-            int bh = kBM / bw;
+            int bh = kBM / bw * rows;
             long area = (long)ceil_div(p->gW, bw) * bw * ceil_div(p->gH, bh) * bh;
-            if (best < 0 || area <= best) { best = area; BW = bw; }
+            if (best < 0 || area <= best) { best = area; bw_best = bw; }
         }
+        if (area_out) *area_out = best;
+        return bw_best;
+    };
+    // persistent 256-pixel tiles when there is at least one tile per SM (P3D_CONV_PERSIST=0 disables, for A/B runs)
+    bool persist = false;
+    int BW = pick_bw(1, nullptr);
+    {
+        static int env = -1;
+        if (env < 0) { const char* e = getenv("P3D_CONV_PERSIST"); env = (e && e[0] == '0') ? 0 : 1; }
+        long area2 = 0;
+        const int bw2 = pick_bw(2, &area2);
+        const long tiles2 = area2 / 256 * ceil_div(p->Cout_padded, BN) * p->B;
+        if (env && tiles2 >= sm_count() && BN >= 32) { persist = true; BW = bw2; }
     }
     const int BH = kBM / BW;
-    const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
     const int K = p->n_kblocks * p->C;
     if (p->n_kblocks < 1) return P3D_BAD_ARG;
 
@@ -363,7 +536,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)p->x_planes};
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
-        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)BH, 1, 1};
+        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)(persist ? 2 * BH : BH), 1, 1};
         int rc = make_tmap_f16_sw128(&tmA, p->x, 5, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
@@ -390,7 +563,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.kc_steps = p->C / kBK;
     a.Cin = p->C;
     a.BW = BW; a.BH = BH;
-    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, BH);
+    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, persist ? 2 * BH : BH);
     a.BN = BN; a.w_per_sample = p->Bw > 1 ? 1 : 0;
     a.idesc = tc::umma_idesc_f16(kBM, BN, 0);
     a.tmem_cols = BN <= 32 ? 32u : BN <= 64 ? 64u : 128u;
@@ -415,6 +588,25 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
     const int total_k = a.n_groups * a.kc_steps;
     const long base_ctas = (long)grid.x * grid.y * grid.z;
+    if (persist) {
+        a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
+        const int tiles_n = (int)grid.y, n_tiles = (int)base_ctas;
+        const size_t stage_bytes_p = 2 * (size_t)kBM * 128 + (size_t)BN * 128;
+        const size_t smem_p = kPStages * stage_bytes_p + 128 + 2 * 256 * sizeof(float) + 1024;
+        const int ctas = n_tiles < sm_count() ? n_tiles : sm_count();
+#define P3D_LAUNCH_PERSIST(ACT, CL)                                                                                           \
+    do {                                                                                                                      \
+        P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_persist_kernel<ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                          (int)smem_p));                                                                      \
+        conv_gemm_persist_kernel<ACT, CL><<<ctas, 320, smem_p, (cudaStream_t)stream>>>(tmA, tmB, a, n_tiles, tiles_n);        \
+    } while (0)
+        if (act == 0) { if (clamp) P3D_LAUNCH_PERSIST(0, true); else P3D_LAUNCH_PERSIST(0, false); }
+        else if (act == 1) { if (clamp) P3D_LAUNCH_PERSIST(1, true); else P3D_LAUNCH_PERSIST(1, false); }
+        else { if (clamp) P3D_LAUNCH_PERSIST(2, true); else P3D_LAUNCH_PERSIST(2, false); }
+#undef P3D_LAUNCH_PERSIST
+        P3D_LAUNCH_CHECK();
+        return P3D_OK;
+    }
     // split-K for grids far smaller than the machine (4^2..16^2 layers: 16-32 CTAs each streaming 100-200 k-steps at
     // the per-SM L2 ingest rate): every k-range becomes its own CTA writing raw fp32 partials into the caller's scratch
     // buffer; conv_splitk_finish_kernel adds them in a fixed order and applies the epilogue.

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from conftest import load_golden, rel_err
-from make_golden import SYNTH_CASES, build_generator, state_digest
+from make_golden import SEMGEN_CASES, SYNTH_CASES, build_generator, state_digest
 
 pytestmark = pytest.mark.gpu
 
@@ -14,12 +14,12 @@ def _replay(g, dev):
     return (lambda x, *a, **k: next(it)), (lambda *a, **k: next(it))
 
 
-@pytest.mark.parametrize('name', list(SYNTH_CASES))
+@pytest.mark.parametrize('name', list(SYNTH_CASES) + list(SEMGEN_CASES))
 @pytest.mark.parametrize('force_fp32', [True, False])
 def test_synthesis_cuda_matches_reference(name, force_fp32):
     import pix2pix3d_b200.training.triplane_cond as tc
     from pix2pix3d_b200 import _lib
-    case = SYNTH_CASES[name]
+    case = SYNTH_CASES.get(name) or SEMGEN_CASES[name]
     g = load_golden('synthesis_' + name)
     dev = torch.device('cuda')
     torch.backends.cudnn.allow_tf32 = False        # any ATen convolution left on the path must be true fp32
@@ -53,6 +53,8 @@ def test_synthesis_cuda_matches_reference(name, force_fp32):
         smp = G.sample_mixed(torch.from_numpy(g['pts']).to(dev), None, ws, noise_mode='const')
     assert rel_err(smp['rgb'].cpu().numpy(), g['sample_rgb']) < 1e-3
     assert rel_err(smp['sigma'].cpu().numpy(), g['sample_sigma']) < 1e-3
+    if 'semantic' in smp:
+        assert rel_err(smp['semantic'].cpu().numpy(), g['sample_semantic']) < 1e-3
 
 
 def test_mapping_cuda_matches_reference():

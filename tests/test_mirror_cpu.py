@@ -5,13 +5,13 @@ import pytest
 import torch
 
 from conftest import load_golden, rel_err
-from make_golden import SYNTH_CASES, build_generator, capture_rand, state_digest
+from make_golden import SEMGEN_CASES, SYNTH_CASES, build_generator, capture_rand, state_digest
 
 
-@pytest.mark.parametrize('name', list(SYNTH_CASES))
+@pytest.mark.parametrize('name', list(SYNTH_CASES) + list(SEMGEN_CASES))
 def test_synthesis_cpu_matches_reference(name):
     import pix2pix3d_b200.training.triplane_cond as tc
-    case = SYNTH_CASES[name]
+    case = SYNTH_CASES.get(name) or SEMGEN_CASES[name]
     g = load_golden('synthesis_' + name)
     G = build_generator(tc, case)
     assert state_digest(G) == bytes(g['state_digest']).decode()
@@ -40,6 +40,8 @@ def test_synthesis_cpu_matches_reference(name):
         assert rel_err(v.numpy(), g['out_' + k]) < 1e-4, k
     assert rel_err(smp['rgb'].numpy(), g['sample_rgb']) < 1e-5
     assert rel_err(smp['sigma'].numpy(), g['sample_sigma']) < 1e-5
+    if 'semantic' in smp:
+        assert rel_err(smp['semantic'].numpy(), g['sample_semantic']) < 1e-5
 
 
 def test_ops_ref_paths_match_reference():

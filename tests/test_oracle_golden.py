@@ -6,7 +6,7 @@ import torch
 
 import p3d_oracle as O
 from conftest import load_golden, rel_err
-from make_golden import SYNTH_CASES
+from make_golden import SEMGEN_CASES, SYNTH_CASES
 
 RENDER_CASES = ['seg', 'seg48', 'car', 'rgb_only', 'coarse_only', 'far_outside', 'seg16', 'rgb24', 'coarse8', 'car64']
 TC_RENDER_CASES = ['seg48', 'car', 'seg16', 'rgb24', 'coarse8', 'car64']     # Sc and Sf multiples of 8
@@ -152,6 +152,34 @@ def test_generator_synthesis_matches_reference(name):
     for k in ('image_raw', 'image_depth', 'image', 'semantic_raw', 'semantic'):
         if 'out_' + k in g:
             assert rel_err(out[k], g['out_' + k]) < 1e-3, k
+
+
+@pytest.mark.parametrize('name', list(SEMGEN_CASES))
+def test_semantic_generator_synthesis_matches_reference(name):
+    """TriPlaneSemanticGenerator.synthesis (two backbones + ImportanceSemanticRenderer) in the oracle."""
+    import pix2pix3d_b200.training.triplane_cond as tc
+    from make_golden import build_generator, state_digest
+    case = SEMGEN_CASES[name]
+    g = load_golden('synthesis_' + name)
+    G = build_generator(tc, case)
+    assert state_digest(G) == bytes(g['state_digest']).decode(), 'mirror and reference initialise differently'
+    sd = {k: v.numpy() for k, v in G.state_dict().items()}
+    cfg = dict(nrr=case['nrr'], rendering_kwargs=dict(G.rendering_kwargs), semantic_channels=case['semantic_channels'],
+               w_dim=case['w_dim'], sr_kind='SuperresolutionHybrid2X', sr_kind_semantic='SuperresolutionHybrid2X_semantic', sr_fp16=True)
+    out = O.networks.generator_synthesis_semantic(g['ws'], g['c'], sd, cfg, g['jitter'], g['u'])
+    n = g['ws'].shape[0]
+    assert rel_err(out['planes_texture'].reshape(n, 96, 256, 256)[:, :, 3::16, 5::16], g['planes_texture_sub']) < 1e-4
+    assert rel_err(out['planes_semantic'].reshape(n, 96, 256, 256)[:, :, 3::16, 5::16], g['planes_semantic_sub']) < 1e-4
+    for k in ('image_raw', 'image_depth', 'image', 'semantic_raw', 'semantic'):
+        assert rel_err(out[k], g['out_' + k]) < 1e-3, k
+    # run_model at free points (G.sample_mixed)
+    rk = G.rendering_kwargs
+    dec_t = O.networks.decoder_from_state_dict(sd, 'decoder', 'OSGDecoder')
+    dec_s = O.networks.decoder_from_state_dict(sd, 'decoder_semantic', 'OSGDecoder_semantic',
+                                               semantic_sigmoid=case['semantic_channels'] == 1)
+    rgb, sigma, sem = O.renderer.run_model_semantic(out['planes_texture'], out['planes_semantic'], dec_t, dec_s, g['pts'], rk['box_warp'])
+    assert rel_err(rgb, g['sample_rgb']) < 1e-4 and rel_err(sigma, g['sample_sigma']) < 1e-4
+    assert rel_err(sem, g['sample_semantic']) < 1e-4
 
 
 def test_filtered_lrelu_composition():
