@@ -127,6 +127,16 @@ __device__ __forceinline__ float ldg_f32_off(const float* base, uint32_t elem_of
     asm("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(addr));
     return v;
 }
+__device__ __forceinline__ float4 ldg_f32x4_off(const float* base, uint32_t elem_off) {
+    uint64_t addr;
+    float4 v;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(addr) : "r"(elem_off), "l"(base));
+    asm("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32x2(uint32_t addr, uint32_t v0, uint32_t v1) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v0), "r"(v1) : "memory");
+}
 __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -232,40 +242,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             *reinterpret_cast<float4*>(r + ((5 ^ sw) << 4)) = make_float4(t2.w00, t2.w01, t2.w10, t2.w11);
         }
         __syncwarp();
-        unsigned active = __ballot_sync(0xffffffffu, valid);
-        const float* pl = a.planes_nhwc + lane;
-        auto fetch = [&](int row, float& f) {
+        const unsigned active = __ballot_sync(0xffffffffu, valid);
+        // Step 2: a quarter-warp per row, lane = 4 consecutive channels: one LDG.128 per tap serves 4 rows at once, so the
+        // address arithmetic, the broadcast of the parked taps and the loop overhead are paid once per 4 samples.
+        const int sub = lane >> 3, cq = lane & 7;
+        const float* pl4 = a.planes_nhwc + cq * 4;
+        auto fetch4 = [&](int row, float (&f)[4]) {
             // the row base is 128-byte aligned, so base | ((chunk << 4) ^ (swizzle << 4)) is one LOP3 per 16-byte chunk
             const uint32_t rb = tb32 + row * 128, swx = (uint32_t)(row & 7) << 4;
             const uint4 o0 = lds_u4(rb | (0x00u ^ swx)), o1 = lds_u4(rb | (0x10u ^ swx)), o2 = lds_u4(rb | (0x20u ^ swx));
             const uint4 x0 = lds_u4(rb | (0x30u ^ swx)), x1 = lds_u4(rb | (0x40u ^ swx)), x2 = lds_u4(rb | (0x50u ^ swx));
-            const float v00 = ldg_f32_off(pl, o0.x), v01 = ldg_f32_off(pl, o0.y), v02 = ldg_f32_off(pl, o0.z), v03 = ldg_f32_off(pl, o0.w);
-            const float v10 = ldg_f32_off(pl, o1.x), v11 = ldg_f32_off(pl, o1.y), v12 = ldg_f32_off(pl, o1.z), v13 = ldg_f32_off(pl, o1.w);
-            const float v20 = ldg_f32_off(pl, o2.x), v21 = ldg_f32_off(pl, o2.y), v22 = ldg_f32_off(pl, o2.z), v23 = ldg_f32_off(pl, o2.w);
-            const float f0 = fmaf(v03, __uint_as_float(x0.w), fmaf(v02, __uint_as_float(x0.z), fmaf(v01, __uint_as_float(x0.y), __fmul_rn(v00, __uint_as_float(x0.x)))));
-            const float f1 = fmaf(v13, __uint_as_float(x1.w), fmaf(v12, __uint_as_float(x1.z), fmaf(v11, __uint_as_float(x1.y), __fmul_rn(v10, __uint_as_float(x1.x)))));
-            const float f2 = fmaf(v23, __uint_as_float(x2.w), fmaf(v22, __uint_as_float(x2.z), fmaf(v21, __uint_as_float(x2.y), __fmul_rn(v20, __uint_as_float(x2.x)))));
-            f = __fadd_rn(__fadd_rn(f0, f1), f2);      // the mean's 1/3 lives in the packed layer-1 weights
+            const float4 v00 = ldg_f32x4_off(pl4, o0.x), v01 = ldg_f32x4_off(pl4, o0.y), v02 = ldg_f32x4_off(pl4, o0.z), v03 = ldg_f32x4_off(pl4, o0.w);
+            const float4 v10 = ldg_f32x4_off(pl4, o1.x), v11 = ldg_f32x4_off(pl4, o1.y), v12 = ldg_f32x4_off(pl4, o1.z), v13 = ldg_f32x4_off(pl4, o1.w);
+            const float4 v20 = ldg_f32x4_off(pl4, o2.x), v21 = ldg_f32x4_off(pl4, o2.y), v22 = ldg_f32x4_off(pl4, o2.z), v23 = ldg_f32x4_off(pl4, o2.w);
+#define P3D_BILERP(c, va, vb, vc, vd, WT) \
+    fmaf(vd.c, __uint_as_float(WT.w), fmaf(vc.c, __uint_as_float(WT.z), fmaf(vb.c, __uint_as_float(WT.y), __fmul_rn(va.c, __uint_as_float(WT.x)))))
+            // the mean's 1/3 lives in the packed layer-1 weights
+            f[0] = __fadd_rn(__fadd_rn(P3D_BILERP(x, v00, v01, v02, v03, x0), P3D_BILERP(x, v10, v11, v12, v13, x1)), P3D_BILERP(x, v20, v21, v22, v23, x2));
+            f[1] = __fadd_rn(__fadd_rn(P3D_BILERP(y, v00, v01, v02, v03, x0), P3D_BILERP(y, v10, v11, v12, v13, x1)), P3D_BILERP(y, v20, v21, v22, v23, x2));
+            f[2] = __fadd_rn(__fadd_rn(P3D_BILERP(z, v00, v01, v02, v03, x0), P3D_BILERP(z, v10, v11, v12, v13, x1)), P3D_BILERP(z, v20, v21, v22, v23, x2));
+            f[3] = __fadd_rn(__fadd_rn(P3D_BILERP(w, v00, v01, v02, v03, x0), P3D_BILERP(w, v10, v11, v12, v13, x1)), P3D_BILERP(w, v20, v21, v22, v23, x2));
+#undef P3D_BILERP
         };
-        auto store = [&](int row, float f) {
-            const __half hi = __float2half_rn(f), lo = __float2half_rn(f - __half2float(hi));
+        auto store4 = [&](int row, const float (&f)[4]) {
+            const __half2 h01 = __floats2half2_rn(f[0], f[1]), h23 = __floats2half2_rn(f[2], f[3]);
+            const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(f[0] - b01.x, f[1] - b01.y), l23 = __floats2half2_rn(f[2] - b23.x, f[3] - b23.y);
             const uint32_t rb = tb32 + row * 128, swx = (uint32_t)(row & 7) << 4;
-            // lane's hi at k-byte 2*lane, lo at 64 + 2*lane: chunks (lane >> 3) and 4 + (lane >> 3), byte (lane & 7) * 2
-            const uint32_t c = ((uint32_t)(lane >> 3) << 4), inb = (uint32_t)(lane & 7) * 2;
-            sts_u16((rb | (c ^ swx)) + inb, __half_as_ushort(hi));
-            sts_u16((rb | ((c + 0x40u) ^ swx)) + inb, __half_as_ushort(lo));
+            // channels 4cq..4cq+3: hi at k-bytes [8cq, 8cq+8), lo at 64 + the same: chunks (cq >> 1) and 4 + (cq >> 1)
+            const uint32_t c = ((uint32_t)(cq >> 1) << 4), inb = (uint32_t)(cq & 1) * 8;
+            sts_u32x2((rb | (c ^ swx)) + inb, *reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            sts_u32x2((rb | ((c + 0x40u) ^ swx)) + inb, *reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
         };
-        while (active) {
-            const int s0 = __ffs(active) - 1;
-            active &= active - 1;
-            int s1 = -1;
-            if (active) { s1 = __ffs(active) - 1; active &= active - 1; }
-            float fa = 0.f, fb = 0.f;
-            fetch(q * 32 + s0, fa);
-            if (s1 >= 0) fetch(q * 32 + s1, fb);
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            if ((active >> (it * 4) & 0xfu) == 0) continue;           // warp-uniform: nothing valid in these 4 rows
+            const int r = it * 4 + sub;
+            const bool ok = (active >> r) & 1u;
+            float f[4];
+            if (ok) fetch4(q * 32 + r, f);                           // 12 x 16 B per lane in flight
             __syncwarp();            // every lane has read the parked taps before the rows are overwritten
-            store(q * 32 + s0, fa);
-            if (s1 >= 0) store(q * 32 + s1, fb);
+            if (ok) store4(q * 32 + r, f);
         }
     };
     // sigma of this thread's row after layer 1 of the sigma net landed in D1[:, 0:64)
@@ -588,6 +605,8 @@ extern "C" int p3d_render_fwd_tc(const p3d_render_args_t* args, p3d_stream_t str
         const bool dense = !(a.plane_strides[0] || a.plane_strides[1] || a.plane_strides[2]);
         const int64_t is = dense ? 3 * psz : a.plane_strides[0], pls = dense ? psz : a.plane_strides[1], pxs = dense ? kC : a.plane_strides[2];
         if (is <= 0 || pls <= 0 || pxs < kC) return P3D_BAD_ARG;
+        // 16-byte texel vectors: base and strides must keep every 4-channel group aligned
+        if ((((uintptr_t)a.planes_nhwc) & 15) != 0 || (is & 3) || (pls & 3) || (pxs & 3)) return P3D_UNSUPPORTED;
         // largest element offset the kernel forms must fit 32 bits
         const int64_t max_off = (int64_t)(a.B - 1) * is + 2 * pls + ((int64_t)a.H * a.W - 1) * pxs + kC;
         if (max_off >= ((int64_t)1 << 32)) return P3D_UNSUPPORTED;
