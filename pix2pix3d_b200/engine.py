@@ -22,8 +22,6 @@ _SQRT2 = float(np.sqrt(2))
 
 # set False to force the generic op-by-op formulation (A/B checks in tests)
 enabled = True
-# weight modulation of all layers ahead of time on a side stream (False: inline, layer by layer)
-premodulate_enabled = True
 
 
 def block_supported(block, ws, noise_mode, need_grad):
@@ -156,79 +154,15 @@ def _alloc(planes, b, h, w, c, cp, device):
     return torch.zeros(shape, device=device, dtype=torch.float16) if cp != c else torch.empty(shape, device=device, dtype=torch.float16)
 
 
-class ReadyWeights:
-    """Modulated weights of one layer produced ahead of time on the side stream (see `premodulate`)."""
-    __slots__ = ('wk', 'event', 'batch')
-
-    def __init__(self, wk, event, batch):
-        self.wk, self.event, self.batch = wk, event, batch
-
-
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    s = _SIDE_STREAMS.get(device)
-    if s is None:
-        s = torch.cuda.Stream(device=device)
-        _SIDE_STREAMS[device] = s
-    return s
-
-
-def _block_specs(block, force_fp32, first_cin_p=None, first_cin_off=0):
-    """Per layer of `_block_layers(block)`: the arguments of its weight modulation (they depend on the module only)."""
-    split = not (block.use_fp16 and not force_fp32)
-    planes = 2 if split else 1
-    specs = []
-    for k, layer in enumerate(_block_layers(block)):
-        torgb = layer is block.torgb
-        cin_p = tcconv.pad_to(layer.in_channels, 64)
-        cin_off = 0
-        if k == 0 and first_cin_p is not None and not torgb:
-            cin_p, cin_off = first_cin_p, first_cin_off
-        specs.append(dict(layer=layer, demodulate=not torgb, pre_scale=float(layer.weight_gain) if torgb else 1.0, planes=planes,
-                          cin_padded=cin_p, cin_offset=cin_off))
-    return specs
-
-
-def premodulate(specs, styles):
-    """Runs every `p3d_modulate_weights_t` of a step on a side stream, in execution order, while the main stream starts on
-    the first convolutions: the modulation kernels are HBM streams that fit next to the persistent tensor-core CTAs
-    (32 KB of shared memory and half the register file stay free), so they disappear from the critical path. Each
-    layer waits on its own event. Returns the list that replaces `styles` for `synthesis_block`."""
-    dev = styles[0].device
-    cur = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
-    side.wait_stream(cur)
-    out = []
-    with torch.cuda.stream(side):
-        for spec, st in zip(specs, styles):
-            layer = spec['layer']
-            wk = tcconv.modulate_weights(layer.weight, st, demodulate=spec['demodulate'], pre_scale=spec['pre_scale'],
-                                         planes=spec['planes'], cin_padded=spec['cin_padded'], cin_offset=spec['cin_offset'],
-                                         prepared=_prepared(layer))
-            wk.record_stream(cur)
-            ev = torch.cuda.Event()
-            ev.record(side)
-            out.append(ReadyWeights(wk, ev, st.shape[0]))
-    return out
-
-
-def _weights_for(layer, styles, **mod_kwargs):
-    if isinstance(styles, ReadyWeights):
-        torch.cuda.current_stream(styles.wk.device).wait_event(styles.event)
-        return styles.wk, styles.batch
-    return tcconv.modulate_weights(layer.weight, styles, prepared=_prepared(layer), **mod_kwargs), styles.shape[0]
-
-
 def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0):
     """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]; styles = layer.affine(w)."""
     planes = 2 if split else 1
+    b = styles.shape[0]
     cin_p = x.shape[-1]
     cout = layer.out_channels
     cout_p = tcconv.pad_to(cout, 64)
-    wk, b = _weights_for(layer, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset)
-    assert wk.shape[0] == planes and wk.shape[-1] == layer.weight.shape[2] * layer.weight.shape[3] * cin_p
+    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset,
+                                 prepared=_prepared(layer))
     noise = _noise(layer, noise_mode)
     bias = _bias(layer, cout_p)
     act_gain = layer.act_gain * gain
@@ -255,9 +189,10 @@ def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0)
 def torgb_layer(layer, x, styles, img, split):
     """ToRGBLayer.forward (:354-359) accumulated into the fp32 NHWC skip image (or creating it)."""
     planes = 2 if split else 1
+    b = styles.shape[0]
     cout = layer.out_channels
-    wk, b = _weights_for(layer, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes, cin_padded=x.shape[-1])
-    assert wk.shape[0] == planes and wk.shape[-1] == x.shape[-1]
+    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes,
+                                 cin_padded=x.shape[-1], prepared=_prepared(layer))
     h, w = x.shape[2], x.shape[3]
     bias = _bias(layer, cout)
     clamp = float(layer.conv_clamp) if layer.conv_clamp is not None else -1.0
@@ -296,7 +231,7 @@ def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False,
     planes = 2 if split else 1
     s_iter = iter(styles)
     if block.in_channels == 0:
-        x = _const_input(block, styles[0].batch if isinstance(styles[0], ReadyWeights) else styles[0].shape[0], planes)
+        x = _const_input(block, styles[0].shape[0], planes)
         x = synthesis_layer(block.conv1, x, next(s_iter), noise_mode, split)
     else:
         if x.shape[0] != planes:   # precision change between blocks
@@ -405,25 +340,6 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
     n_net = len(net_layers)
     all_layers = net_layers + [lw for sr in srs for lw in _sr_layers(sr, ws.shape[1] - 1)]
     styles = style_plan(gen, 'gen', all_layers).run(ws.to(torch.float32))
-    if premodulate_enabled:
-        nch_feat = 64 if semantic else 32                  # feature channels the renderer returns (two decoder nets / one)
-        specs = []
-        if not (use_cached_backbone and gen._last_planes is not None):
-            for res in net.block_resolutions:
-                specs += _block_specs(getattr(net, f'b{res}'), force_fp32)
-            sel = styles[:n_net]
-        else:
-            sel = []
-        for k, sr in enumerate(srs):
-            first_p = tcconv.pad_to(nch_feat, 64)
-            first_off = (nch_feat // 2 if semantic else 0) if k == 1 else 0
-            specs += _block_specs(sr.block0, force_fp32, first_p, first_off) + _block_specs(sr.block1, force_fp32)
-        sel = list(sel) + list(styles[n_net:])
-        ready = premodulate(specs, sel)
-        if len(sel) == len(styles):
-            styles = ready
-        else:
-            styles = list(styles[:n_net]) + ready
     if use_cached_backbone and gen._last_planes is not None:
         planes_nchw = gen._last_planes
         planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
@@ -470,6 +386,4 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
     if semantic:
         cs = gen.semantic_channels
         out['semantic'], out['semantic_raw'] = run_sr(gen.superresolution_semantic, half, cs, styles[n_net + n_sr:])
-    if premodulate_enabled:
-        torch.cuda.current_stream(ws.device).wait_stream(_side_stream(ws.device))     # join (required inside graph capture)
     return out
