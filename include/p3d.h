@@ -226,6 +226,21 @@ int p3d_modulate_weights_t(const float* weight_t, const float* wsq, const float*
                            int Cout_padded, int Cin_padded, int cin_offset, int demodulate, float pre_scale,
                            float out_scale, int planes, void* out, p3d_stream_t stream);
 
+/* p3d_modulate_weights_t for every layer of a synthesis stack in one launch. descs_dev: device array, one entry per
+ * layer (same meaning as the arguments of p3d_modulate_weights_t; styles_off / out_off are element offsets into
+ * styles_base (fp32) / out_base (fp16)); block_layer_dev: int32 [n_blocks], the layer each CTA belongs to, CTAs of a layer
+ * being consecutive and starting at first_block (n_blocks = sum of Cout_padded). Constraints on Cin_padded as above. */
+typedef struct {
+    const float* weight_t;
+    const float* wsq;
+    int64_t styles_off, out_off;
+    int32_t Cout, Cin, ktaps, Cout_padded, Cin_padded, cin_offset, demodulate, planes;
+    float pre_scale, out_scale;
+    int32_t first_block, reserved;
+} p3d_modw_desc_t;
+int p3d_modulate_weights_batch(const p3d_modw_desc_t* descs_dev, const int32_t* block_layer_dev, int n_blocks,
+                               const float* styles_base, void* out_base, int B, p3d_stream_t stream);
+
 /* Every style affine of a synthesis stack in one launch (layer.affine(w) of SynthesisLayer.forward / ToRGBLayer.forward,
  * networks_stylegan2.py:313-315, 354-355; FullyConnectedLayer.forward :111-123 with the weight and bias gains already
  * applied by the caller): for each row r of weight [rows, w_dim],

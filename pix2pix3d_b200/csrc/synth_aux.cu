@@ -116,12 +116,10 @@ __global__ void __launch_bounds__(256) prepare_weights_kernel(const float* __res
 }
 
 // One CTA per output channel, all samples. Thread = (8-channel chunk, tap row); no integer division in the loops.
-__global__ void __launch_bounds__(256) modulate_weights_t_kernel(const float* __restrict__ wt, const float* __restrict__ wsq,
-                                                                 const float* __restrict__ styles, int Cout, int Cin, int ktaps,
-                                                                 int Cout_p, int Cin_p, int cin_off, int demod, float pre_scale,
-                                                                 float out_scale, int planes, int B, __half* __restrict__ out) {
-    __shared__ float dsm[64];
-    const int o = blockIdx.x;
+__device__ __forceinline__ void modulate_row(const float* __restrict__ wt, const float* __restrict__ wsq,
+                                             const float* __restrict__ styles, int o, int Cout, int Cin, int ktaps, int Cout_p,
+                                             int Cin_p, int cin_off, int demod, float pre_scale, float out_scale, int planes,
+                                             int B, __half* __restrict__ out, float* dsm) {
     const size_t row_elems = (size_t)ktaps * Cin_p;
     const size_t plane_stride = (size_t)B * Cout_p * row_elems;
     const int nchunk = Cin_p >> 3;                 // host guarantees Cin_p % 8 == 0 and 256 % nchunk == 0
@@ -176,6 +174,27 @@ __global__ void __launch_bounds__(256) modulate_weights_t_kernel(const float* __
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) modulate_weights_t_kernel(const float* __restrict__ wt, const float* __restrict__ wsq,
+                                                                 const float* __restrict__ styles, int Cout, int Cin, int ktaps,
+                                                                 int Cout_p, int Cin_p, int cin_off, int demod, float pre_scale,
+                                                                 float out_scale, int planes, int B, __half* __restrict__ out) {
+    __shared__ float dsm[64];
+    modulate_row(wt, wsq, styles, blockIdx.x, Cout, Cin, ktaps, Cout_p, Cin_p, cin_off, demod, pre_scale, out_scale, planes, B, out,
+                 dsm);
+}
+
+// every layer of a synthesis stack in ONE launch: block -> (layer, output channel) through a lookup table
+__global__ void __launch_bounds__(256) modulate_weights_batch_kernel(const p3d_modw_desc_t* __restrict__ descs,
+                                                                     const int32_t* __restrict__ block_layer,
+                                                                     const float* __restrict__ styles_base,
+                                                                     __half* __restrict__ out_base, int B) {
+    __shared__ float dsm[64];
+    const p3d_modw_desc_t d = descs[__ldg(block_layer + blockIdx.x)];
+    modulate_row(d.weight_t, d.wsq, styles_base + d.styles_off, (int)blockIdx.x - d.first_block, d.Cout, d.Cin, d.ktaps,
+                 d.Cout_padded, d.Cin_padded, d.cin_offset, d.demodulate, d.pre_scale, d.out_scale, d.planes, B,
+                 out_base + d.out_off, dsm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -491,6 +510,15 @@ extern "C" int p3d_modulate_weights_t(const float* weight_t, const float* wsq, c
     modulate_weights_t_kernel<<<Cout_padded, 256, 0, (cudaStream_t)stream>>>(weight_t, wsq, styles, Cout, Cin, ktaps, Cout_padded,
                                                                              Cin_padded, cin_offset, demodulate, pre_scale, out_scale,
                                                                              planes, B, (__half*)out);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+extern "C" int p3d_modulate_weights_batch(const p3d_modw_desc_t* descs_dev, const int32_t* block_layer_dev, int n_blocks,
+                                          const float* styles_base, void* out_base, int B, p3d_stream_t stream) {
+    if (!descs_dev || !block_layer_dev || !styles_base || !out_base || n_blocks <= 0 || B <= 0) return P3D_BAD_ARG;
+    modulate_weights_batch_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, block_layer_dev, styles_base,
+                                                                              (__half*)out_base, B);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

@@ -132,9 +132,101 @@ class StylePlan:
         return out
 
 
+class ReadyWeights:
+    """Modulated weights of one layer produced ahead of the layer loop (WeightPlan.run)."""
+    __slots__ = ('wk', 'batch')
+
+    def __init__(self, wk, batch):
+        self.wk, self.batch = wk, batch
+
+
 def _block_layers(block):
     names = (['conv1'] if block.in_channels == 0 else ['conv0', 'conv1']) + ['torgb']
     return [getattr(block, n) for n in names]
+
+
+def _block_specs(block, force_fp32, first_cin_p=None, first_cin_off=0):
+    """Per layer of `_block_layers(block)`: the arguments of its weight modulation (they depend on the modules only)."""
+    split = not (block.use_fp16 and not force_fp32)
+    planes = 2 if split else 1
+    specs = []
+    for k, layer in enumerate(_block_layers(block)):
+        torgb = layer is block.torgb
+        cin_p = tcconv.pad_to(layer.in_channels, 64)
+        cin_off = 0
+        if k == 0 and first_cin_p is not None and not torgb:
+            cin_p, cin_off = first_cin_p, first_cin_off
+        specs.append(dict(layer=layer, demodulate=not torgb, pre_scale=float(layer.weight_gain) if torgb else 1.0, planes=planes,
+                          cin_padded=cin_p, cin_offset=cin_off))
+    return specs
+
+
+class WeightPlan(StylePlan):
+    """StylePlan + every layer's weight modulation as one `p3d_modulate_weights_batch` launch: `run(ws)` returns the
+    ReadyWeights of all layers (views into one fp16 buffer), i.e. two launches replace 2 x n_layers."""
+
+    def __init__(self, layers, specs):
+        super().__init__(layers)
+        self.specs = specs
+        self.key = self.key + tuple((sp['layer'].weight.data_ptr(), sp['layer'].weight._version, sp['planes'], sp['cin_padded'],
+                                     sp['cin_offset']) for sp in specs)
+        self.prepared = [_prepared(sp['layer']) for sp in specs]
+        self._tables = {}
+
+    def tables(self, b):
+        t = self._tables.get(b)
+        if t is None:
+            descs = (tcconv.ModwDesc * len(self.specs))()
+            block_layer, out_off, styles_off, first = [], 0, 0, 0
+            shapes = []
+            for k, (sp, (wt, wsq), n_in) in enumerate(zip(self.specs, self.prepared, self.sizes)):
+                layer = sp['layer']
+                o, i, kh, kw = layer.weight.shape
+                assert i == n_in
+                op, ip = tcconv.pad_to(o, 16), sp['cin_padded']
+                nchunk = ip // 8
+                assert ip % 8 == 0 and nchunk <= 256 and 256 % nchunk == 0, 'unsupported channel padding for the batched kernel'
+                d = descs[k]
+                d.weight_t, d.wsq = wt.data_ptr(), wsq.data_ptr()
+                d.styles_off, d.out_off = styles_off, out_off
+                d.Cout, d.Cin, d.ktaps, d.Cout_padded, d.Cin_padded = o, i, kh * kw, op, ip
+                d.cin_offset, d.demodulate, d.planes = sp['cin_offset'], 1 if sp['demodulate'] else 0, sp['planes']
+                d.pre_scale, d.out_scale = sp['pre_scale'], tcconv.WEIGHT_SCALE
+                d.first_block = first
+                block_layer += [k] * op
+                n_out = sp['planes'] * b * op * kh * kw * ip
+                shapes.append((out_off, n_out, (sp['planes'], b, op, kh * kw * ip)))
+                out_off += (n_out + 63) // 64 * 64            # keep every layer 128-byte aligned
+                styles_off += b * i
+                first += op
+            raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(self.device)
+            bl = torch.tensor(block_layer, dtype=torch.int32, device=self.device)
+            t = (raw, bl, first, out_off, shapes)
+            self._tables[b] = t
+        return t
+
+    def run(self, ws):
+        b = ws.shape[0]
+        meta, total = self.meta(b)
+        flat = tcconv.affine_batch(ws, self.weight, self.bias, meta, total)
+        raw, bl, n_blocks, out_total, shapes = self.tables(b)
+        out = torch.empty(out_total, device=self.device, dtype=torch.float16)
+        tcconv.modulate_weights_batch(raw, bl, n_blocks, flat, out, b)
+        return [ReadyWeights(out[off:off + n].view(shape), b) for off, n, shape in shapes]
+
+
+def weight_plan(owner, tag, layers, specs):
+    """Cached WeightPlan, stored against `owner`; rebuilt when any parameter it derives from changes."""
+    slot = _derived.setdefault(owner, {})
+    key = tuple((l.affine.weight.data_ptr(), l.affine.weight._version, l.affine.bias.data_ptr(), l.affine.bias._version)
+                for l, _ in layers) + tuple(i for _, i in layers) + \
+        tuple((sp['layer'].weight.data_ptr(), sp['layer'].weight._version, sp['planes'], sp['cin_padded'], sp['cin_offset'])
+              for sp in specs)
+    plan = slot.get(('weights', tag))
+    if plan is None or plan.key != key:
+        plan = WeightPlan(layers, specs)
+        slot[('weights', tag)] = plan
+    return plan
 
 
 def style_plan(owner, tag, layers):
@@ -157,12 +249,16 @@ def _alloc(planes, b, h, w, c, cp, device):
 def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0):
     """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]; styles = layer.affine(w)."""
     planes = 2 if split else 1
-    b = styles.shape[0]
     cin_p = x.shape[-1]
     cout = layer.out_channels
     cout_p = tcconv.pad_to(cout, 64)
-    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset,
-                                 prepared=_prepared(layer))
+    if isinstance(styles, ReadyWeights):
+        wk, b = styles.wk, styles.batch
+        assert wk.shape[0] == planes and wk.shape[-1] == layer.weight.shape[2] * layer.weight.shape[3] * cin_p
+    else:
+        b = styles.shape[0]
+        wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset,
+                                     prepared=_prepared(layer))
     noise = _noise(layer, noise_mode)
     bias = _bias(layer, cout_p)
     act_gain = layer.act_gain * gain
@@ -189,10 +285,14 @@ def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0)
 def torgb_layer(layer, x, styles, img, split):
     """ToRGBLayer.forward (:354-359) accumulated into the fp32 NHWC skip image (or creating it)."""
     planes = 2 if split else 1
-    b = styles.shape[0]
     cout = layer.out_channels
-    wk = tcconv.modulate_weights(layer.weight, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes,
-                                 cin_padded=x.shape[-1], prepared=_prepared(layer))
+    if isinstance(styles, ReadyWeights):
+        wk, b = styles.wk, styles.batch
+        assert wk.shape[0] == planes and wk.shape[-1] == x.shape[-1]
+    else:
+        b = styles.shape[0]
+        wk = tcconv.modulate_weights(layer.weight, styles, demodulate=False, pre_scale=layer.weight_gain, planes=planes,
+                                     cin_padded=x.shape[-1], prepared=_prepared(layer))
     h, w = x.shape[2], x.shape[3]
     bias = _bias(layer, cout)
     clamp = float(layer.conv_clamp) if layer.conv_clamp is not None else -1.0
@@ -231,7 +331,7 @@ def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False,
     planes = 2 if split else 1
     s_iter = iter(styles)
     if block.in_channels == 0:
-        x = _const_input(block, styles[0].shape[0], planes)
+        x = _const_input(block, styles[0].batch if isinstance(styles[0], ReadyWeights) else styles[0].shape[0], planes)
         x = synthesis_layer(block.conv1, x, next(s_iter), noise_mode, split)
     else:
         if x.shape[0] != planes:   # precision change between blocks
@@ -268,7 +368,8 @@ def _run_network(net, styles, noise_mode, force_fp32):
 
 def synthesis_network(net, ws, noise_mode='const', force_fp32=False):
     """SynthesisNetwork.forward (:505-520) -> fp32 NHWC image [B,R,R,img_channels]."""
-    styles = style_plan(net, 'net', _network_layers(net)).run(ws.to(torch.float32))
+    specs = [sp for res in net.block_resolutions for sp in _block_specs(getattr(net, f'b{res}'), force_fp32)]
+    styles = weight_plan(net, ('net', bool(force_fp32)), _network_layers(net), specs).run(ws.to(torch.float32))
     return _run_network(net, styles, noise_mode, force_fp32)
 
 
@@ -281,7 +382,9 @@ def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=F
     """Superresolution*.forward (superresolution.py:48-57) with the feature image as NCHW fp32 and the low-res image as
     fp32 NHWC; returns the fp32 NHWC output image."""
     ws = ws.to(torch.float32)
-    styles = style_plan(sr, 'sr', _sr_layers(sr, ws.shape[1] - 1)).run(ws)
+    first_p = tcconv.pad_to(feat_nchw.shape[1], 64)
+    specs = _block_specs(sr.block0, force_fp32, first_p, 0) + _block_specs(sr.block1, force_fp32)
+    styles = weight_plan(sr, ('sr', bool(force_fp32), first_p), _sr_layers(sr, ws.shape[1] - 1), specs).run(ws)
     split0 = not (sr.block0.use_fp16 and not force_fp32)
     x = tcconv.to_nhwc_f16(feat_nchw, c_padded=tcconv.pad_to(feat_nchw.shape[1], 64), planes=2 if split0 else 1)
     up0 = sr.block0.conv0.up == 2
@@ -339,7 +442,12 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
     net_layers = _network_layers(net)
     n_net = len(net_layers)
     all_layers = net_layers + [lw for sr in srs for lw in _sr_layers(sr, ws.shape[1] - 1)]
-    styles = style_plan(gen, 'gen', all_layers).run(ws.to(torch.float32))
+    nch_feat = 64 if semantic else 32                      # feature channels the renderer returns (two decoder nets / one)
+    specs = [sp for res in net.block_resolutions for sp in _block_specs(getattr(net, f'b{res}'), force_fp32)]
+    for k, sr in enumerate(srs):
+        specs += _block_specs(sr.block0, force_fp32, tcconv.pad_to(nch_feat, 64), nch_feat // 2 if k == 1 else 0)
+        specs += _block_specs(sr.block1, force_fp32)
+    styles = weight_plan(gen, ('gen', bool(force_fp32)), all_layers, specs).run(ws.to(torch.float32))
     if use_cached_backbone and gen._last_planes is not None:
         planes_nchw = gen._last_planes
         planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))

@@ -105,6 +105,24 @@ def modulate_weights(weight, styles, demodulate=True, pre_scale=1.0, planes=1, c
     return out
 
 
+class ModwDesc(ctypes.Structure):  # p3d_modw_desc_t
+    _fields_ = [
+        ('weight_t', ctypes.c_void_p), ('wsq', ctypes.c_void_p), ('styles_off', ctypes.c_int64), ('out_off', ctypes.c_int64),
+        ('Cout', ctypes.c_int32), ('Cin', ctypes.c_int32), ('ktaps', ctypes.c_int32), ('Cout_padded', ctypes.c_int32),
+        ('Cin_padded', ctypes.c_int32), ('cin_offset', ctypes.c_int32), ('demodulate', ctypes.c_int32), ('planes', ctypes.c_int32),
+        ('pre_scale', ctypes.c_float), ('out_scale', ctypes.c_float), ('first_block', ctypes.c_int32), ('reserved', ctypes.c_int32),
+    ]
+
+
+def modulate_weights_batch(descs_dev, block_layer_dev, n_blocks, styles_flat, out_flat, batch):
+    """One launch for every layer described by `descs_dev` (device bytes of ModwDesc[]); see p3d_modulate_weights_batch."""
+    with torch.cuda.device(styles_flat.device):
+        st = _lib.lib().p3d_modulate_weights_batch(_lib.ptr(descs_dev), _lib.ptr(block_layer_dev), n_blocks, _lib.ptr(styles_flat),
+                                                   _lib.ptr(out_flat), batch, _lib.stream_ptr())
+    _lib.check(st, 'p3d_modulate_weights_batch')
+    _lib.bump()
+
+
 def affine_batch(ws, weight, bias, meta, out_numel):
     """ws [B,num_ws,w_dim] fp32; weight [rows,w_dim] (gains applied), bias [rows], meta int32 [rows,4] -> flat fp32 buffer."""
     ws = ws.detach().float().contiguous()
