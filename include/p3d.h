@@ -199,6 +199,11 @@ typedef struct {
     int32_t act;              /* 1 linear, 3 lrelu */
     float alpha, gain, clamp; /* activation slope, output gain, clamp (<0: none) */
     float acc_scale;          /* multiplies the accumulator first (undoes the power-of-two weight scaling) */
+    /* fused ToRGB tail (networks_stylegan2.py:452-458): when up_prev != NULL the launch writes
+     *   y = upsample2d(up_prev, up_filter) + result     (result rounded to fp16 first when round16, as fp16 blocks do)
+     * with up_prev [B, oH/2, oW/2, Cout] fp32 NHWC; out_mode must be 2; out_nchw writes y as [B, Cout, oH, oW]. */
+    const float* up_prev; const float* up_filter;
+    int32_t round16, out_nchw;
     void* splitk_scratch;     /* optional fp32 scratch (32-byte aligned): lets launches much smaller than the machine split */
     int64_t splitk_scratch_bytes; /* their K range over up to 16 CTAs each (deterministic two-kernel reduction); NULL/0 = never */
 } p3d_conv_args_t;

@@ -45,6 +45,10 @@ struct ConvKernelArgs {
     int splits;                       // split-K: blockIdx.z = b * splits + s; s covers k-steps [s*total/splits, (s+1)*total/splits)
     float* partial;                   // split-K: raw fp32 accumulators [splits][B][gH][gW][Cout_pad] (finished by a second kernel)
     int Cout_pad;
+    // fused ToRGB tail (SynthesisBlock.forward, networks_stylegan2.py:452-458): out = upsample2d(prev, f) + [fp16-rounded] y
+    const float* up_prev;             // [B, oH/2, oW/2, Cout] fp32 NHWC skip image of the previous block, or NULL
+    const float* up_f;                // 4x4 FIR
+    int round16, out_nchw;            // round y to fp16 first (fp16 blocks); write [B, Cout, oH, oW] instead of NHWC
     float pre_gain, post_gain;        // gain folded into scale/bias/noise (lrelu is positively homogeneous) or applied last
 };
 
@@ -75,9 +79,70 @@ __device__ __forceinline__ float conv_epilogue_act(float x, float alpha, float p
 // activation, clamp, and the store in the requested output mode.
 template <int kAct, bool kClamp>
 __device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32_t (&v)[32], const float* s_scale,
-                                                 const float* s_bias, int c0, int ch0, size_t off, float nz, bool vec_ok) {
+                                                 const float* s_bias, int c0, int ch0, size_t off, float nz, bool vec_ok,
+                                                 int b, int Y, int X) {
     const float alpha = a.alpha, post_gain = a.post_gain, clampv = a.clamp;
     const int out_mode = a.out_mode;
+    if (a.up_prev) {
+        // out = upsample2d(prev)[b, Y, X, :] + y. Polyphase form of the zero-insert x2 + 4x4 FIR + gain 4 (upfirdn2d.py:344-350):
+        // output row Y = 2*iy + py reads prev rows iy - 1 + py + {0, 1} with filter taps of parity py (same in x).
+        const int ph = a.oH >> 1, pw = a.oW >> 1, C = a.Cout;
+        const int iy = Y >> 1, py = Y & 1, ix = X >> 1, px = X & 1;
+        float w4[2][2];
+        const float* pp[2][2];
+#pragma unroll
+        for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                const int ry = iy - 1 + py + aa, rx = ix - 1 + px + cc;
+                const bool ok = ry >= 0 && ry < ph && rx >= 0 && rx < pw;
+                w4[aa][cc] = ok ? __ldg(a.up_f + (3 - (py + 2 * aa)) * 4 + (3 - (px + 2 * cc))) * 4.f : 0.f;
+                pp[aa][cc] = a.up_prev + (((size_t)b * ph + (ok ? ry : 0)) * pw + (ok ? rx : 0)) * C;
+            }
+        const int nvalid = min(32, C - ch0);
+        float* yo = reinterpret_cast<float*>(a.y);
+        if (!a.out_nchw && (C & 3) == 0 && nvalid == 32 && a.base_aligned) {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const int ch = ch0 + 4 * g4;
+                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(pp[aa][cc] + ch));
+                        const float w = w4[aa][cc];
+                        u.x = fmaf(w, t.x, u.x); u.y = fmaf(w, t.y, u.y); u.z = fmaf(w, t.z, u.z); u.w = fmaf(w, t.w, u.w);
+                    }
+                float r[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    float x = conv_epilogue_act<kAct, kClamp>(fmaf(__uint_as_float(v[4 * g4 + t]), s_scale[c0 + 4 * g4 + t], s_bias[c0 + 4 * g4 + t]) + nz,
+                                                              alpha, post_gain, clampv);
+                    if (a.round16) x = __half2float(__float2half_rn(x));
+                    r[t] = x;
+                }
+                *reinterpret_cast<float4*>(yo + off + 4 * g4) = make_float4(u.x + r[0], u.y + r[1], u.z + r[2], u.w + r[3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i >= nvalid) break;
+                const int ch = ch0 + i;
+                float u = 0.f;
+#pragma unroll
+                for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) u = fmaf(w4[aa][cc], __ldg(pp[aa][cc] + ch), u);
+                float x = conv_epilogue_act<kAct, kClamp>(fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_bias[c0 + i]) + nz, alpha,
+                                                          post_gain, clampv);
+                if (a.round16) x = __half2float(__float2half_rn(x));
+                const size_t o = a.out_nchw ? (((size_t)b * C + ch) * a.oH + Y) * a.oW + X : off + i;
+                yo[o] = u + x;
+            }
+        }
+        return;
+    }
                 if (vec_ok) {
     #pragma unroll
                     for (int j = 0; j < 2; ++j) {           // 16 channels per step
@@ -272,7 +337,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
             }
             if (ch0 >= a.Cout) continue;
             const size_t off = pix * a.y_cstride + a.y_coff + ch0;
-            conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, off, nz, vec_ok);
+            conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, off, nz, vec_ok, b, Y, X);
         }
     }
     tc::tc_fence_before();
@@ -416,7 +481,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
                 tc::tmem_ld_wait();
                 const int ch0 = n0 + c0;
                 if (!pix_ok || ch0 >= a.Cout) continue;
-                conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok);
+                conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok, b, Y, X);
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -573,6 +638,16 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.bias = p->bias; a.noise = p->noise; a.dscale = p->dscale;
     a.alpha = p->alpha; a.clamp = p->clamp; a.acc_scale = p->acc_scale;
     a.base_aligned = ((((uintptr_t)p->y) | ((uintptr_t)p->y_lo)) & 31) == 0;
+    a.up_prev = p->up_prev; a.up_f = p->up_filter; a.round16 = p->round16; a.out_nchw = p->out_nchw;
+    if (p->up_prev) {
+        // fused ToRGB tail: full-resolution 1:1 output map, fp32 output, even size, prev / y 16-byte aligned
+        if (!p->up_filter || p->out_mode != 2 || p->sy != 1 || p->sx != 1 || p->oy != 0 || p->ox != 0 || (p->oH & 1) || (p->oW & 1) ||
+            p->gH != p->oH || p->gW != p->oW || p->y_coff != 0 || (!p->out_nchw && p->y_cstride != p->Cout) ||
+            ((((uintptr_t)p->up_prev) | ((uintptr_t)p->y)) & 15) != 0)
+            return P3D_BAD_ARG;
+    } else if (p->out_nchw || p->round16) {
+        return P3D_BAD_ARG;
+    }
     // act(x) * gain == act(x * gain) for gain > 0 (linear and leaky-relu are positively homogeneous): fold the gain into the
     // per-channel scale / bias / noise so the per-element epilogue is fma + add + max (+ clamp)
     const bool fold = p->gain > 0.f;
@@ -611,7 +686,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     // the per-SM L2 ingest rate): every k-range becomes its own CTA writing raw fp32 partials into the caller's scratch
     // buffer; conv_splitk_finish_kernel adds them in a fixed order and applies the epilogue.
     a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
-    if (p->splitk_scratch && base_ctas * 2 <= sm_count() && total_k >= 8) {
+    if (p->splitk_scratch && !p->up_prev && base_ctas * 2 <= sm_count() && total_k >= 8) {
         int splits = (int)(sm_count() / base_ctas);
         if (splits > total_k / 4) splits = total_k / 4;
         if (splits > 16) splits = 16;

@@ -282,8 +282,13 @@ def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0)
                                alpha=0.2, act_gain=act_gain, clamp=clamp)
 
 
-def torgb_layer(layer, x, styles, img, split):
-    """ToRGBLayer.forward (:354-359) accumulated into the fp32 NHWC skip image (or creating it)."""
+def torgb_layer(layer, x, styles, img, split, upsample_filter=None, final_nchw=False):
+    """ToRGBLayer.forward (:354-359) plus the skip connection of SynthesisBlock.forward (:452-458).
+
+    img: fp32 NHWC skip image at THIS resolution (the convolution accumulates into it), or, with `upsample_filter`, the
+    skip image of the previous block at half resolution: `upsample2d(img, f) + y` is then formed in the convolution's
+    epilogue (one launch instead of upsample + conv + add [+ layout change]). `final_nchw` makes that launch write the
+    [B,C,H,W] tensor the caller returns."""
     planes = 2 if split else 1
     cout = layer.out_channels
     if isinstance(styles, ReadyWeights):
@@ -296,13 +301,21 @@ def torgb_layer(layer, x, styles, img, split):
     h, w = x.shape[2], x.shape[3]
     bias = _bias(layer, cout)
     clamp = float(layer.conv_clamp) if layer.conv_clamp is not None else -1.0
+    if upsample_filter is not None and img is not None:
+        assert img.shape[1] * 2 == h and img.shape[2] * 2 == w and img.shape[3] == cout
+        shape = (b, cout, h, w) if final_nchw else (b, h, w, cout)
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+        # fp16 blocks: the reference rounds the ToRGB output to fp16 before the fp32 skip add (:455-457)
+        tcconv.conv_gemm(x, wk, cout, tcconv.TAPS_1X1, (h, w), out, out_mode=2, split=split, bias=bias, act=1, gain=1.0, clamp=clamp,
+                         up_prev=img.contiguous(), up_filter=upsample_filter, round16=not split, out_nchw=final_nchw)
+        return out
+    assert not final_nchw
     if img is None:
         img = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float32)
         mode = 2
     else:
         mode = 3
     if not split:
-        # fp16 blocks: the reference rounds the ToRGB output to fp16 before the fp32 skip add (:455-457)
         y16 = torch.empty(b, h, w, cout, device=x.device, dtype=torch.float16)
         tcconv.conv_gemm(x, wk, cout, tcconv.TAPS_1X1, (h, w), y16, out_mode=0, bias=bias, act=1, gain=1.0, clamp=clamp)
         if mode == 2:
@@ -322,7 +335,7 @@ def _const_input(block, b, planes):
     return _cached(block, ('const', b, planes), [block.const], make)
 
 
-def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False, upsample=True, cin_offset=0):
+def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False, upsample=True, cin_offset=0, final_nchw=False):
     """One block on NHWC tensors. x: [planes,B,h,w,Cp] fp16 or None (first block); img: [B,h,w,Ci] fp32 or None;
     styles: the affine outputs of this block's layers in execution order (conv0, conv1, torgb).
     Returns (x, img) in the same representation. The precision of x switches at block boundaries as
@@ -339,8 +352,10 @@ def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False,
         x = synthesis_layer(block.conv0, x, next(s_iter), noise_mode, split, cin_offset=cin_offset)
         x = synthesis_layer(block.conv1, x, next(s_iter), noise_mode, split)
     if upsample and img is not None:
-        img = tcconv.upsample2x_nhwc(img, block.resample_filter)
-    img = torgb_layer(block.torgb, x, next(s_iter), img, split)
+        img = torgb_layer(block.torgb, x, next(s_iter), img, split, upsample_filter=block.resample_filter, final_nchw=final_nchw)
+    else:
+        assert not final_nchw
+        img = torgb_layer(block.torgb, x, next(s_iter), img, split)
     return x, img
 
 
@@ -486,8 +501,8 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
         x, im = synthesis_block(sr.block0, x, rgb, st[:n0], noise_mode=sr_noise, force_fp32=force_fp32, upsample=up0, cin_offset=c_off)
         if not up0:
             raw = im
-        x, im = synthesis_block(sr.block1, x, im, st[n0:], noise_mode=sr_noise, force_fp32=force_fp32, upsample=True)
-        return tcconv.nhwc_to_nchw_f32(im), raw.permute(0, 3, 1, 2).contiguous()
+        x, im = synthesis_block(sr.block1, x, im, st[n0:], noise_mode=sr_noise, force_fp32=force_fp32, upsample=True, final_nchw=True)
+        return im, raw.permute(0, 3, 1, 2).contiguous()
 
     image, image_raw = run_sr(gen.superresolution, 0, 3, styles[n_net:n_net + n_sr])
     out = {'image': image, 'image_raw': image_raw, 'image_depth': depth_image}

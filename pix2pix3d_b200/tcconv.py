@@ -28,6 +28,7 @@ class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
         ('bias', ctypes.c_void_p), ('noise', ctypes.c_void_p), ('dscale', ctypes.c_void_p),
         ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
         ('acc_scale', ctypes.c_float),
+        ('up_prev', ctypes.c_void_p), ('up_filter', ctypes.c_void_p), ('round16', ctypes.c_int32), ('out_nchw', ctypes.c_int32),
         ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64),
     ]
 
@@ -151,7 +152,8 @@ def _splitk_scratch(device):
 
 
 def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
-              noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True):
+              noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True,
+              up_prev=None, up_filter=None, round16=False, out_nchw=False):
     """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;
     out: NHWC tensor [B,oH,oW,Cs] (fp16 or fp32); out_map = (sy, oy, sx, ox)."""
     xp, b, h, wd, c = x.shape
@@ -166,7 +168,10 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
         a.tap_dy[i], a.tap_dx[i], a.tap_k[i] = dy, dx, kb
     a.split = 1 if split else 0
     a.gH, a.gW = grid_hw
-    ob, oh, ow, ocs = out.shape
+    if out_nchw:
+        ob, ocs, oh, ow = out.shape
+    else:
+        ob, oh, ow, ocs = out.shape
     assert ob == b and out.is_contiguous()
     a.oH, a.oW = oh, ow
     a.sy, a.oy, a.sx, a.ox = out_map
@@ -183,6 +188,10 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
     for t in (bias, noise, dscale):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     a.act, a.alpha, a.gain, a.clamp, a.acc_scale = act, alpha, gain, clamp, acc_scale
+    if up_prev is not None:      # fused ToRGB tail: out = upsample2d(up_prev, up_filter) + result
+        assert up_prev.dtype == torch.float32 and up_prev.is_contiguous() and up_filter.dtype == torch.float32 and up_filter.numel() == 16
+        a.up_prev, a.up_filter = up_prev.data_ptr(), up_filter.contiguous().data_ptr()
+        a.round16, a.out_nchw = int(round16), int(out_nchw)
     if split_k:
         scratch = _splitk_scratch(x.device)
         a.splitk_scratch, a.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4

@@ -230,3 +230,44 @@ def test_conv_large_tile_counts_and_fp16_output():
     torch.backends.cudnn.allow_tf32 = False
     ref = F.conv2d(x.half().float(), wm[0], padding=1)
     assert rel_err(out.float().permute(0, 3, 1, 2).cpu().numpy(), ref.cpu().numpy()) < 2e-3
+
+
+@pytest.mark.parametrize('cout,hw,split,nchw', [(3, (32, 48), False, True), (6, (16, 16), False, False), (96, (32, 32), True, False),
+                                                (19, (64, 64), False, True), (96, (256, 256), True, False)])
+def test_fused_torgb_tail_matches_upsample_plus_conv(cout, hw, split, nchw):
+    """out = upsample2d(prev, f) + ToRGB(x) in the convolution epilogue (networks_stylegan2.py:452-458), incl. the fp16
+    rounding of y in fp16 blocks and the direct NCHW output of the last block."""
+    from pix2pix3d_b200 import tcconv
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    torch.manual_seed(12)
+    b, c = 2, 128
+    h, w = hw
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 1, 1, device='cuda') / np.sqrt(c)
+    bias = torch.randn(cout, device='cuda')
+    prev = torch.randn(b, h // 2, w // 2, cout, device='cuda')
+    planes = 2 if split else 1
+    xn = tcconv.to_nhwc_f16(x, planes=planes)
+    wk = _weights_kmajor(wt, planes=planes, scale=tcconv.WEIGHT_SCALE)
+    out = torch.empty((b, cout, h, w) if nchw else (b, h, w, cout), device='cuda')
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_1X1, (h, w), out, out_mode=2, split=split, bias=bias, act=1, gain=1.0, clamp=256.0,
+                     up_prev=prev, up_filter=f, round16=not split, out_nchw=nchw)
+    # composition of the separate kernels
+    up = tcconv.upsample2x_nhwc(prev, f)
+    if split:
+        ref = up.clone()
+        tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_1X1, (h, w), ref, out_mode=3, split=True, bias=bias, act=1, gain=1.0, clamp=256.0)
+    else:
+        y16 = torch.empty(b, h, w, cout, device='cuda', dtype=torch.float16)
+        tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_1X1, (h, w), y16, out_mode=0, bias=bias, act=1, gain=1.0, clamp=256.0)
+        ref = up + y16
+    got = out.permute(0, 2, 3, 1) if nchw else out
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-6
+    # and against the plain torch formulation
+    y = F.conv2d(x if split else x.half().float(), wt if split else (wt * tcconv.WEIGHT_SCALE).half().float() / tcconv.WEIGHT_SCALE) + bias[None, :, None, None]
+    y = y.clamp(-256, 256)
+    if not split:
+        y = y.half().float()
+    tref = upfirdn2d.upsample2d(prev.permute(0, 3, 1, 2).contiguous(), f) + y
+    assert rel_err(got.permute(0, 3, 1, 2).cpu().numpy(), tref.cpu().numpy()) < (3e-5 if split else 2e-3)
