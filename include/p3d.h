@@ -267,13 +267,6 @@ int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* n
                      int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                      float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
 
-/* Same operation for fp16 tensors and a SEPARABLE filter (f[j][i] = fy[j] * fx[i], which the caller guarantees -- every
- * filter upfirdn2d.setup_filter builds from a 1-D kernel is): rows are filtered horizontally once and reused by the
- * four output rows they feed. Returns P3D_UNSUPPORTED for fp32 input (use p3d_fir_act_nhwc, which is HBM-bound there). */
-int p3d_fir_act_nhwc_sep(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
-                         int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                         float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
-
 /* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */
 int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream);
 

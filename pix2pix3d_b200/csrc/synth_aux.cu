@@ -379,114 +379,6 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant
     }
 }
 
-// Separable variant for fp16 tensors and rank-1 filters f = fy (x) fx (every filter setup_filter builds from a 1-D kernel,
-// upfirdn2d.py:64-69): a thread owns 4 rows x 2 columns x 4 channels; each input row is filtered horizontally once
-// (2 x 4 taps) and the result feeds the four output rows it belongs to. 11 FMA and 4.4 half->float conversions per
-// output element instead of 16 and 6.25 -- the 2-D kernel above is issue-bound on exactly those.
-__global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ f,
-                                                               const float* __restrict__ noise, const float* __restrict__ bias,
-                                                               __half* __restrict__ y, int out_planes, size_t out_plane_stride,
-                                                               int outH, int outW, int C, int padx0, int pady0, float fir_gain,
-                                                               int act, float alpha, float act_gain, float clamp) {
-    __shared__ __align__(128) uint2 tile[kFirIH * kFirIW * 16];     // 209 pixels x 128 bytes, as 8-byte channel quads
-    __shared__ __align__(8) uint64_t bar;
-    const int tiles_x = (outW + kFirTW - 1) / kFirTW;
-    const int tx0 = (blockIdx.x % tiles_x) * kFirTW, ty0 = (blockIdx.x / tiles_x) * kFirTH;
-    const int c0 = blockIdx.y * 64, b = blockIdx.z;
-    if (threadIdx.x == 0) {
-        tc::mbar_init(&bar, 1);
-        tc::fence_barrier_init();
-        tc::mbar_expect_tx(&bar, (uint32_t)sizeof(tile));
-        tc::tma_load_4d(tile, &tmX, &bar, c0, tx0 - padx0, ty0 - pady0, b);
-    }
-    // mirrored taps ft[j][i] = f[3-j][3-i] * gain = gy[j] * gx[i]
-    float gx[4], gy[4];
-    {
-        const float f00 = __ldg(f + 15);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            gx[i] = __ldg(f + 3 * 4 + (3 - i)) * fir_gain;          // row j = 0 of ft
-            gy[i] = __ldg(f + (3 - i) * 4 + 3) / f00;               // column i = 0 of ft, relative to ft[0][0]
-        }
-    }
-    const int cq = threadIdx.x & 15, blk = threadIdx.x >> 4;        // 16 blocks: 2 block-rows (4 rows) x 8 block-cols (2 cols)
-    const int by = (blk >> 3) * 4, bx = (blk & 7) * 2;
-    const int c = c0 + cq * 4;
-    float bv[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) bv[k] = bias ? __ldg(bias + c + k) : 0.f;
-    __syncthreads();
-    tc::mbar_wait(&bar, 0);
-    float acc[4][2][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        float win[5][4];
-#pragma unroll
-        for (int cc = 0; cc < 5; ++cc) {
-            const uint2 raw = tile[((by + r) * kFirIW + bx + cc) * 16 + cq];
-            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-            win[cc][0] = lo.x; win[cc][1] = lo.y; win[cc][2] = hi.x; win[cc][3] = hi.y;
-        }
-        float h[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                h[j][k] = fmaf(gx[3], win[j + 3][k], fmaf(gx[2], win[j + 2][k], fmaf(gx[1], win[j + 1][k], gx[0] * win[j][k])));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int ty = r - i;
-            if (ty < 0 || ty > 3) continue;
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][j][k] = fmaf(gy[ty], h[j][k], acc[i][j][k]);
-        }
-    }
-    const bool fast_lrelu = alpha >= 0.f && alpha <= 1.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int py = ty0 + by + i, px = tx0 + bx + j;
-            if (py >= outH || px >= outW) continue;
-            const float nz = noise ? __ldg(noise + (size_t)py * outW + px) : 0.f;
-            const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
-            __align__(8) __half2 hv[2], lv[2];
-#pragma unroll
-            for (int k = 0; k < 4; k += 2) {
-                // the fp16 reference rounds the FIR output, and again after the in-place noise add
-                float2 t = __half22float2(__floats2half2_rn(acc[i][j][k], acc[i][j][k + 1]));
-                float v0 = t.x, v1 = t.y;
-                if (noise) { t = __half22float2(__floats2half2_rn(v0 + nz, v1 + nz)); v0 = t.x; v1 = t.y; }
-                v0 += bv[k]; v1 += bv[k + 1];
-                if (act == 3) {
-                    const float m0 = v0 * alpha, m1 = v1 * alpha;
-                    if (fast_lrelu) { v0 = fmaxf(v0, m0); v1 = fmaxf(v1, m1); }
-                    else { v0 = v0 > 0.f ? v0 : m0; v1 = v1 > 0.f ? v1 : m1; }
-                }
-                v0 *= act_gain; v1 *= act_gain;
-                if (clamp >= 0.f) { v0 = fminf(fmaxf(v0, -clamp), clamp); v1 = fminf(fmaxf(v1, -clamp), clamp); }
-                const __half2 hh = __floats2half2_rn(v0, v1);
-                hv[k / 2] = hh;
-                if (out_planes == 2) {
-                    const float2 back = __half22float2(hh);
-                    lv[k / 2] = __floats2half2_rn(v0 - back.x, v1 - back.y);
-                }
-            }
-            *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
-            if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
-        }
-    }
-}
-
 // upsample2d(img, [1,3,3,1]) on fp32 NHWC: zero-insert x2, pad (2,1), 4x4 FIR, gain 4 (upfirdn2d.py:344-350).
 // Polyphase form: one thread owns an input pixel (x VEC channels) and writes its 2x2 output quad from the 3x3 input
 // neighbourhood; output (2y+py, 2x+px) only sees filter taps of parity (py, px), i.e. 2x2 of the 16 taps.
@@ -666,7 +558,7 @@ extern "C" int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, 
     return P3D_OK;
 }
 
-static int fir_act_nhwc_impl(bool separable, const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
+extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
                                 int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                                 float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
     if (!x || !f || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
@@ -688,11 +580,7 @@ static int fir_act_nhwc_impl(bool separable, const void* x, int in_dtype, const 
         if (rc != P3D_OK) return rc;
     }
     dim3 grid(tiles, C / cb, B);
-    if (separable) {
-        if (in_dtype != P3D_F16) return P3D_UNSUPPORTED;
-        fir_act_nhwc_sep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0,
-                                                                        pady0, fir_gain, act, alpha, act_gain, clamp);
-    } else if (in_dtype == P3D_F32)
+    if (in_dtype == P3D_F32)
         fir_act_nhwc_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW,
                                                                               C, padx0, pady0, fir_gain, act, alpha, act_gain, clamp);
     else
@@ -701,20 +589,6 @@ static int fir_act_nhwc_impl(bool separable, const void* x, int in_dtype, const 
                                                                                clamp);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
-}
-
-extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
-                                int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
-    return fir_act_nhwc_impl(false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
-                             alpha, act_gain, clamp, stream);
-}
-
-extern "C" int p3d_fir_act_nhwc_sep(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
-                                    int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                    float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
-    return fir_act_nhwc_impl(true, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
-                             alpha, act_gain, clamp, stream);
 }
 
 extern "C" int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream) {

@@ -236,32 +236,13 @@ def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SC
     return out
 
 
-_SEPARABLE = {}
-
-
-def filter_is_separable(f):
-    """True when the 4x4 filter is an outer product (checked once per filter tensor version, on the host)."""
-    key = (f.data_ptr(), f._version, f.device)
-    hit = _SEPARABLE.get(key)
-    if hit is None:
-        m = f.detach().double().cpu()
-        hit = bool(tuple(m.shape) == (4, 4) and float(m[0, 0]) != 0 and
-                   torch.allclose(m, torch.outer(m[:, 0], m[0, :]) / m[0, 0], rtol=1e-6, atol=1e-12))
-        if len(_SEPARABLE) > 64:
-            _SEPARABLE.clear()
-        _SEPARABLE[key] = hit
-    return hit
-
-
 def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):
     """x [B,inH,inW,C] fp32/fp16 NHWC -> [out_planes,B,outH,outW,C] fp16."""
     b, ih, iw, c = x.shape
     oh, ow = out_hw
     y = torch.empty(out_planes, b, oh, ow, c, device=x.device, dtype=torch.float16)
-    fn = _lib.lib().p3d_fir_act_nhwc_sep if (x.dtype == torch.float16 and c % 64 == 0 and filter_is_separable(f)) \
-        else _lib.lib().p3d_fir_act_nhwc
     with torch.cuda.device(x.device):
-        st = fn(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias),
+        st = _lib.lib().p3d_fir_act_nhwc(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias),
                                          _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha,
                                          act_gain, clamp, _lib.stream_ptr())
     _lib.check(st, 'p3d_fir_act_nhwc')
