@@ -267,19 +267,45 @@ def main():
     sem_host = torch.empty(B, w['semantic_channels'], w['img_resolution'], w['img_resolution'], dtype=torch.float32).pin_memory()
     ws_d, c_d = torch.empty_like(ws), torch.empty_like(c)
 
+    # Serving-style pipeline: inputs go in on the compute stream; outputs are staged device-side (two buffers) and read
+    # back on a copy stream, so the device->host copy of step i runs under the compute of step i+1. Every step still
+    # copies its own inputs in and its own outputs out, and the timed region ends after the last read-back has landed.
+    copy_stream = torch.cuda.Stream()
+    stage = [(torch.empty(img_host.shape, device=dev), torch.empty(sem_host.shape, device=dev)) for _ in range(2)]
+    staged_ev = [torch.cuda.Event() for _ in range(2)]      # outputs of a step are in stage[k]
+    drained_ev = [torch.cuda.Event() for _ in range(2)]     # stage[k] has been read back
+    for ev in drained_ev:
+        ev.record()
+    step_no = [0]
+
     def e2e_step():
+        k = step_no[0] & 1
+        step_no[0] += 1
+        cur = torch.cuda.current_stream()
         ws_d.copy_(ws_host, non_blocking=True)
         c_d.copy_(c_host, non_blocking=True)
         o = step(ws_d, c_d)
-        img_host.copy_(o['image'], non_blocking=True)
-        sem_host.copy_(o['semantic'], non_blocking=True)
+        cur.wait_event(drained_ev[k])
+        stage[k][0].copy_(o['image'], non_blocking=True)
+        stage[k][1].copy_(o['semantic'], non_blocking=True)
+        staged_ev[k].record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(staged_ev[k])
+            img_host.copy_(stage[k][0], non_blocking=True)
+            sem_host.copy_(stage[k][1], non_blocking=True)
+            drained_ev[k].record(copy_stream)
+
+    def e2e_drain():
+        torch.cuda.current_stream().wait_stream(copy_stream)
 
     for _ in range(3):
         e2e_step()
+    e2e_drain()
     barrier()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    e2e_drain()
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -345,7 +371,9 @@ def main():
         'rays_per_s': world * B * nrr * nrr * args.steps / (ms / 1000.0),
         'gpu_launches': launches,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': ms_e2e / args.steps},
+                'ms_per_step': ms_e2e / args.steps,
+                'pipeline': 'pinned-host ws/c in and image+semantic out every step; read-back of step i overlaps step i+1 '
+                            '(two staging buffers, copy stream); timed region ends after the last read-back'},
         'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor, 'cpu_baseline': cpu_baseline,
     }
     print(json.dumps(line), flush=True)
