@@ -498,6 +498,160 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for layers with >= 256 output channels: the two CTAs of a cluster sit on the two SMs of a
+// TPC and issue ONE M=256 x N=256 MMA per k-step. Each CTA stages its own 128 pixel rows of A and HALF of the weight
+// tile (128 of the 256 channel rows), so a k-step costs 32 KB per SM for 4.2 MFLOP per SM (131 FLOP/B, against 87 for
+// the single-CTA persistent kernel) -- the quantity that bounds these kernels is bytes into each SM per FLOP.
+// Persistent over a static schedule of (256-pixel, 256-channel) tiles; accumulators double-buffered (2 x 256 TMEM columns
+// per CTA). Leader (cluster rank 0): counts both CTAs' TMA bytes on its `full` barriers and issues the MMAs; completion is
+// multicast to both CTAs' `empty` / `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty`.
+// ---------------------------------------------------------------------------------------------
+constexpr int kQStages = 6;
+
+template <int kAct, bool kClamp>
+__global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                 const ConvKernelArgs a, int n_tiles, int tiles_n) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr uint32_t a_bytes = kBM * 128, b_bytes = 128 * 128, stage_bytes = a_bytes + b_bytes;   // per CTA
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kQStages * stage_bytes);
+    uint64_t* empty_bar = full_bar + kQStages;
+    uint64_t* tmem_full_bar = empty_bar + kQStages;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2] (the leader's are used)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_const = reinterpret_cast<float*>(smem + kQStages * stage_bytes + 256);     // [2 parities][scale 256 | bias 256]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc::cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int total_k = a.n_groups * a.kc_steps;
+    const int tiles_m = a.tiles_x * a.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmA);
+        tc::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kQStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 16); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc_pair(tmem_ptr_smem, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();                               // both CTAs' barriers exist before any remote arrive / complete_tx
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own half of B; bytes counted on the leader's barrier =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
+                const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+                const int n0 = tn * 256 + (int)rank * 128;
+                int g = 0, kc = 0;
+                for (int k = 0; k < total_k; ++k) {
+                    const int x0 = tx * a.BW + a.dx[g], y0 = (ty * 2 + (int)rank) * a.BH + a.dy[g];
+                    const int kb = a.tap[g] * a.Cin;
+                    tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    const uint32_t lead_full = tc::mapa_u32(tc::smem_u32(&full_bar[stage]), 0);
+                    if (rank == 0) tc::mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                    tc::tma_load_5d_pair(sa, &tmA, lead_full, kc * kBK, x0, y0, b, a.a_plane[g]);
+                    tc::tma_load_4d_pair(sa + a_bytes, &tmB, lead_full, kb + kc * kBK, n0, a.w_per_sample ? b : 0, a.b_plane[g]);
+                    if (++stage == kQStages) { stage = 0; phase ^= 1; }
+                    if (++kc == a.kc_steps) { kc = 0; ++g; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA =====
+        if (rank == 0 && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                tc::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);        // both CTAs' epilogues drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(as * 256);
+                for (int k = 0; k < total_k; ++k) {
+                    tc::mbar_wait(&full_bar[stage], phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
+                    const uint64_t da = tc::umma_desc_k128(sa), db = tc::umma_desc_k128(sa + a_bytes);
+#pragma unroll
+                    for (int j = 0; j < kBK / 16; ++j)
+                        tc::umma_f16_pair(acc, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
+                    tc::umma_commit_pair(&empty_bar[stage], 3);        // stage free in both CTAs
+                    if (k == total_k - 1) tc::umma_commit_pair(&tmem_full_bar[as], 3);
+                    if (++stage == kQStages) { stage = 0; phase ^= 1; }
+                }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): warps 2..9; column half = (warp - 2) / 4, TMEM lane quarter = warp % 4 =====
+        const int e = warp - 2, hsel = e >> 2, q = warp & 3;
+        const int m = q * 32 + lane;
+        const int et = threadIdx.x - 64;                // 0..255
+        const uint32_t lead_empty0 = tc::mapa_u32(tc::smem_u32(&tmem_empty_bar[0]), 0);
+        const uint32_t lead_empty1 = tc::mapa_u32(tc::smem_u32(&tmem_empty_bar[1]), 0);
+        int as = 0; uint32_t aphase = 0;
+        int parity = 0;
+        for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+            const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
+            const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+            const int n0 = tn * 256;
+            float* s_scale = s_const + parity * 512;
+            float* s_bias = s_scale + 256;
+            {
+                const int ch = n0 + et;
+                float sc = 0.f, bi = 0.f;
+                if (ch < a.Cout) {
+                    sc = a.acc_scale * a.pre_gain;
+                    if (a.dscale) sc *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
+                    if (a.bias) bi = __ldg(a.bias + ch) * a.pre_gain;
+                }
+                s_scale[et] = sc;
+                s_bias[et] = bi;
+            }
+            tc::named_bar_sync(1, 256);
+            const int gy = (ty * 2 + (int)rank) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
+            const bool pix_ok = (gy < a.gH) && (gx < a.gW);
+            const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
+            const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
+            const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+            const bool vec_ok = a.base_aligned && ((n0 + 256) <= a.Cout) &&
+                                (a.out_mode <= 1 ? ((a.y_cstride % 16) == 0 && ((a.y_coff + n0) % 16) == 0)
+                                                 : ((a.y_cstride % 8) == 0 && ((a.y_coff + n0) % 8) == 0));
+            tc::mbar_wait(&tmem_full_bar[as], aphase);
+            tc::tc_fence_after();
+            const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + hsel * 128);
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+                uint32_t v[32];
+                tc::tmem_ld_32x32(acc + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+                const int cc = hsel * 128 + c0, ch0 = n0 + cc;
+                if (!pix_ok || ch0 >= a.Cout) continue;
+                conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, cc, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok, b, Y, X);
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive_cluster(as == 0 ? lead_empty0 : lead_empty1);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+            parity ^= 1;
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::cluster_sync_all();                               // the peer may still be reading this CTA's smem / signalling its barriers
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
 // Second half of a split-K convolution: sums the k-range partials in a fixed order (deterministic) and applies the same
 // epilogue as the fused path. One thread per (pixel, 4 channels).
 __global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const ConvKernelArgs a, int B, int act) {
@@ -582,7 +736,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         return bw_best;
     };
     // persistent 256-pixel tiles when there is at least one tile per SM (P3D_CONV_PERSIST=0 disables, for A/B runs)
-    bool persist = false;
+    bool persist = false, pair = false;
     int BW = pick_bw(1, nullptr);
     {
         static int env = -1;
@@ -591,6 +745,12 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         const int bw2 = pick_bw(2, &area2);
         const long tiles2 = area2 / 256 * ceil_div(p->Cout_padded, BN) * p->B;
         if (env && tiles2 >= sm_count() && BN >= 32) { persist = true; BW = bw2; }
+        // CTA pairs (cta_group::2) for >= 256 output channels: one 256-pixel x 256-channel tile per pair
+        // (P3D_CONV_PAIR=0 keeps the single-CTA persistent kernel, for A/B runs)
+        static int env_pair = -1;
+        if (env_pair < 0) { const char* e = getenv("P3D_CONV_PAIR"); env_pair = (e && e[0] == '0') ? 0 : 1; }
+        const long tiles_pair = area2 / 256 * (p->Cout_padded / 256) * p->B;
+        if (persist && env_pair && p->Cout_padded % 256 == 0 && tiles_pair * 2 >= sm_count()) pair = true;
     }
     const int BH = kBM / BW;
     const int K = p->n_kblocks * p->C;
@@ -601,14 +761,14 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)p->x_planes};
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
-        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)(persist ? 2 * BH : BH), 1, 1};
+        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)((persist && !pair) ? 2 * BH : BH), 1, 1};
         int rc = make_tmap_f16_sw128(&tmA, p->x, 5, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)p->Cout_padded, (uint64_t)p->Bw, (uint64_t)p->w_planes};
         uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)p->Cout_padded * K * 2, (uint64_t)p->Bw * p->Cout_padded * K * 2};
-        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)BN, 1, 1};
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(pair ? 128 : BN), 1, 1};     // a pair CTA stages half of a 256-channel tile
         int rc = make_tmap_f16_sw128(&tmB, p->w, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
@@ -663,6 +823,37 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
     const int total_k = a.n_groups * a.kc_steps;
     const long base_ctas = (long)grid.x * grid.y * grid.z;
+    if (pair) {
+        a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
+        a.BN = 256;
+        a.idesc = tc::umma_idesc_f16(256, 256, 0);
+        const int tiles_n = p->Cout_padded / 256, n_tiles = a.tiles_x * a.tiles_y * tiles_n * p->B;
+        const size_t smem_q = kQStages * (size_t)(kBM * 128 + 128 * 128) + 256 + 2 * 512 * sizeof(float) + 1024;
+        int pairs = sm_count() / 2;
+        if (pairs > n_tiles) pairs = n_tiles;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs, 1, 1);
+        cfg.blockDim = dim3(320, 1, 1);
+        cfg.dynamicSmemBytes = smem_q;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+#define P3D_LAUNCH_PAIR(ACT, CL)                                                                                              \
+    do {                                                                                                                      \
+        P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_pair_kernel<ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                          (int)smem_q));                                                                      \
+        P3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<ACT, CL>, tmA, tmB, a, n_tiles, tiles_n));                \
+    } while (0)
+        if (act == 0) { if (clamp) P3D_LAUNCH_PAIR(0, true); else P3D_LAUNCH_PAIR(0, false); }
+        else if (act == 1) { if (clamp) P3D_LAUNCH_PAIR(1, true); else P3D_LAUNCH_PAIR(1, false); }
+        else { if (clamp) P3D_LAUNCH_PAIR(2, true); else P3D_LAUNCH_PAIR(2, false); }
+#undef P3D_LAUNCH_PAIR
+        P3D_LAUNCH_CHECK();
+        return P3D_OK;
+    }
     if (persist) {
         a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
         const int tiles_n = (int)grid.y, n_tiles = (int)base_ctas;

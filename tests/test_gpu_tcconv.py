@@ -271,3 +271,30 @@ def test_fused_torgb_tail_matches_upsample_plus_conv(cout, hw, split, nchw):
         y = y.half().float()
     tref = upfirdn2d.upsample2d(prev.permute(0, 3, 1, 2).contiguous(), f) + y
     assert rel_err(got.permute(0, 3, 1, 2).cpu().numpy(), tref.cpu().numpy()) < (3e-5 if split else 2e-3)
+
+
+@pytest.mark.parametrize('split', [False, True])
+def test_cta_pair_kernel_256_channel_tiles(split):
+    """Layers with >= 256 output channels and >= 74 tile pairs run on CTA pairs (cta_group::2, one 256x256 tile per two
+    SMs); the result must equal the single-CTA kernels' (P3D_CONV_PAIR=0 is read once per process, so compare with torch)."""
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(21)
+    b, c, h, w, cout = 2, 128, 96, 80, 512           # 2 * ceil(96*80/256) * 2 = 120 tile pairs, odd tile edges
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    bias = torch.randn(cout, device='cuda')
+    noise = torch.randn(h, w, device='cuda') * 0.3
+    planes = 2 if split else 1
+    xn = tcconv.to_nhwc_f16(x, planes=planes)
+    wk = _weights_kmajor(wt, planes=planes, scale=tcconv.WEIGHT_SCALE)
+    hi = torch.zeros(b, h, w, cout, device='cuda', dtype=torch.float16)
+    lo = torch.zeros_like(hi)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), hi, out_lo=lo if split else None, out_mode=1 if split else 0, split=split,
+                     bias=bias, noise=noise, act=3, alpha=0.2, gain=float(np.sqrt(2)), clamp=4.0)
+    got = (hi.float() + lo.float()) if split else hi.float()
+    torch.backends.cudnn.allow_tf32 = False
+    xr = x.double() if split else _h(x)
+    wr = wt.double() if split else (_h(wt * tcconv.WEIGHT_SCALE) / tcconv.WEIGHT_SCALE)
+    ref = F.conv2d(xr.cpu(), wr.cpu(), padding=1) + noise.double().cpu() + bias.double().cpu()[None, :, None, None]
+    ref = (F.leaky_relu(ref, 0.2) * np.sqrt(2)).clamp(-4, 4)
+    assert rel_err(got.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < (2e-5 if split else 1e-3)
