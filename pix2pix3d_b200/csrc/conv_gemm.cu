@@ -750,7 +750,10 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         static int env_pair = -1;
         if (env_pair < 0) { const char* e = getenv("P3D_CONV_PAIR"); env_pair = (e && e[0] == '0') ? 0 : 1; }
         const long tiles_pair = area2 / 256 * (p->Cout_padded / 256) * p->B;
-        if (persist && env_pair && p->Cout_padded % 256 == 0 && tiles_pair * 2 >= sm_count()) pair = true;
+        // (launches with a handful of k-steps per tile -- the 1- and 2-tap phases of a narrow transposed convolution -- are
+        //  prologue/epilogue-bound and measured slightly slower on pairs)
+        const int k_steps = (p->split ? 3 : 1) * p->n_taps * (p->C / kBK);
+        if (persist && env_pair && p->Cout_padded % 256 == 0 && tiles_pair * 2 >= sm_count() && k_steps >= 8) pair = true;
     }
     const int BH = kBM / BW;
     const int K = p->n_kblocks * p->C;
