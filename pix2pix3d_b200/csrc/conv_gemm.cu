@@ -507,23 +507,21 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
 // per CTA). Leader (cluster rank 0): counts both CTAs' TMA bytes on its `full` barriers and issues the MMAs; completion is
 // multicast to both CTAs' `empty` / `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty`.
 // ---------------------------------------------------------------------------------------------
-// Two shapes: kSub = 1, kN = 256 (a pair tile is 256 pixels x 256 channels) for layers with >= 256 output channels, and
-// kSub = 2, kN = 128 (512 pixels x 128 channels: each CTA stacks two 128-row sub-tiles that share its 64-row half of the weight
-// tile: 40 KB per SM per 4.2 MFLOP) for the 128-channel layers.
-template <int kAct, bool kClamp, int kSub, int kN>
+constexpr int kQStages = 6;
+
+template <int kAct, bool kClamp>
 __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                  const __grid_constant__ CUtensorMap tmB,
                                                                  const ConvKernelArgs a, int n_tiles, int tiles_n) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int kQStages = kSub == 1 ? 6 : 5;
-    constexpr uint32_t a_bytes = kSub * kBM * 128, b_bytes = (kN / 2) * 128, stage_bytes = a_bytes + b_bytes;   // per CTA
+    constexpr uint32_t a_bytes = kBM * 128, b_bytes = 128 * 128, stage_bytes = a_bytes + b_bytes;   // per CTA
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kQStages * stage_bytes);
     uint64_t* empty_bar = full_bar + kQStages;
     uint64_t* tmem_full_bar = empty_bar + kQStages;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2] (the leader's are used)
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    float* s_const = reinterpret_cast<float*>(smem + kQStages * stage_bytes + 256);     // [2 parities][scale kN | bias kN]
+    float* s_const = reinterpret_cast<float*>(smem + kQStages * stage_bytes + 256);     // [2 parities][scale 256 | bias 256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
@@ -552,10 +550,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
                 const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
                 const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
-                const int n0 = tn * kN + (int)rank * (kN / 2);
+                const int n0 = tn * 256 + (int)rank * 128;
                 int g = 0, kc = 0;
                 for (int k = 0; k < total_k; ++k) {
-                    const int x0 = tx * a.BW + a.dx[g], y0 = (ty * 2 + (int)rank) * kSub * a.BH + a.dy[g];
+                    const int x0 = tx * a.BW + a.dx[g], y0 = (ty * 2 + (int)rank) * a.BH + a.dy[g];
                     const int kb = a.tap[g] * a.Cin;
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
@@ -583,12 +581,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
                     const uint32_t sa = tc::smem_u32(smem + stage * stage_bytes);
                     const uint64_t da = tc::umma_desc_k128(sa), db = tc::umma_desc_k128(sa + a_bytes);
 #pragma unroll
-                    for (int mt = 0; mt < kSub; ++mt) {
-                        const uint64_t dam = da + (uint64_t)(mt * (kBM * 128 >> 4));
-#pragma unroll
-                        for (int j = 0; j < kBK / 16; ++j)
-                            tc::umma_f16_pair(acc + (uint32_t)(mt * kN), dam + (uint64_t)(j * 2), db + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
-                    }
+                    for (int j = 0; j < kBK / 16; ++j)
+                        tc::umma_f16_pair(acc, da + (uint64_t)(j * 2), db + (uint64_t)(j * 2), a.idesc, (k | j) != 0);
                     tc::umma_commit_pair(&empty_bar[stage], 3);        // stage free in both CTAs
                     if (k == total_k - 1) tc::umma_commit_pair(&tmem_full_bar[as], 3);
                     if (++stage == kQStages) { stage = 0; phase ^= 1; }
@@ -597,9 +591,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
             }
         }
     } else {
-        // ===== epilogue (both CTAs): warps 2..9; (warp - 2) / 4 = column half (kSub 1) or sub-tile (kSub 2), lane quarter = warp % 4
+        // ===== epilogue (both CTAs): warps 2..9; column half = (warp - 2) / 4, TMEM lane quarter = warp % 4 =====
         const int e = warp - 2, hsel = e >> 2, q = warp & 3;
-        const int mt = kSub == 2 ? hsel : 0, col0 = kSub == 2 ? 0 : hsel * 128;
         const int m = q * 32 + lane;
         const int et = threadIdx.x - 64;                // 0..255
         const uint32_t lead_empty0 = tc::mapa_u32(tc::smem_u32(&tmem_empty_bar[0]), 0);
@@ -609,10 +602,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
             const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
             const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
-            const int n0 = tn * kN;
-            float* s_scale = s_const + parity * (2 * kN);
-            float* s_bias = s_scale + kN;
-            if (et < kN) {
+            const int n0 = tn * 256;
+            float* s_scale = s_const + parity * 512;
+            float* s_bias = s_scale + 256;
+            {
                 const int ch = n0 + et;
                 float sc = 0.f, bi = 0.f;
                 if (ch < a.Cout) {
@@ -624,12 +617,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
                 s_bias[et] = bi;
             }
             tc::named_bar_sync(1, 256);
-            const int gy = ((ty * 2 + (int)rank) * kSub + mt) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
+            const int gy = (ty * 2 + (int)rank) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
             const bool pix_ok = (gy < a.gH) && (gx < a.gW);
             const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
             const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
             const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
-            const bool vec_ok = a.base_aligned && ((n0 + kN) <= a.Cout) &&
+            const bool vec_ok = a.base_aligned && ((n0 + 256) <= a.Cout) &&
                                 (a.out_mode <= 1 ? ((a.y_cstride % 16) == 0 && ((a.y_coff + n0) % 16) == 0)
                                                  : ((a.y_cstride % 8) == 0 && ((a.y_coff + n0) % 8) == 0));
             tc::mbar_wait(&tmem_full_bar[as], aphase);
@@ -639,7 +632,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
                 uint32_t v[32];
                 tc::tmem_ld_32x32(acc + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
-                const int cc = col0 + c0, ch0 = n0 + cc;
+                const int cc = hsel * 128 + c0, ch0 = n0 + cc;
                 if (!pix_ok || ch0 >= a.Cout) continue;
                 conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, cc, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok, b, Y, X);
             }
@@ -744,7 +737,6 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     };
     // persistent 256-pixel tiles when there is at least one tile per SM (P3D_CONV_PERSIST=0 disables, for A/B runs)
     bool persist = false, pair = false;
-    int pair_sub = 1;                 // 128-row sub-tiles per CTA of a pair (1: 256-channel tiles, 2: 128-channel tiles)
     int BW = pick_bw(1, nullptr);
     {
         static int env = -1;
@@ -758,16 +750,10 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         static int env_pair = -1;
         if (env_pair < 0) { const char* e = getenv("P3D_CONV_PAIR"); env_pair = (e && e[0] == '0') ? 0 : 1; }
         const long tiles_pair = area2 / 256 * (p->Cout_padded / 256) * p->B;
-        long area4 = 0;
-        const int bw4 = pick_bw(4, &area4);
-        const long tiles_pair128 = area4 / 512 * (p->Cout_padded / 128) * p->B;
         // (launches with a handful of k-steps per tile -- the 1- and 2-tap phases of a narrow transposed convolution -- are
         //  prologue/epilogue-bound and measured slightly slower on pairs)
         const int k_steps = (p->split ? 3 : 1) * p->n_taps * (p->C / kBK);
         if (persist && env_pair && p->Cout_padded % 256 == 0 && tiles_pair * 2 >= sm_count() && k_steps >= 8) pair = true;
-        else if (persist && env_pair && p->Cout_padded % 128 == 0 && tiles_pair128 * 2 >= sm_count() && k_steps >= 8) {
-            pair = true; pair_sub = 2; BW = bw4;
-        }
     }
     const int BH = kBM / BW;
     const int K = p->n_kblocks * p->C;
@@ -778,14 +764,14 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)p->x_planes};
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
-        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)(pair ? pair_sub * BH : (persist ? 2 * BH : BH)), 1, 1};
+        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)((persist && !pair) ? 2 * BH : BH), 1, 1};
         int rc = make_tmap_f16_sw128(&tmA, p->x, 5, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
     {
         uint64_t dims[4] = {(uint64_t)K, (uint64_t)p->Cout_padded, (uint64_t)p->Bw, (uint64_t)p->w_planes};
         uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)p->Cout_padded * K * 2, (uint64_t)p->Bw * p->Cout_padded * K * 2};
-        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(pair ? (pair_sub == 1 ? 128 : 64) : BN), 1, 1};     // a pair CTA stages half of the channel tile
+        uint32_t box[4] = {(uint32_t)kBK, (uint32_t)(pair ? 128 : BN), 1, 1};     // a pair CTA stages half of a 256-channel tile
         int rc = make_tmap_f16_sw128(&tmB, p->w, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
     }
@@ -805,7 +791,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.kc_steps = p->C / kBK;
     a.Cin = p->C;
     a.BW = BW; a.BH = BH;
-    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, pair ? 2 * pair_sub * BH : (persist ? 2 * BH : BH));
+    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, persist ? 2 * BH : BH);
     a.BN = BN; a.w_per_sample = p->Bw > 1 ? 1 : 0;
     a.idesc = tc::umma_idesc_f16(kBM, BN, 0);
     a.tmem_cols = BN <= 32 ? 32u : BN <= 64 ? 64u : 128u;
@@ -842,11 +828,10 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     const long base_ctas = (long)grid.x * grid.y * grid.z;
     if (pair) {
         a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
-        const int kn = pair_sub == 1 ? 256 : 128;
-        a.BN = kn;
-        a.idesc = tc::umma_idesc_f16(256, kn, 0);
-        const int tiles_n = p->Cout_padded / kn, n_tiles = a.tiles_x * a.tiles_y * tiles_n * p->B;
-        const size_t smem_q = (pair_sub == 1 ? 6 : 5) * (size_t)(pair_sub * kBM * 128 + (kn / 2) * 128) + 256 + 2 * 2 * kn * sizeof(float) + 1024;
+        a.BN = 256;
+        a.idesc = tc::umma_idesc_f16(256, 256, 0);
+        const int tiles_n = p->Cout_padded / 256, n_tiles = a.tiles_x * a.tiles_y * tiles_n * p->B;
+        const size_t smem_q = kQStages * (size_t)(kBM * 128 + 128 * 128) + 256 + 2 * 512 * sizeof(float) + 1024;
         int pairs = sm_count() / 2;
         if (pairs > n_tiles) pairs = n_tiles;
         cudaLaunchConfig_t cfg;
@@ -861,15 +846,9 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         cfg.attrs = attr; cfg.numAttrs = 1;
 #define P3D_LAUNCH_PAIR(ACT, CL)                                                                                              \
     do {                                                                                                                      \
-        if (pair_sub == 1) {                                                                                                  \
-            P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_pair_kernel<ACT, CL, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              (int)smem_q));                                                                  \
-            P3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<ACT, CL, 1, 256>, tmA, tmB, a, n_tiles, tiles_n));    \
-        } else {                                                                                                              \
-            P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_pair_kernel<ACT, CL, 2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                              (int)smem_q));                                                                  \
-            P3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<ACT, CL, 2, 128>, tmA, tmB, a, n_tiles, tiles_n));    \
-        }                                                                                                                     \
+        P3D_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_pair_kernel<ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                          (int)smem_q));                                                                      \
+        P3D_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<ACT, CL>, tmA, tmB, a, n_tiles, tiles_n));                \
     } while (0)
         if (act == 0) { if (clamp) P3D_LAUNCH_PAIR(0, true); else P3D_LAUNCH_PAIR(0, false); }
         else if (act == 1) { if (clamp) P3D_LAUNCH_PAIR(1, true); else P3D_LAUNCH_PAIR(1, false); }

@@ -273,15 +273,13 @@ def test_fused_torgb_tail_matches_upsample_plus_conv(cout, hw, split, nchw):
     assert rel_err(got.permute(0, 3, 1, 2).cpu().numpy(), tref.cpu().numpy()) < (3e-5 if split else 2e-3)
 
 
-@pytest.mark.parametrize('cout,hw', [(512, (96, 80)), (128, (168, 120)), (384, (100, 100))])
 @pytest.mark.parametrize('split', [False, True])
-def test_cta_pair_kernel_256_channel_tiles(split, cout, hw):
+def test_cta_pair_kernel_256_channel_tiles(split):
     """Layers with >= 256 output channels and >= 74 tile pairs run on CTA pairs (cta_group::2, one 256x256 tile per two
     SMs); the result must equal the single-CTA kernels' (P3D_CONV_PAIR=0 is read once per process, so compare with torch)."""
     from pix2pix3d_b200 import tcconv
     torch.manual_seed(21)
-    b, c = 2, 128          # 512 ch: 256x256 pair tiles; 128 / 384 ch: 512-pixel x 128-channel pair tiles; ragged tile edges
-    h, w = hw
+    b, c, h, w, cout = 2, 128, 96, 80, 512           # 2 * ceil(96*80/256) * 2 = 120 tile pairs, odd tile edges
     x = torch.randn(b, c, h, w, device='cuda')
     wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
     bias = torch.randn(cout, device='cuda')
