@@ -464,14 +464,21 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
         specs += _block_specs(sr.block1, force_fp32)
     styles = weight_plan(gen, ('gen', bool(force_fp32)), all_layers, specs).run(ws.to(torch.float32))
     if use_cached_backbone and gen._last_planes is not None:
+        # multi-view rendering from one latent (generate_video.py:57-69): the planes cached by an earlier call, kept in the
+        # gather layout next to the NCHW tensor the reference API exposes as `_last_planes`
         planes_nchw = gen._last_planes
-        planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
+        cached = _derived.get(gen, {}).get('planes_cl')
+        if cached is not None and cached[0] is planes_nchw and cached[1] == planes_nchw._version:
+            planes_cl = cached[2]
+        else:
+            planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
     else:
         img = _run_network(net, styles[:n_net], noise_mode, force_fp32)                                      # [B,H,W,96]
         h, w = img.shape[1], img.shape[2]
         planes_cl = img.view(b, h, w, 3, 32).permute(0, 3, 1, 2, 4)     # strided view, read in place by the renderer
         if cache_backbone:
             gen._last_planes = tcconv.nhwc_to_nchw_f32(img)
+            _derived.setdefault(gen, {})['planes_cl'] = (gen._last_planes, gen._last_planes._version, planes_cl)
     feats, depth, wsum = gen.renderer(None, gen.decoder, ray_origins, ray_directions, gen.rendering_kwargs,
                                       planes_channels_last=planes_cl)
     nch = feats.shape[-1]

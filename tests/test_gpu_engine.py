@@ -157,3 +157,40 @@ def test_full_size_workloads_engine_matches_generic_path(workload, batch):
     for k in ('image', 'semantic'):                # fp16 super-resolution stacks on both sides
         assert rel_err(fast[k].cpu().numpy(), ref[k].cpu().numpy()) < 2e-2, k
         assert fast[k].shape[-1] == w['img_resolution'] and torch.isfinite(fast[k]).all()
+
+
+def test_cached_backbone_multi_view_rendering():
+    """one latent, several cameras (generate_video.py:57-69): `cache_backbone=True` then
+    `use_cached_backbone=True` must reproduce what an uncached call renders for the same camera and noise."""
+    import pix2pix3d_b200.training.triplane_cond as tc
+    from make_golden import SYNTH_CASES, build_generator
+    from pix2pix3d_b200 import _lib
+    case = dict(SYNTH_CASES['seg_nrr64'])
+    G = build_generator(tc, case).cuda()
+    g = load_golden('synthesis_seg_nrr64')
+    ws, c = torch.from_numpy(g['ws']).cuda(), torch.from_numpy(g['c']).cuda()
+    kw = dict(noise_mode='const', neural_rendering_resolution=case['nrr'])
+    with torch.no_grad():
+        torch.manual_seed(3)
+        first = G.synthesis(ws, c, cache_backbone=True, **kw)
+        assert G._last_planes is not None and tuple(G._last_planes.shape[1:]) == (96, 256, 256)
+        c2 = c.clone()
+        c2[:, 3] += 0.04                                     # a second view
+        n0 = _lib.launch_count
+        torch.manual_seed(4)
+        cached = G.synthesis(ws, c2, use_cached_backbone=True, **kw)
+        n_cached = _lib.launch_count - n0
+        n0 = _lib.launch_count
+        torch.manual_seed(4)
+        fresh = G.synthesis(ws, c2, **kw)
+        n_fresh = _lib.launch_count - n0
+    assert n_cached < n_fresh                                # the backbone was skipped
+    for k in fresh:
+        assert rel_err(cached[k].cpu().numpy(), fresh[k].cpu().numpy()) < 1e-6, k
+    assert (first['image'] - cached['image']).abs().max() > 1e-4
+    # the reference API contract: a caller may overwrite _last_planes with its own NCHW tensor
+    with torch.no_grad():
+        G._last_planes = G._last_planes.clone()
+        torch.manual_seed(4)
+        again = G.synthesis(ws, c2, use_cached_backbone=True, **kw)
+    assert rel_err(again['image'].cpu().numpy(), fresh['image'].cpu().numpy()) < 1e-6
