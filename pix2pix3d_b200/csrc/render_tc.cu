@@ -355,6 +355,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
                     for (int i = lane; i < Sc - 1; i += 32) o[i] = rb[L.o_w + i];
                 }
                 warp_importance_cdf(rb + L.o_w, Sc, rb + L.o_om, rb + L.o_cdf, lane);
+                // stratified depths are non-decreasing by construction (renderer.py:169-192); when they are, the merge below
+                // knows a coarse sample's rank among the coarse ones (its index) and can binary-search them
+                bool mono = true;
+                for (int i = lane; i < Sc - 1; i += 32) mono = mono && (rb[L.o_dC + i] <= rb[L.o_dC + i + 1]);
+                mono = __all_sync(0xffffffffu, mono);
+                if (lane == 0) scal[4 * r + 1] = mono ? 1.f : 0.f;
             }
             __syncthreads();
 
@@ -392,7 +398,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             const float* dc = rbC + L.o_dC;
             const float* df = rbC + L.o_dF;
             int cnt = 0;
-            for (int i = 0; i < Sc; ++i) { float v = dc[i]; cnt += (v < dC) || (v == dC && i < sC); }
+            if (Sf > 0 && scal[4 * rC + 1] != 0.f) cnt = sC;
+            else for (int i = 0; i < Sc; ++i) { float v = dc[i]; cnt += (v < dC) || (v == dC && i < sC); }
             for (int k = 0; k < Sf; ++k) cnt += (df[k] < dC);
             rankC = cnt;
             rbC[L.o_sd + cnt] = dC;
@@ -404,7 +411,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             const float* df = rbF + L.o_dF;
             const float dFv = df[sF];
             int cnt = 0;
-            for (int i = 0; i < Sc; ++i) cnt += (dc[i] <= dFv);
+            if (scal[4 * rF + 1] != 0.f) {
+                int lo = 0, hi = Sc;                         // upper bound: number of coarse depths <= dFv
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (dc[mid] <= dFv) lo = mid + 1; else hi = mid; }
+                cnt = lo;
+            } else {
+                for (int i = 0; i < Sc; ++i) cnt += (dc[i] <= dFv);
+            }
             for (int k = 0; k < Sf; ++k) { float v = df[k]; cnt += (v < dFv) || (v == dFv && k < sF); }
             rankF = cnt;
             rbF[L.o_sd + cnt] = dFv;

@@ -220,3 +220,30 @@ def test_importance_renderer_module_dispatches_to_fused_kernel():
     assert rel_err(feat.cpu().numpy(), g['feat']) < TOL
     assert rel_err(depth.cpu().numpy(), g['depth']) < TOL
     assert rel_err(wsum.cpu().numpy(), g['wsum']) < TOL
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc'])
+def test_unsorted_and_tied_coarse_depths_still_merge_like_a_stable_sort(impl):
+    """The C-ABI accepts any depths_coarse. The tensor-core kernel takes a shortcut when a ray's coarse depths are
+    non-decreasing (what sample_stratified produces); rays that are not, and rays with exact ties, must still produce the
+    stable sort permutation of torch.sort / np.argsort(kind='stable') (renderer.py:162)."""
+    from pix2pix3d_b200 import native
+    g = load_golden('renderer_seg16')
+    dev = torch.device('cuda')
+    opts = render_opts(g)
+    b, m = g['ray_origins'].shape[:2]
+    sc, sf = int(g['Sc']), int(g['Sf'])
+    dc = O.renderer.sample_stratified(b, m, opts['ray_start'], opts['ray_end'], sc, g['jitter']).reshape(b, m, sc).copy()
+    dc[:, 0::3, [3, 4]] = dc[:, 0::3, [4, 3]]            # every third ray: one inversion
+    dc[:, 1::3, 7] = dc[:, 1::3, 6]                      # every third ray: an exact tie (still non-decreasing)
+    planes = torch.from_numpy(g['planes']).to(dev)
+    dec = native.pack_decoder(torch_decoder(g, dev))
+    feat, depth, wsum, dbg = native.render_fwd(native.planes_to_channels_last(planes), dec, torch.from_numpy(g['ray_origins']).to(dev),
+                                               torch.from_numpy(g['ray_dirs']).to(dev), torch.from_numpy(dc[..., None]).to(dev),
+                                               torch.from_numpy(g['u']).to(dev), opts['box_warp'], debug=True, impl=impl)
+    torch.cuda.synchronize()
+    kf = dbg['depths_fine'].cpu().numpy().reshape(b, m, sf)
+    alld = np.concatenate([dc, kf], -1)
+    perm = np.argsort(alld, axis=-1, kind='stable')
+    assert np.array_equal(dbg['perm'].cpu().numpy(), perm)
+    assert torch.isfinite(feat).all() and torch.isfinite(depth).all()
