@@ -235,6 +235,9 @@ SYNTH_CASES = {
     # neural rendering at the super-resolution stack's native input resolution (no resize): the whole-generator fast path
     'seg_nrr64': dict(seed=24, cls='TriPlaneSemanticEntangleGenerator', img_resolution=128, semantic_channels=6, nrr=64, Sc=8,
                       Sf=8, B=1, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
+    # BASELINE config 3 (celeba): 19 semantic classes -> 19-channel ToRGB / raw-logit semantic branch
+    'face_tiny': dict(seed=25, cls='TriPlaneSemanticEntangleGenerator', img_resolution=128, semantic_channels=19, nrr=16, Sc=8,
+                      Sf=8, B=1, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
     'rgb_tiny': dict(seed=23, cls='TriPlaneGenerator', img_resolution=128, semantic_channels=0, nrr=16, Sc=10, Sf=6, B=1,
                      channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32),
 }
