@@ -744,7 +744,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         long area2 = 0;
         const int bw2 = pick_bw(2, &area2);
         const long tiles2 = area2 / 256 * ceil_div(p->Cout_padded, BN) * p->B;
-        if (env && tiles2 >= sm_count() && BN >= 32) { persist = true; BW = bw2; }
+        if (env && tiles2 >= sm_count()) { persist = true; BW = bw2; }
         // CTA pairs (cta_group::2) for >= 256 output channels: one 256-pixel x 256-channel tile per pair
         // (P3D_CONV_PAIR=0 keeps the single-CTA persistent kernel, for A/B runs)
         static int env_pair = -1;

@@ -233,7 +233,8 @@ def test_conv_large_tile_counts_and_fp16_output():
 
 
 @pytest.mark.parametrize('cout,hw,split,nchw', [(3, (32, 48), False, True), (6, (16, 16), False, False), (96, (32, 32), True, False),
-                                                (19, (64, 64), False, True), (96, (256, 256), True, False)])
+                                                (19, (64, 64), False, True), (96, (256, 256), True, False),
+                                                (3, (256, 256), False, True), (6, (256, 192), False, True)])
 def test_fused_torgb_tail_matches_upsample_plus_conv(cout, hw, split, nchw):
     """out = upsample2d(prev, f) + ToRGB(x) in the convolution epilogue (networks_stylegan2.py:452-458), incl. the fp16
     rounding of y in fp16 blocks and the direct NCHW output of the last block."""
