@@ -204,6 +204,12 @@ typedef struct {
      * with up_prev [B, oH/2, oW/2, Cout] fp32 NHWC; out_mode must be 2; out_nchw writes y as [B, Cout, oH, oW]. */
     const float* up_prev; const float* up_filter;
     int32_t round16, out_nchw;
+    /* strided convolutions (conv2d_resample.py:108-111, the down=2 layers of DiscriminatorBlock / the label-map Encoder):
+     * output pixel (y, x) reads input pixels (stride*y + dy, stride*x + dx); stride 0/1 = dense, 2 supported. */
+    int32_t stride, reserved0;
+    /* resnet skip connection (networks_stylegan2.py:524-528): fp32 [B, oH, oW, Cout] (32-byte aligned, Cout % 8 == 0 for the
+     * vector path) added after activation / gain / clamp; out_mode 0-2 with the identity output map. NULL = none. */
+    const float* residual;
     void* splitk_scratch;     /* optional fp32 scratch (32-byte aligned): lets launches much smaller than the machine split */
     int64_t splitk_scratch_bytes; /* their K range over up to 16 CTAs each (deterministic two-kernel reduction); NULL/0 = never */
 } p3d_conv_args_t;
@@ -266,6 +272,13 @@ int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, int c_strid
 int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
                      int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                      float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
+
+/* The same operation on a split (hi/lo) fp16 input [2][B][inH][inW][C] whose value is hi + lo (fp32 semantics, no fp16
+ * rounding of the filtered value): the FIR in front of the strided convolutions of the down=2 layers
+ * (conv2d_resample.py:108-111) when the producer wrote a split tensor. */
+int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noise, const float* bias, void* y,
+                           int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                           float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
 
 /* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */
 int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream);

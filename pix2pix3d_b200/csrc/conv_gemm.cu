@@ -48,6 +48,8 @@ struct ConvKernelArgs {
     // fused ToRGB tail (SynthesisBlock.forward, networks_stylegan2.py:452-458): out = upsample2d(prev, f) + [fp16-rounded] y
     const float* up_prev;             // [B, oH/2, oW/2, Cout] fp32 NHWC skip image of the previous block, or NULL
     const float* up_f;                // 4x4 FIR
+    int stride;                       // input pixels per output pixel (1, or 2 for the down=2 layers)
+    const float* residual;            // fp32 [B, oH, oW, Cout]: added after the activation (resnet skip), or NULL
     int round16, out_nchw;            // round y to fp16 first (fp16 blocks); write [B, Cout, oH, oW] instead of NHWC
     float pre_gain, post_gain;        // gain folded into scale/bias/noise (lrelu is positively homogeneous) or applied last
 };
@@ -159,6 +161,16 @@ __device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32
                         }
     #pragma unroll
                         for (int t = 0; t < 16; ++t) r[t] = conv_epilogue_act<kAct, kClamp>(r[t], alpha, post_gain, clampv);
+                        if (a.residual) {       // resnet skip (networks_stylegan2.py:524-528): added after the activation
+                            const float* rp = a.residual + (((size_t)b * a.oH + Y) * a.oW + X) * a.Cout + ch0 + 16 * j;
+    #pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t o[8];
+                                ld_global_256(rp + 8 * h, o);
+    #pragma unroll
+                                for (int t = 0; t < 8; ++t) r[8 * h + t] += __uint_as_float(o[t]);
+                            }
+                        }
                         if (out_mode >= 2) {
                             float* yp = reinterpret_cast<float*>(a.y) + off + 16 * j;
     #pragma unroll
@@ -196,8 +208,9 @@ __device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32
     #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (i < nvalid) {
-                            const float x = conv_epilogue_act<kAct, kClamp>(
+                            float x = conv_epilogue_act<kAct, kClamp>(
                                 fmaf(__uint_as_float(v[i]), s_scale[c0 + i], s_bias[c0 + i]) + nz, alpha, post_gain, clampv);
+                            if (a.residual) x += __ldg(a.residual + (((size_t)b * a.oH + Y) * a.oW + X) * a.Cout + ch0 + i);
                             if (out_mode <= 1) {
                                 const __half h = __float2half_rn(x);
                                 reinterpret_cast<__half*>(a.y)[off + i] = h;
@@ -272,7 +285,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
             int stage = 0; uint32_t phase = 0;
             int g = k_begin / a.kc_steps, kc = k_begin - g * a.kc_steps;
             for (int k = 0; k < total_k; ++k) {
-                const int x0 = tx * a.BW + a.dx[g], y0 = ty * a.BH + a.dy[g];
+                const int x0 = tx * a.BW * a.stride + a.dx[g], y0 = ty * a.BH * a.stride + a.dy[g];
                 const int kb = a.tap[g] * a.Cin;
                 tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * stage_bytes;
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
                 const int n0 = tn * a.BN;
                 int g = 0, kc = 0;
                 for (int k = 0; k < total_k; ++k) {
-                    const int x0 = tx * a.BW + a.dx[g], y0 = ty * 2 * a.BH + a.dy[g];
+                    const int x0 = tx * a.BW * a.stride + a.dx[g], y0 = ty * 2 * a.BH * a.stride + a.dy[g];
                     const int kb = a.tap[g] * a.Cin;
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
                 const int n0 = tn * 256 + (int)rank * 128;
                 int g = 0, kc = 0;
                 for (int k = 0; k < total_k; ++k) {
-                    const int x0 = tx * a.BW + a.dx[g], y0 = (ty * 2 + (int)rank) * a.BH + a.dy[g];
+                    const int x0 = tx * a.BW * a.stride + a.dx[g], y0 = (ty * 2 + (int)rank) * a.BH * a.stride + a.dy[g];
                     const int kb = a.tap[g] * a.Cin;
                     tc::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
@@ -704,8 +717,8 @@ __global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const ConvKerne
 // host side
 // ---------------------------------------------------------------------------------------------
 static int make_tmap_f16_sw128(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                               const uint32_t* box) {
-    return make_tmap(tm, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, rank, dims, strides_bytes, box);
+                               const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+    return make_tmap(tm, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B, rank, dims, strides_bytes, box, elem_strides);
 }
 
 }  // namespace p3d
@@ -724,11 +737,14 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
     // spatial tile BW x BH = 128 pixels: the power-of-two split with the least padded area (ties -> wider rows);
     // `rows` = sub-tiles stacked in y per CTA tile (2 for the persistent kernel)
+    const int stride = p->stride > 1 ? p->stride : 1;
+    if (stride > 2) return P3D_UNSUPPORTED;
     auto pick_bw = [&](int rows, long* area_out) {
         int bw_best = 1;
         long best = -1;
         for (int bw = 1; bw <= 64; bw *= 2) {
             int bh = kBM / bw * rows;
+            if (bw * stride > 256 || bh * stride > 256) continue;      // TMA box extent (in input pixels) <= 256
             long area = (long)ceil_div(p->gW, bw) * bw * ceil_div(p->gH, bh) * bh;
             if (best < 0 || area <= best) { best = area; bw_best = bw; }
         }
@@ -764,8 +780,11 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         uint64_t dims[5] = {(uint64_t)p->C, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->B, (uint64_t)p->x_planes};
         uint64_t str[4] = {(uint64_t)p->C * 2, (uint64_t)p->W * p->C * 2, (uint64_t)p->H * p->W * p->C * 2,
                            (uint64_t)p->B * p->H * p->W * p->C * 2};
-        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)BW, (uint32_t)((persist && !pair) ? 2 * BH : BH), 1, 1};
-        int rc = make_tmap_f16_sw128(&tmA, p->x, 5, dims, str, box);
+        // a strided convolution samples every `stride`-th input pixel: the TMA walks the box with that element stride
+        // (box extents are then given in input pixels: N loaded pixels need an extent of N * stride)
+        uint32_t box[5] = {(uint32_t)kBK, (uint32_t)(BW * stride), (uint32_t)(((persist && !pair) ? 2 * BH : BH) * stride), 1, 1};
+        uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
+        int rc = make_tmap_f16_sw128(&tmA, p->x, 5, dims, str, box, es);
         if (rc != P3D_OK) return rc;
     }
     {
@@ -802,6 +821,10 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.alpha = p->alpha; a.clamp = p->clamp; a.acc_scale = p->acc_scale;
     a.base_aligned = ((((uintptr_t)p->y) | ((uintptr_t)p->y_lo)) & 31) == 0;
     a.up_prev = p->up_prev; a.up_f = p->up_filter; a.round16 = p->round16; a.out_nchw = p->out_nchw;
+    a.stride = stride; a.residual = p->residual;
+    if (p->residual && (p->up_prev || p->out_mode > 2 || p->sy != 1 || p->sx != 1 || p->oy != 0 || p->ox != 0 ||
+                        (((uintptr_t)p->residual) & 31) != 0))
+        return P3D_BAD_ARG;
     if (p->up_prev) {
         // fused ToRGB tail: full-resolution 1:1 output map, fp32 output, even size, prev / y 16-byte aligned
         if (!p->up_filter || p->out_mode != 2 || p->sy != 1 || p->sx != 1 || p->oy != 0 || p->ox != 0 || (p->oH & 1) || (p->oW & 1) ||
@@ -880,7 +903,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     // the per-SM L2 ingest rate): every k-range becomes its own CTA writing raw fp32 partials into the caller's scratch
     // buffer; conv_splitk_finish_kernel adds them in a fixed order and applies the epilogue.
     a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
-    if (p->splitk_scratch && !p->up_prev && base_ctas * 2 <= sm_count() && total_k >= 8) {
+    if (p->splitk_scratch && !p->up_prev && !p->residual && base_ctas * 2 <= sm_count() && total_k >= 8) {
         int splits = (int)(sm_count() / base_ctas);
         if (splits > total_k / 4) splits = total_k / 4;
         if (splits > 16) splits = 16;

@@ -265,14 +265,17 @@ __device__ __forceinline__ void load_vec<__half, 8>(const __half* p, float (&v)[
 // vector from 25 conflict-free LDS.128. The filter gain is folded into the taps (as upfirdn2d.py:186 scales f).
 constexpr int kFirTH = 8, kFirTW = 16, kFirIH = kFirTH + 3, kFirIW = kFirTW + 3;
 
-template <class TIn, int VEC>
+// kSplitIn (fp16 only): the input is a hi/lo pair of planes [2][B][inH][inW][C] (the value is hi + lo); both halo tiles
+// are staged and summed in fp32 before filtering.
+template <class TIn, int VEC, bool kSplitIn = false>
 __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ f,
                                                            const float* __restrict__ noise, const float* __restrict__ bias,
                                                            __half* __restrict__ y, int out_planes, size_t out_plane_stride,
                                                            int outH, int outW, int C, int padx0, int pady0, float fir_gain,
-                                                           int act, float alpha, float act_gain, float clamp) {
-    __shared__ __align__(128) uint4 tile[kFirIH * kFirIW * 8];      // 209 pixels x 128 bytes
+                                                           int act, float alpha, float act_gain, float clamp, int B) {
+    extern __shared__ __align__(128) uint4 tile[];   // 209 pixels x 128 bytes (x 2 planes when kSplitIn)
     __shared__ __align__(8) uint64_t bar;
+    constexpr int kTileVecs = kFirIH * kFirIW * 8;
     constexpr int CB = 8 * VEC;                      // channels per block (8 vectors of 16 bytes)
     const int tiles_x = (outW + kFirTW - 1) / kFirTW;
     const int tx0 = (blockIdx.x % tiles_x) * kFirTW, ty0 = (blockIdx.x / tiles_x) * kFirTH;
@@ -280,15 +283,16 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant
     if (threadIdx.x == 0) {
         tc::mbar_init(&bar, 1);
         tc::fence_barrier_init();
-        tc::mbar_expect_tx(&bar, (uint32_t)sizeof(tile));
+        tc::mbar_expect_tx(&bar, (uint32_t)(kTileVecs * 16 * (kSplitIn ? 2 : 1)));
         tc::tma_load_4d(tile, &tmX, &bar, c0, tx0 - padx0, ty0 - pady0, b);
+        if (kSplitIn) tc::tma_load_4d(tile + kTileVecs, &tmX, &bar, c0, tx0 - padx0, ty0 - pady0, B + b);      // lo plane
     }
     float ft[4][4];                                  // mirrored taps: true convolution (flip_filter=False)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) ft[j][i] = __ldg(f + (3 - j) * 4 + (3 - i)) * fir_gain;
-    const bool round16 = (sizeof(TIn) == 2);
+    const bool round16 = (sizeof(TIn) == 2) && !kSplitIn;     // a hi/lo input carries fp32 semantics
     const int v = threadIdx.x & 7, blk = threadIdx.x >> 3;          // 32 blocks: 4 rows x 8 cols of 2x2
     const int by = (blk >> 3) * 2, bx = (blk & 7) * 2;
     const int c = c0 + v * VEC;
@@ -315,6 +319,12 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant
                 const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
                 for (int k = 0; k < VEC / 2; ++k) { float2 t = __half22float2(h[k]); win[cc][2 * k] = t.x; win[cc][2 * k + 1] = t.y; }
+                if (kSplitIn) {
+                    const uint4 rawl = tile[kTileVecs + ((by + r) * kFirIW + bx + cc) * 8 + v];
+                    const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
+#pragma unroll
+                    for (int k = 0; k < VEC / 2; ++k) { float2 t = __half22float2(hl[k]); win[cc][2 * k] += t.x; win[cc][2 * k + 1] += t.y; }
+                }
             } else {
                 const float* fp = reinterpret_cast<const float*>(&raw);
 #pragma unroll
@@ -558,7 +568,7 @@ extern "C" int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, 
     return P3D_OK;
 }
 
-extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
+static int fir_act_nhwc_impl(bool split_in, const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
                                 int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                                 float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
     if (!x || !f || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
@@ -567,12 +577,13 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
     const int tiles = ceil_div(outW, kFirTW) * ceil_div(outH, kFirTH);
     if (B > 65535) return P3D_UNSUPPORTED;
     if (in_dtype != P3D_F32 && in_dtype != P3D_F16) return P3D_BAD_ARG;
+    if (split_in && in_dtype != P3D_F16) return P3D_BAD_ARG;
     const int es = in_dtype == P3D_F32 ? 4 : 2, cb = 128 / es;
     if (C % cb) return P3D_UNSUPPORTED;
     if (((uintptr_t)x & 15) != 0) return P3D_BAD_ARG;
     CUtensorMap tm;
     {
-        uint64_t dims[4] = {(uint64_t)C, (uint64_t)inW, (uint64_t)inH, (uint64_t)B};
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)inW, (uint64_t)inH, (uint64_t)B * (split_in ? 2 : 1)};   // lo plane = images B..2B-1
         uint64_t str[3] = {(uint64_t)C * es, (uint64_t)inW * C * es, (uint64_t)inH * inW * C * es};
         uint32_t box[4] = {(uint32_t)cb, (uint32_t)kFirIW, (uint32_t)kFirIH, 1};
         int rc = make_tmap(&tm, x, in_dtype == P3D_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
@@ -580,15 +591,36 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
         if (rc != P3D_OK) return rc;
     }
     dim3 grid(tiles, C / cb, B);
-    if (in_dtype == P3D_F32)
-        fir_act_nhwc_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW,
-                                                                              C, padx0, pady0, fir_gain, act, alpha, act_gain, clamp);
+    const size_t tile_bytes = (size_t)kFirIH * kFirIW * 128;
+    if (split_in) {
+        P3D_CUDA_TRY(cudaFuncSetAttribute(fir_act_nhwc_kernel<__half, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(2 * tile_bytes)));
+        fir_act_nhwc_kernel<__half, 8, true><<<grid, 256, 2 * tile_bytes, (cudaStream_t)stream>>>(
+            tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act, alpha, act_gain, clamp, B);
+    } else if (in_dtype == P3D_F32)
+        fir_act_nhwc_kernel<float, 4><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH,
+                                                                                       outW, C, padx0, pady0, fir_gain, act, alpha, act_gain,
+                                                                                       clamp, B);
     else
-        fir_act_nhwc_kernel<__half, 8><<<grid, 256, 0, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH,
-                                                                               outW, C, padx0, pady0, fir_gain, act, alpha, act_gain,
-                                                                               clamp);
+        fir_act_nhwc_kernel<__half, 8><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH,
+                                                                                        outW, C, padx0, pady0, fir_gain, act, alpha,
+                                                                                        act_gain, clamp, B);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
+}
+
+extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
+                                int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                                float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
+    return fir_act_nhwc_impl(false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
+                             alpha, act_gain, clamp, stream);
+}
+
+extern "C" int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noise, const float* bias, void* y,
+                                      int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                                      float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
+    return fir_act_nhwc_impl(true, x_hi_lo, P3D_F16, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain,
+                             act, alpha, act_gain, clamp, stream);
 }
 
 extern "C" int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream) {

@@ -23,13 +23,14 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 // dims / box: innermost first; strides_bytes[i] = byte stride of dimension i+1. Out-of-bounds elements read as zero.
+// elem_strides (optional): traversal stride per dimension; a dimension with stride s loads ceil(box / s) elements.
 inline int make_tmap(CUtensorMap* tm, const void* base, CUtensorMapDataType dtype, CUtensorMapSwizzle swizzle, int rank,
-                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+                     const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return P3D_UNSUPPORTED;
     cuuint64_t gdim[5], gstr[4];
     cuuint32_t bx[5], es[5];
-    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
     for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
     CUresult r = fn(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -410,6 +410,75 @@ def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=F
 
 
 # ----------------------------------------------------------------------------------------------
+# label-map Encoder of the conditional mapping networks (triplane_cond.py:66-196): a resnet pyramid
+# of DiscriminatorBlocks (networks_stylegan2.py:559-643) with static weights, fp32 semantics -> three-pass split GEMMs
+# ----------------------------------------------------------------------------------------------
+_TAPS_3X3_VALID = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]     # strided conv on the pre-padded FIR output
+
+
+def _static_weights(layer, cin_p):
+    """K-major fp16 hi/lo image of an unmodulated Conv2dLayer weight x weight_gain (computed once per weight version)."""
+    def make():
+        ones = torch.ones(1, layer.weight.shape[1], device=layer.weight.device)
+        return tcconv.modulate_weights(layer.weight, ones, demodulate=False, pre_scale=float(layer.weight_gain), planes=2,
+                                       cin_padded=cin_p)
+    return _cached(layer, ('wstatic', cin_p), [layer.weight], make)
+
+
+def encoder_supported(enc, img):
+    if not enabled or img.device.type != 'cuda' or grad_needed(enc, img):
+        return False
+    if enc.architecture != 'resnet' or img.shape[-1] != enc.img_resolution or img.shape[-2] != enc.img_resolution:
+        return False
+    for res in enc.block_resolutions:
+        blk = getattr(enc, f'b{res}')
+        if blk.use_fp16 or blk.architecture != 'resnet' or blk.conv0.activation != 'lrelu' or blk.conv1.activation != 'lrelu':
+            return False
+        if blk.conv0.conv_clamp is not None or blk.conv0.out_channels % 64 or blk.conv1.out_channels % 64:
+            return False
+    return True
+
+
+def _encoder_block(blk, x, xin, b, res):
+    c, cout = blk.conv0.out_channels, blk.conv1.out_channels
+    dev = (x if x is not None else xin).device
+    if blk.in_channels == 0:                                   # fromrgb: 1x1 + bias + lrelu (:518-522)
+        lay = blk.fromrgb
+        x = _alloc(2, b, res, res, c, c, dev)
+        tcconv.conv_gemm(xin, _static_weights(lay, xin.shape[-1]), c, tcconv.TAPS_1X1, (res, res), x[0], out_lo=x[1], out_mode=1,
+                         split=True, bias=_bias(lay, c), act=3, alpha=0.2, gain=float(lay.act_gain))
+    f = blk.resample_filter
+    h2 = res // 2
+    # skip = 1x1 conv of the FIR-downsampled input (conv2d_resample.py:96-99 with pad (1,1), down 2): the full-resolution FIR
+    # output with pad (2,2), sampled at the odd positions -- i.e. tap (1,1) of the same stride-2 grid conv1 uses
+    fx = tcconv.fir_act_nhwc(x, f, None, None, 2, (res + 1, res + 1), pad0=(2, 2), fir_gain=1.0, act=1, act_gain=1.0)
+    y = torch.empty(b, h2, h2, cout, device=dev, dtype=torch.float32)
+    tcconv.conv_gemm(fx, _static_weights(blk.skip, c), cout, [(1, 1, 0)], (h2, h2), y, out_mode=2, split=True, act=1,
+                     gain=float(np.sqrt(0.5)), stride=2)
+    # conv0: 3x3 + bias + lrelu, kept in fp32 for the FIR that precedes the strided conv1
+    t = torch.empty(b, res, res, c, device=dev, dtype=torch.float32)
+    tcconv.conv_gemm(x, _static_weights(blk.conv0, c), c, tcconv.TAPS_3X3, (res, res), t, out_mode=2, split=True,
+                     bias=_bias(blk.conv0, c), act=3, alpha=0.2, gain=float(blk.conv0.act_gain))
+    ft = tcconv.fir_act_nhwc(t, f, None, None, 2, (res + 1, res + 1), pad0=(2, 2), fir_gain=1.0, act=1, act_gain=1.0)
+    # conv1: FIR (above) then 3x3 stride 2 (:108-111), bias + lrelu with gain sqrt(2) * sqrt(0.5), plus the skip branch (:524-528)
+    xn = _alloc(2, b, h2, h2, cout, cout, dev)
+    tcconv.conv_gemm(ft, _static_weights(blk.conv1, c), cout, _TAPS_3X3_VALID, (h2, h2), xn[0], out_lo=xn[1], out_mode=1, split=True,
+                     bias=_bias(blk.conv1, cout), act=3, alpha=0.2, gain=float(blk.conv1.act_gain * np.sqrt(0.5)), stride=2, residual=y)
+    return xn
+
+
+def encoder_forward(enc, img):
+    """Encoder.forward (triplane_cond.py:168-196) on the tensor-core path -> the projector's [B, out_dim] output."""
+    b = img.shape[0]
+    xin = tcconv.to_nhwc_f16(img.float(), c_padded=tcconv.pad_to(img.shape[1], 64), planes=2)
+    x = None
+    for res in enc.block_resolutions:
+        x = _encoder_block(getattr(enc, f'b{res}'), x, xin, b, res)
+    feat = (x[0].float() + x[1].float()).permute(0, 3, 1, 2)                     # [B, 512, 4, 4]
+    return torch.nn.functional.conv2d(feat, enc.projector.weight * enc.projector.scale)[:, :, 0, 0]
+
+
+# ----------------------------------------------------------------------------------------------
 # whole-generator fast path
 # ----------------------------------------------------------------------------------------------
 def _sr_supported(sr, ws, noise_mode, feat_res):

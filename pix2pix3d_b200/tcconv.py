@@ -29,6 +29,7 @@ class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
         ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
         ('acc_scale', ctypes.c_float),
         ('up_prev', ctypes.c_void_p), ('up_filter', ctypes.c_void_p), ('round16', ctypes.c_int32), ('out_nchw', ctypes.c_int32),
+        ('stride', ctypes.c_int32), ('reserved0', ctypes.c_int32), ('residual', ctypes.c_void_p),
         ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64),
     ]
 
@@ -153,7 +154,7 @@ def _splitk_scratch(device):
 
 def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
               noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True,
-              up_prev=None, up_filter=None, round16=False, out_nchw=False):
+              up_prev=None, up_filter=None, round16=False, out_nchw=False, stride=1, residual=None):
     """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;
     out: NHWC tensor [B,oH,oW,Cs] (fp16 or fp32); out_map = (sy, oy, sx, ox)."""
     xp, b, h, wd, c = x.shape
@@ -188,6 +189,10 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
     for t in (bias, noise, dscale):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     a.act, a.alpha, a.gain, a.clamp, a.acc_scale = act, alpha, gain, clamp, acc_scale
+    a.stride = stride
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.is_contiguous() and tuple(residual.shape) == (b, grid_hw[0], grid_hw[1], cout)
+        a.residual = residual.data_ptr()
     if up_prev is not None:      # fused ToRGB tail: out = upsample2d(up_prev, up_filter) + result
         assert up_prev.dtype == torch.float32 and up_prev.is_contiguous() and up_filter.dtype == torch.float32 and up_filter.numel() == 16
         a.up_prev, a.up_filter = up_prev.data_ptr(), up_filter.contiguous().data_ptr()
@@ -237,14 +242,24 @@ def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SC
 
 
 def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):
-    """x [B,inH,inW,C] fp32/fp16 NHWC -> [out_planes,B,outH,outW,C] fp16."""
-    b, ih, iw, c = x.shape
+    """x [B,inH,inW,C] fp32/fp16 NHWC, or a split fp16 pair [2,B,inH,inW,C] -> [out_planes,B,outH,outW,C] fp16."""
+    split_in = x.ndim == 5
+    if split_in:
+        assert x.shape[0] == 2 and x.dtype == torch.float16 and x.is_contiguous()
+        _, b, ih, iw, c = x.shape
+    else:
+        b, ih, iw, c = x.shape
     oh, ow = out_hw
     y = torch.empty(out_planes, b, oh, ow, c, device=x.device, dtype=torch.float16)
     with torch.cuda.device(x.device):
-        st = _lib.lib().p3d_fir_act_nhwc(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias),
-                                         _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha,
-                                         act_gain, clamp, _lib.stream_ptr())
+        if split_in:
+            st = _lib.lib().p3d_fir_act_nhwc_split(_lib.ptr(x), _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b,
+                                                   ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha, act_gain, clamp,
+                                                   _lib.stream_ptr())
+        else:
+            st = _lib.lib().p3d_fir_act_nhwc(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias),
+                                             _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha,
+                                             act_gain, clamp, _lib.stream_ptr())
     _lib.check(st, 'p3d_fir_act_nhwc')
     _lib.bump()
     return y

@@ -101,10 +101,16 @@ class Encoder(torch.nn.Module):
 
     def forward(self, inputs, **block_kwargs):
         img = inputs['img'] if isinstance(inputs, dict) else inputs
-        x = None
-        for res in self.block_resolutions:
-            x, img = getattr(self, f'b{res}')(x, img, **block_kwargs)
-        out = self.projector(x)[:, :, 0, 0]
+        out = None
+        if img.device.type == 'cuda' and not block_kwargs:
+            from .. import engine
+            if engine.encoder_supported(self, img):
+                out = engine.encoder_forward(self, img)
+        if out is None:
+            x = None
+            for res in self.block_resolutions:
+                x, img = getattr(self, f'b{res}')(x, img, **block_kwargs)
+            out = self.projector(x)[:, :, 0, 0]
         if self.output_mode == 'W+':
             out = out.reshape(out.shape[0], self.num_ws, self.w_dim)
         elif self.output_mode == 'W':

@@ -194,3 +194,37 @@ def test_cached_backbone_multi_view_rendering():
         torch.manual_seed(4)
         again = G.synthesis(ws, c2, use_cached_backbone=True, **kw)
     assert rel_err(again['image'].cpu().numpy(), fresh['image'].cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize('res,in_ch', [(64, 6), (256, 1)])
+def test_encoder_engine_matches_generic_path(res, in_ch):
+    """Label-map Encoder (triplane_cond.py:66-196) on the tensor-core path -- static-weight 3x3 convs, FIR + stride-2 convs
+    (TMA element strides), resnet skip added in the epilogue -- against the op-by-op fp32 formulation."""
+    from pix2pix3d_b200 import _lib, engine
+    from pix2pix3d_b200.training.triplane_cond import Encoder
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(31)
+    enc = Encoder(img_resolution=res, img_channels=in_ch, model_kwargs={'num_ws': 7, 'w_dim': 512, 'output_mode': 'W+'}).cuda()
+    enc.requires_grad_(False)
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if n.endswith('.bias'):
+                p.copy_(torch.randn_like(p) * 0.2)
+    if in_ch > 1:
+        lab = torch.randint(0, in_ch, (3, res, res), device='cuda')
+        img = torch.nn.functional.one_hot(lab, in_ch).permute(0, 3, 1, 2).float()
+    else:
+        img = (torch.rand(3, 1, res, res, device='cuda') < 0.1).float() * 2 - 1
+    n0 = _lib.launch_count
+    with torch.no_grad():
+        fast = enc(img)['ws']
+    assert _lib.launch_count - n0 > 5 * len(enc.block_resolutions)
+    engine.enabled = False
+    try:
+        with torch.no_grad():
+            ref = enc(img)['ws']
+    finally:
+        engine.enabled = True
+    assert fast.shape == ref.shape == (3, 7, 512)
+    assert rel_err(fast.cpu().numpy(), ref.cpu().numpy()) < 2e-4

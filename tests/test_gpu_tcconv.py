@@ -299,3 +299,42 @@ def test_cta_pair_kernel_256_channel_tiles(split):
     ref = F.conv2d(xr.cpu(), wr.cpu(), padding=1) + noise.double().cpu() + bias.double().cpu()[None, :, None, None]
     ref = (F.leaky_relu(ref, 0.2) * np.sqrt(2)).clamp(-4, 4)
     assert rel_err(got.permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < (2e-5 if split else 1e-3)
+
+
+def test_strided_conv_and_residual_epilogue():
+    """down=2 layers: out(y, x) = sum_d w[d] * in(2y + dy, 2x + dx) through TMA element strides, plus the resnet skip tensor
+    added after the activation; small (split-K-sized) and large (persistent / pair kernel) shapes."""
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(14)
+    for b, c, hw, cout in ((2, 64, 17, 64), (2, 128, 129, 128), (1, 64, 257, 256)):
+        x = torch.randn(b, c, hw, hw, device='cuda')
+        wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+        bias = torch.randn(cout, device='cuda')
+        ho = (hw - 3) // 2 + 1
+        res = torch.randn(b, ho, ho, cout, device='cuda')
+        xn = tcconv.to_nhwc_f16(x, planes=2)
+        wk = _weights_kmajor(wt, planes=2, scale=tcconv.WEIGHT_SCALE)
+        hi = torch.zeros(b, ho, ho, cout, device='cuda', dtype=torch.float16)
+        lo = torch.zeros_like(hi)
+        taps = [(ky, kx, ky * 3 + kx) for ky in range(3) for kx in range(3)]
+        tcconv.conv_gemm(xn, wk, cout, taps, (ho, ho), hi, out_lo=lo, out_mode=1, split=True, bias=bias, act=3, alpha=0.2,
+                         gain=1.0, stride=2, residual=res)
+        ref = F.leaky_relu(F.conv2d(x.double().cpu(), wt.double().cpu(), stride=2) + bias.double().cpu()[None, :, None, None], 0.2)
+        ref = ref + res.double().cpu().permute(0, 3, 1, 2)
+        got = (hi.float() + lo.float()).permute(0, 3, 1, 2)
+        assert rel_err(got.cpu().numpy(), ref.numpy()) < 2e-5, (b, c, hw, cout)
+        # 1x1 tap at the odd positions (the skip branch)
+        w1 = torch.randn(cout, c, 1, 1, device='cuda') / np.sqrt(c)
+        wk1 = _weights_kmajor(w1, planes=2, scale=tcconv.WEIGHT_SCALE)
+        y = torch.empty(b, ho, ho, cout, device='cuda')
+        tcconv.conv_gemm(xn, wk1, cout, [(1, 1, 0)], (ho, ho), y, out_mode=2, split=True, act=1, gain=0.5, stride=2)
+        ref1 = F.conv2d(x.double().cpu()[:, :, 1::2, 1::2][:, :, :ho, :ho], w1.double().cpu()) * 0.5
+        assert rel_err(y.permute(0, 3, 1, 2).cpu().numpy(), ref1.numpy()) < 2e-5
+    # split (hi/lo) input FIR
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    xs = torch.randn(2, 64, 33, 33, device='cuda')
+    sp = tcconv.to_nhwc_f16(xs, planes=2)
+    out = tcconv.fir_act_nhwc(sp, f, None, None, 2, (34, 34), pad0=(2, 2), fir_gain=1.0, act=1, act_gain=1.0)
+    refd = upfirdn2d.upfirdn2d(xs, f, padding=[2, 2, 2, 2])
+    assert rel_err((out[0].float() + out[1].float()).permute(0, 3, 1, 2).cpu().numpy(), refd.cpu().numpy()) < 2e-6
