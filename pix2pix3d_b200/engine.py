@@ -474,8 +474,13 @@ def encoder_forward(enc, img):
     x = None
     for res in enc.block_resolutions:
         x = _encoder_block(getattr(enc, f'b{res}'), x, xin, b, res)
-    feat = (x[0].float() + x[1].float()).permute(0, 3, 1, 2)                     # [B, 512, 4, 4]
-    return torch.nn.functional.conv2d(feat, enc.projector.weight * enc.projector.scale)[:, :, 0, 0]
+    # projector: a 4x4 "valid" convolution of the 4x4 map = one GEMM over (y, x, c); cuDNN picks an FFT algorithm for this
+    # shape (3.7 ms), a plain fp32 matmul against the NHWC-ordered weight streams the 117 MB of weights once
+    proj = enc.projector
+    wp = _cached(proj, 'proj_nhwc', [proj.weight],
+                 lambda: (proj.weight.detach().float().permute(0, 2, 3, 1).reshape(proj.weight.shape[0], -1) * proj.scale).contiguous())
+    feat = (x[0].float() + x[1].float()).reshape(b, -1)                          # [B, 4*4*512] in (y, x, c) order
+    return feat @ wp.t()
 
 
 # ----------------------------------------------------------------------------------------------
