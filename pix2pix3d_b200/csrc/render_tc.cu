@@ -35,12 +35,21 @@ struct PackTcArgs {
     int n_nets;
 };
 
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+// softplus(x) / ln 2 for t = x * log2(e): max(t, 0) + log2(1 + 2^-|t|). The decoder image packed below carries log2(e) in the
+// layer-1 weights and biases and ln 2 in the layer-2 weights, so the kernel never multiplies by either.
+__device__ __forceinline__ float softplus2(float t) {
+    return fmaxf(t, 0.f) + lg2_ftz(1.f + ex2_ftz(-fabsf(t)));
+}
+
 __global__ void pack_decoder_tc_kernel(PackTcArgs a, uint8_t* __restrict__ out) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     // layer 1: row n = net*64 + j, k = 0..31
     for (int i = tid; i < 128 * 32; i += nth) {
         int n = i / 32, k = i % 32, net = n / 64, j = n % 64;
-        float v = net < a.n_nets ? __fmul_rn(a.w1[net][j * 32 + k], a.w1g[net]) * (1.f / 3.f) : 0.f;   // x = mean of 3 planes
+        // x = mean of 3 planes -> 1/3; hidden pre-activations are produced in log2 units (softplus2 below) -> log2(e)
+        float v = net < a.n_nets ? __fmul_rn(a.w1[net][j * 32 + k], a.w1g[net]) * (kLog2e / 3.f) : 0.f;
         __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
         *reinterpret_cast<__half*>(out + kTcW1A + sw128(n, k * 2)) = hi;
         *reinterpret_cast<__half*>(out + kTcW1A + sw128(n, 64 + k * 2)) = hi;
@@ -52,8 +61,9 @@ __global__ void pack_decoder_tc_kernel(PackTcArgs a, uint8_t* __restrict__ out) 
         int net = i / 4096, r = (i / 64) % 64, k = i % 64;
         float v = 0.f;
         if (net < a.n_nets) {
-            if (r < 32) v = __fmul_rn(a.w2[net][(r + 1) * 64 + k], a.w2g[net]);
-            else if (r == 32) v = __fmul_rn(a.w2[net][k], a.w2g[net]);
+            // hidden activations are softplus / ln 2 (softplus2): ln 2 goes into the layer-2 weights
+            if (r < 32) v = __fmul_rn(a.w2[net][(r + 1) * 64 + k], a.w2g[net]) * kLn2;
+            else if (r == 32) v = __fmul_rn(a.w2[net][k], a.w2g[net]) * kLn2;
         }
         __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
         *reinterpret_cast<__half*>(out + kTcW2H + net * 8192 + sw128(r, k * 2)) = hi;
@@ -62,10 +72,10 @@ __global__ void pack_decoder_tc_kernel(PackTcArgs a, uint8_t* __restrict__ out) 
     float* tail = reinterpret_cast<float*>(out + kTcTail);
     for (int i = tid; i < kTcTailFloats; i += nth) {
         float v = 0.f;
-        if (i < 128) { int net = i / 64, j = i % 64; if (net < a.n_nets) v = a.b1g[net] != 1.f ? __fmul_rn(a.b1[net][j], a.b1g[net]) : a.b1[net][j]; }
+        if (i < 128) { int net = i / 64, j = i % 64; if (net < a.n_nets) v = (a.b1g[net] != 1.f ? __fmul_rn(a.b1[net][j], a.b1g[net]) : a.b1[net][j]) * kLog2e; }
         else if (i < 192) { int net = (i - 128) / 32, o = (i - 128) % 32; if (net < a.n_nets) v = a.b2g[net] != 1.f ? __fmul_rn(a.b2[net][o + 1], a.b2g[net]) : a.b2[net][o + 1]; }
         else if (i < 194) { int net = i - 192; if (net < a.n_nets) v = a.b2g[net] != 1.f ? __fmul_rn(a.b2[net][0], a.b2g[net]) : a.b2[net][0]; }
-        else if (i >= 196) { int net = (i - 196) / 64, j = (i - 196) % 64; if (net < a.n_nets) v = __fmul_rn(a.w2[net][j], a.w2g[net]); }
+        else if (i >= 196) { int net = (i - 196) / 64, j = (i - 196) % 64; if (net < a.n_nets) v = __fmul_rn(a.w2[net][j], a.w2g[net]) * kLn2; }
         tail[i] = v;
     }
 }
@@ -296,8 +306,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 const int jj = half * 32 + j;
-                acc0 = fmaf(w2s[sig * 64 + jj], softplus_f(__uint_as_float(v[j]) + b1[sig * 64 + jj]), acc0);
-                acc1 = fmaf(w2s[sig * 64 + jj + 1], softplus_f(__uint_as_float(v[j + 1]) + b1[sig * 64 + jj + 1]), acc1);
+                acc0 = fmaf(w2s[sig * 64 + jj], softplus2(__uint_as_float(v[j]) + b1[sig * 64 + jj]), acc0);
+                acc1 = fmaf(w2s[sig * 64 + jj + 1], softplus2(__uint_as_float(v[j + 1]) + b1[sig * 64 + jj + 1]), acc1);
             }
         }
         return acc0 + acc1;
@@ -480,8 +490,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
 #pragma unroll
                     for (int j = 0; j < 32; j += 2) {
                         const int jj = net * 64 + half * 32 + j;
-                        const float h0 = softplus_f(__uint_as_float(vv[j]) + b1[jj]);
-                        const float h1 = softplus_f(__uint_as_float(vv[j + 1]) + b1[jj + 1]);
+                        const float h0 = softplus2(__uint_as_float(vv[j]) + b1[jj]);
+                        const float h1 = softplus2(__uint_as_float(vv[j + 1]) + b1[jj + 1]);
                         const __half2 hh = __floats2half2_rn(h0, h1);
                         const float2 back = __half22float2(hh);
                         const __half2 ll = __floats2half2_rn(h0 - back.x, h1 - back.y);
@@ -506,15 +516,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
                     c = ((smask >> i) & 1u) ? sigmoid_clamp_f(c) : c;
                     acc[i] = v ? c * coef : 0.f;
                 }
-                for (int o = g >> 1; o > 0; o >>= 1) {
+                float* dst = part + ((size_t)(rr < RT ? rr : 0) * (L.NGc + L.NGf) + slot) * P.cout + net * kOut;
+                if (g == 16) {
+                    // transposed butterfly over the 16 lanes of a ray segment: every step halves the channels a lane keeps
+                    // (30 shuffles instead of 128); lane ends with the two channels [base, base + 2)
+                    int base = 0;
+#define P3D_RED_STEP(O, N)                                                                         \
+    {                                                                                              \
+        const bool up = (lane & O) != 0;                                                           \
+        _Pragma("unroll") for (int i = 0; i < N / 2; ++i) {                                        \
+            const float send = up ? acc[i] : acc[i + N / 2];                                       \
+            const float keep = up ? acc[i + N / 2] : acc[i];                                       \
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);                                 \
+        }                                                                                          \
+        base += up ? N / 2 : 0;                                                                    \
+    }
+                    P3D_RED_STEP(8, 32) P3D_RED_STEP(4, 16) P3D_RED_STEP(2, 8) P3D_RED_STEP(1, 4)
+#undef P3D_RED_STEP
+                    if (rr < RT) *reinterpret_cast<float2*>(dst + base) = make_float2(acc[0], acc[1]);
+                } else {
+                    for (int o = g >> 1; o > 0; o >>= 1) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-                }
-                if ((lane & (g - 1)) == 0 && rr < RT) {
-                    float* dst = part + ((size_t)rr * (L.NGc + L.NGf) + slot) * P.cout + net * kOut;
+                        for (int i = 0; i < 32; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+                    }
+                    if ((lane & (g - 1)) == 0 && rr < RT) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                    }
                 }
             }
         }
