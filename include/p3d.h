@@ -125,6 +125,15 @@ int p3d_run_model(const float* planes_nhwc, const float* coords, const float* de
                   int B, int M, int H, int W, float coord_scale,
                   float* out_rgb, float* out_sigma, p3d_stream_t stream);
 
+/* The same query with the decoder MLP on tcgen05 (pix2pix3d_b200/csrc/query_tc.cu): the call behind
+ * TriPlane*Generator.sample / sample_mixed (triplane_cond.py:1063-1074), e.g. the 512^3 sigma grid of
+ * applications/extract_mesh.py:60-81. decoder_tc_packed is the image of p3d_pack_decoder_tc; plane_strides as in
+ * p3d_render_args_t (NULL or all zero = dense [B,3,H,W,32]). */
+int p3d_run_model_tc(const float* planes_nhwc, const int64_t plane_strides[3], const float* coords,
+                     const void* decoder_tc_packed, int n_nets, int sigma_net, const uint32_t sigmoid_mask[2],
+                     int B, int64_t M, int H, int W, float coord_scale,
+                     float* out_rgb, float* out_sigma, p3d_stream_t stream);
+
 /* sample_from_planes alone -- renderer.py:55-65: features [B,3,M,32] (the reference's output layout). */
 int p3d_sample_from_planes(const float* planes_nhwc, const float* coords, int B, int M, int H, int W,
                            float coord_scale, float* out_features, p3d_stream_t stream);

@@ -206,9 +206,21 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
     return feat, depth, wsum
 
 
-def run_model(planes_nhwc, dec, coords, box_warp):
-    """Fused sample_from_planes + decoder: coords [B,M,3] -> (rgb [B,M,C], sigma [B,M,1])."""
-    B, _, H, W, _ = planes_nhwc.shape
+def run_model(planes_nhwc, dec, coords, box_warp, impl=None):
+    """Fused sample_from_planes + decoder: coords [B,M,3] -> (rgb [B,M,C], sigma [B,M,1]).
+
+    `impl`: 'auto' / 'tc' run the tensor-core query (p3d_run_model_tc), 'simt' the CUDA-core kernel."""
+    B, _, H, W, C = planes_nhwc.shape
+    assert C == 32 and planes_nhwc.dtype == torch.float32
+    impl = impl or render_impl
+    use_tc = impl in ('auto', 'tc') and dec.packed_tc is not None
+    strides = None
+    if not planes_nhwc.is_contiguous():
+        st_img, st_plane, st_row, st_pix, st_ch = planes_nhwc.stride()
+        if use_tc and st_ch == 1 and st_row == W * st_pix and st_pix >= 32 and st_plane > 0 and st_img > 0:
+            strides = (ctypes.c_int64 * 3)(st_img, st_plane, st_pix)       # read in place (see render_fwd)
+        else:
+            planes_nhwc = planes_nhwc.contiguous()
     c = _f32c(coords)
     M = c.shape[1]
     dev = planes_nhwc.device
@@ -216,10 +228,16 @@ def run_model(planes_nhwc, dec, coords, box_warp):
     sigma = torch.empty(B, M, 1, device=dev, dtype=torch.float32)
     masks = (ctypes.c_uint32 * 2)(dec.masks[0], dec.masks[1])
     with torch.cuda.device(dev):
-        st = _lib.lib().p3d_run_model(_lib.ptr(planes_nhwc), _lib.ptr(c), _lib.ptr(dec.packed), dec.n_nets, dec.sigma_net,
-                                      masks, B, M, H, W, 2.0 / float(box_warp), _lib.ptr(rgb), _lib.ptr(sigma),
-                                      _lib.stream_ptr())
-    _lib.check(st, 'p3d_run_model')
+        if use_tc:
+            st = _lib.lib().p3d_run_model_tc(_lib.ptr(planes_nhwc), strides, _lib.ptr(c), _lib.ptr(dec.packed_tc), dec.n_nets,
+                                             dec.sigma_net, masks, B, M, H, W, 2.0 / float(box_warp), _lib.ptr(rgb),
+                                             _lib.ptr(sigma), _lib.stream_ptr())
+            _lib.check(st, 'p3d_run_model_tc')
+        else:
+            st = _lib.lib().p3d_run_model(_lib.ptr(planes_nhwc), _lib.ptr(c), _lib.ptr(dec.packed), dec.n_nets, dec.sigma_net,
+                                          masks, B, M, H, W, 2.0 / float(box_warp), _lib.ptr(rgb), _lib.ptr(sigma),
+                                          _lib.stream_ptr())
+            _lib.check(st, 'p3d_run_model')
     _lib.bump()
     return rgb, sigma
 
