@@ -172,6 +172,16 @@ int p3d_upfirdn2d(const void* x, const float* f, void* y, int dtype,
                   int fw, int fh, int upx, int upy, int downx, int downy,
                   int padx0, int pady0, int flip, float gain, p3d_stream_t stream);
 
+/* F.interpolate(x, size, mode='bilinear', align_corners=False, antialias=...) -- the resize of
+ * Superresolution*.forward (training/superresolution.py:315-319) and `filtered_resizing`
+ * (training/dual_discriminator.py:86-102): separable triangle filter of support max(in/out, 1) with per-output
+ * renormalisation at the borders (antialias != 0), or the two clamped taps of plain bilinear interpolation.
+ * x [planes, in_h, in_w] -> y [planes, out_h, out_w], dense, dtype P3D_F32 / P3D_F16 / P3D_F64.
+ * transposed != 0 applies the adjoint (the op's backward): x is then [planes, out_h, out_w] (gradient w.r.t. the
+ * output) and y [planes, in_h, in_w]; higher orders alternate between the two. */
+int p3d_resize_bilinear(const void* x, void* y, int dtype, int64_t planes, int in_h, int in_w, int out_h, int out_w,
+                        int antialias, int transposed, p3d_stream_t stream);
+
 /* Fused epilogue of an up=2 modulated conv (networks_stylegan2.py:324-331 + conv2d_resample.py:128):
  * y = clamp(lrelu(upfirdn2d(x, f, pad, gain=up^2) [* dcoef[n,c]] + noise[h,w]*noise_strength + b[c]) * act_gain).
  * One read of x, one write of y instead of three passes. Any of dcoef/noise/b may be NULL. */

@@ -93,27 +93,49 @@ def synthesis_network(ws, sd, prefix, img_resolution, noise_mode='const', fused_
     return img
 
 
-def bilinear_antialias_resize(x, size):
-    """F.interpolate(mode='bilinear', align_corners=False, antialias=True) for down- or up-scaling by a common
-    factor (superresolution.py:315-319): separable triangle filter of support max(scale,1)."""
-    x = np.asarray(x, f32)
-
-    def weights(in_size, out_size):
-        scale = in_size / out_size
-        support = max(scale, 1.0)
-        m = np.zeros((out_size, in_size), np.float64)
-        for o in range(out_size):
+def resize_matrix(in_size, out_size, antialias=True):
+    """Dense [out, in] matrix of one axis of F.interpolate(mode='bilinear', align_corners=False, antialias=...):
+    ATen `_compute_indices_min_size_weights_aa` (triangle filter, support max(scale, 1), window clipped to the image and
+    renormalised) or, without anti-aliasing, `area_pixel_compute_source_index` + `guard_index_and_lambda` (two clamped taps)."""
+    scale = in_size / out_size
+    m = np.zeros((out_size, in_size), np.float64)
+    for o in range(out_size):
+        if antialias:
+            support = max(scale, 1.0)
             center = scale * (o + 0.5)
             lo = max(int(center - support + 0.5), 0)
             hi = min(int(center + support + 0.5), in_size)
             idx = np.arange(lo, hi)
             wgt = np.clip(1 - np.abs((idx - center + 0.5) / support), 0, None)
             m[o, lo:hi] = wgt / wgt.sum()
-        return m.astype(f32)
+        else:
+            src = max(scale * (o + 0.5) - 0.5, 0.0)
+            i0 = min(int(src), in_size - 1)
+            lam = min(max(src - i0, 0.0), 1.0)
+            m[o, i0] += 1 - lam
+            m[o, min(i0 + 1, in_size - 1)] += lam
+    return m.astype(f32)
 
-    wy = weights(x.shape[2], size[0])
-    wx = weights(x.shape[3], size[1])
+
+def bilinear_resize(x, size, antialias=True):
+    """F.interpolate(x, size, mode='bilinear', align_corners=False, antialias=...) on [N,C,H,W]
+    (superresolution.py:315-319, dual_discriminator.py:86-102)."""
+    x = np.asarray(x, f32)
+    wy = resize_matrix(x.shape[2], size[0], antialias)
+    wx = resize_matrix(x.shape[3], size[1], antialias)
     return np.einsum('oh,nchw,pw->ncop', wy, x, wx, optimize=True).astype(f32)
+
+
+def bilinear_resize_adjoint(g, in_size, antialias=True):
+    """Gradient of `bilinear_resize` w.r.t. its input: g [N,C,out_h,out_w] -> [N,C,in_h,in_w]."""
+    g = np.asarray(g, f32)
+    wy = resize_matrix(in_size[0], g.shape[2], antialias)
+    wx = resize_matrix(in_size[1], g.shape[3], antialias)
+    return np.einsum('oh,ncop,pw->nchw', wy, g, wx, optimize=True).astype(f32)
+
+
+def bilinear_antialias_resize(x, size):
+    return bilinear_resize(x, size, antialias=True)
 
 
 SR_KINDS = {  # class name -> (input_resolution, block0 upsamples?, resize only if smaller?)

@@ -9,14 +9,17 @@ import torch
 
 from ..torch_utils import persistence
 from ..torch_utils.ops import upfirdn2d
+from ..torch_utils.ops.resize import interpolate_bilinear
 from .networks_stylegan2 import DiscriminatorBlock, DiscriminatorEpilogue, MappingNetwork
 
 
 def filtered_resizing(image_orig_tensor, size, f, filter_mode='antialiased'):
     """Resize the raw render to the discriminator resolution (:86-102)."""
-    interp = torch.nn.functional.interpolate
     if filter_mode == 'antialiased':
-        return interp(image_orig_tensor, size=(size, size), mode='bilinear', align_corners=False, antialias=True)
+        return interpolate_bilinear(image_orig_tensor, (size, size), antialias=True)
+
+    def interp(x, size, mode='bilinear', align_corners=False, antialias=False):
+        return interpolate_bilinear(x, size, antialias=antialias)
     if filter_mode == 'classic':
         y = upfirdn2d.upsample2d(image_orig_tensor, f, up=2)
         y = interp(y, size=(size * 2 + 2, size * 2 + 2), mode='bilinear', align_corners=False)

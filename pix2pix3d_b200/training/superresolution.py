@@ -8,6 +8,7 @@ import torch
 
 from ..torch_utils import persistence
 from ..torch_utils.ops import upfirdn2d
+from ..torch_utils.ops.resize import interpolate_bilinear
 from .networks_stylegan2 import SynthesisBlock, _block_forward, _block_setup
 
 
@@ -61,8 +62,8 @@ class _TwoBlockSR(torch.nn.Module):
         need = (x.shape[-1] < self.input_resolution) if self.RESIZE_ONLY_IF_SMALLER else (x.shape[-1] != self.input_resolution)
         if need:
             size = (self.input_resolution, self.input_resolution)
-            x = torch.nn.functional.interpolate(x, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)
-            rgb = torch.nn.functional.interpolate(rgb, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)
+            x = interpolate_bilinear(x, size, antialias=self.sr_antialias)
+            rgb = interpolate_bilinear(rgb, size, antialias=self.sr_antialias)
         if ws.device.type == 'cuda':
             from .. import engine, tcconv
             noise_mode = block_kwargs.get('noise_mode', 'random')
