@@ -182,6 +182,20 @@ int p3d_upfirdn2d(const void* x, const float* f, void* y, int dtype,
 int p3d_resize_bilinear(const void* x, void* y, int dtype, int64_t planes, int in_h, int in_w, int out_h, int out_w,
                         int antialias, int transposed, p3d_stream_t stream);
 
+/* cross_entropy2d -- training/loss_utils.py:4-18 (after its optional label resize), called by training/loss.py:611-616:
+ * logits [N,C,H,W] fp32 (read in place, no [N*H*W,C] copy), target [N,H,W] int64, class_weight [C] fp32 or NULL.
+ * loss[0] = sum_i w[t_i] (logsumexp(x_i) - x_i[t_i]) / sum_i w[t_i] over the pixels with t_i != ignore_index
+ * (F.cross_entropy, reduction='mean'); sum_w[0] = the denominator, kept for the backward. A target outside [0,C) makes
+ * the loss NaN. workspace: P3D_CE_WORKSPACE_DOUBLES doubles; partial sums are combined in a fixed order (deterministic). */
+#define P3D_CE_WORKSPACE_DOUBLES 2048
+int p3d_cross_entropy2d_fwd(const float* logits, const int64_t* target, const float* class_weight, int N, int C,
+                            int64_t HW, int64_t ignore_index, float* loss, float* sum_w, double* workspace,
+                            p3d_stream_t stream);
+/* grad_logits [N,C,H,W] = grad_loss[0] * w[t] * (softmax(x) - onehot(t)) / sum_w[0]; zero at ignored pixels. */
+int p3d_cross_entropy2d_bwd(const float* logits, const int64_t* target, const float* class_weight,
+                            const float* grad_loss, const float* sum_w, int N, int C, int64_t HW,
+                            int64_t ignore_index, float* grad_logits, p3d_stream_t stream);
+
 /* Fused epilogue of an up=2 modulated conv (networks_stylegan2.py:324-331 + conv2d_resample.py:128):
  * y = clamp(lrelu(upfirdn2d(x, f, pad, gain=up^2) [* dcoef[n,c]] + noise[h,w]*noise_strength + b[c]) * act_gain).
  * One read of x, one write of y instead of three passes. Any of dcoef/noise/b may be NULL. */

@@ -405,3 +405,27 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=_S
     x = upfirdn2d(x, fu, up=up, padding=[px0, px1, py0, py1], gain=up ** 2, flip_filter=flip_filter)
     x = bias_act(x, act='lrelu', alpha=slope, gain=gain, clamp=clamp)
     return upfirdn2d(x, fd, down=down, flip_filter=flip_filter)
+
+
+# ---------------------------------------------------------------------------------------------
+# training/loss_utils.py:4-18 (cross_entropy2d, same-size case) = F.cross_entropy(reduction='mean') per pixel
+# ---------------------------------------------------------------------------------------------
+def cross_entropy2d(logits, target, weight=None, ignore_index=-100):
+    """logits [N,C,H,W], target [N,H,W] int -> (loss, grad_logits). loss = sum_i w[t_i] (lse_i - x_i[t_i]) / sum_i w[t_i]
+    over the pixels with t_i != ignore_index; grad = w[t] (softmax - onehot) / sum w."""
+    x = np.asarray(logits, np.float64)
+    t = np.asarray(target, np.int64)
+    n, c, h, w = x.shape
+    m = x.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(x - m).sum(axis=1))
+    valid = t != ignore_index
+    tc = np.where(valid, t, 0)
+    xt = np.take_along_axis(x, tc[:, None], axis=1)[:, 0]
+    wt = np.ones_like(lse) if weight is None else np.asarray(weight, np.float64)[tc]
+    wt = wt * valid
+    denom = wt.sum()
+    loss = (wt * (lse - xt)).sum() / denom
+    sm = np.exp(x - lse[:, None])
+    onehot = (np.arange(c)[None, :, None, None] == tc[:, None]).astype(np.float64)
+    grad = wt[:, None] * (sm - onehot) / denom
+    return np.float32(loss), grad.astype(np.float32)
