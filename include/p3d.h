@@ -128,7 +128,8 @@ int p3d_run_model(const float* planes_nhwc, const float* coords, const float* de
 /* The same query with the decoder MLP on tcgen05 (pix2pix3d_b200/csrc/query_tc.cu): the call behind
  * TriPlane*Generator.sample / sample_mixed (triplane_cond.py:1063-1074), e.g. the 512^3 sigma grid of
  * applications/extract_mesh.py:60-81. decoder_tc_packed is the image of p3d_pack_decoder_tc; plane_strides as in
- * p3d_render_args_t (NULL or all zero = dense [B,3,H,W,32]). */
+ * p3d_render_args_t (NULL or all zero = dense [B,3,H,W,32]). out_rgb may be NULL: densities only (what extract_mesh
+ * keeps), which skips layer 2 of the decoder and the colour writes. */
 int p3d_run_model_tc(const float* planes_nhwc, const int64_t plane_strides[3], const float* coords,
                      const void* decoder_tc_packed, int n_nets, int sigma_net, const uint32_t sigmoid_mask[2],
                      int B, int64_t M, int H, int W, float coord_scale,

@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(kQThreads, 1) run_model_tc_kernel(const TcQuer
     const uint32_t tmem_row = tmem_grp + ((uint32_t)(q * 32) << 16);
     uint32_t bar_phase = 0;
     const uint32_t w1a = tc::smem_u32(smem + kTcW1A), w1b = tc::smem_u32(smem + kTcW1B);
-    const uint32_t idesc_l1 = n_nets == 2 ? tc::umma_idesc_f16(128, 128, 0) : tc::umma_idesc_f16(128, 64, 0);
+    const bool colours = P.out_rgb != nullptr;      // sigma-only query (mesh extraction): layer 1 of the sigma net + one dot
+    const uint32_t idesc_l1 = (colours && n_nets == 2) ? tc::umma_idesc_f16(128, 128, 0) : tc::umma_idesc_f16(128, 64, 0);
+    const int l1_row0 = colours ? 0 : sig * 64;     // first W1 row (= hidden unit) layer 1 computes
     const uint32_t idesc_n32 = tc::umma_idesc_f16(128, 32, 0);
     const uint32_t tile32 = tc::smem_u32(tile);
     const TcPlaneView pv{P.planes, P.H, P.W, P.img_stride, P.plane_stride, P.pix_stride};
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(kQThreads, 1) run_model_tc_kernel(const TcQuer
         if (m == 0) {
             // layer 1: D1[:, 0:64*n_nets) = [hi|lo] x [Whi|Whi]^T + [hi|lo] x [Wlo|0]^T
             const uint64_t da = tc::umma_desc_k128(tile32);
-            const uint64_t dba = tc::umma_desc_k128(w1a), dbb = tc::umma_desc_k128(w1b);
+            const uint64_t dba = tc::umma_desc_k128(w1a + l1_row0 * 128), dbb = tc::umma_desc_k128(w1b + l1_row0 * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc::umma_f16(tmem_grp, da + 2 * k, dba + 2 * k, idesc_l1, k != 0);
 #pragma unroll
@@ -103,8 +105,23 @@ __global__ void __launch_bounds__(kQThreads, 1) run_model_tc_kernel(const TcQuer
         }
         wait_mma();                    // the feature rows are free from here on (used as the colour staging rows below)
         float sg0 = b2s[sig], sg1 = 0.f;
+        if (!colours) {
+            // D1[:, 0:64) holds the sigma net's hidden pre-activations: sigma = w2[0] . softplus(h) + b2[0]
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t vv[32];
+                tc::tmem_ld_32x32(tmem_row + half * 32, vv);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int jj = sig * 64 + half * 32 + j;
+                    sg0 = fmaf(w2s[jj], softplus2(__uint_as_float(vv[j]) + b1[jj]), sg0);
+                    sg1 = fmaf(w2s[jj + 1], softplus2(__uint_as_float(vv[j + 1]) + b1[jj + 1]), sg1);
+                }
+            }
+        }
 #pragma unroll 1
-        for (int net = 0; net < n_nets; ++net) {
+        for (int net = 0; colours && net < n_nets; ++net) {
             // hidden: D1[:, net*64 .. +64) -> softplus -> packed fp16 hi (32 cols) | lo (32 cols), in place
             uint32_t ph[32], pl[32];
             const bool is_sig = net == sig;
@@ -189,12 +206,13 @@ __global__ void __launch_bounds__(kQThreads, 1) run_model_tc_kernel(const TcQuer
 using namespace p3d;
 
 // ImportanceRenderer.run_model on the tensor cores; same contract as p3d_run_model (render.cu) with the decoder image of
-// p3d_pack_decoder_tc and optional plane strides (elements; all zero = dense [B,3,H,W,32]).
+// p3d_pack_decoder_tc and optional plane strides (elements; all zero = dense [B,3,H,W,32]). out_rgb == NULL asks for the
+// densities only (applications/extract_mesh.py discards the colours): layer 2, the sigmoids and the colour writes are skipped.
 extern "C" int p3d_run_model_tc(const float* planes_nhwc, const int64_t plane_strides[3], const float* coords,
                                 const void* decoder_tc_packed, int n_nets, int sigma_net, const uint32_t sigmoid_mask[2],
                                 int B, int64_t M, int H, int W, float coord_scale, float* out_rgb, float* out_sigma,
                                 p3d_stream_t stream) {
-    if (!planes_nhwc || !coords || !decoder_tc_packed || !out_rgb || !out_sigma || !sigmoid_mask) return P3D_BAD_ARG;
+    if (!planes_nhwc || !coords || !decoder_tc_packed || !out_sigma || !sigmoid_mask) return P3D_BAD_ARG;
     if (B <= 0 || M <= 0 || H <= 0 || W <= 0 || n_nets < 1 || n_nets > 2 || sigma_net < 0 || sigma_net >= n_nets) return P3D_BAD_ARG;
     if (M > INT32_MAX) return P3D_UNSUPPORTED;
     TcQueryParams P;
@@ -211,7 +229,7 @@ extern "C" int p3d_run_model_tc(const float* planes_nhwc, const int64_t plane_st
         const int64_t is = dense ? 3 * psz : plane_strides[0], pls = dense ? psz : plane_strides[1], pxs = dense ? kC : plane_strides[2];
         if (is <= 0 || pls <= 0 || pxs < kC) return P3D_BAD_ARG;
         if ((((uintptr_t)planes_nhwc) & 15) != 0 || (is & 3) || (pls & 3) || (pxs & 3)) return P3D_UNSUPPORTED;
-        if ((((uintptr_t)out_rgb) & 15) != 0) return P3D_UNSUPPORTED;
+        if (out_rgb && (((uintptr_t)out_rgb) & 15) != 0) return P3D_UNSUPPORTED;
         const int64_t max_off = (int64_t)(B - 1) * is + 2 * pls + ((int64_t)H * W - 1) * pxs + kC;
         if (max_off >= ((int64_t)1 << 32)) return P3D_UNSUPPORTED;
         P.img_stride = (uint32_t)is; P.plane_stride = (uint32_t)pls; P.pix_stride = (uint32_t)pxs;

@@ -206,10 +206,11 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
     return feat, depth, wsum
 
 
-def run_model(planes_nhwc, dec, coords, box_warp, impl=None):
+def run_model(planes_nhwc, dec, coords, box_warp, impl=None, sigma_only=False):
     """Fused sample_from_planes + decoder: coords [B,M,3] -> (rgb [B,M,C], sigma [B,M,1]).
 
-    `impl`: 'auto' / 'tc' run the tensor-core query (p3d_run_model_tc), 'simt' the CUDA-core kernel."""
+    `impl`: 'auto' / 'tc' run the tensor-core query (p3d_run_model_tc), 'simt' the CUDA-core kernel.
+    `sigma_only` (tensor-core query): skip the colours and return (None, sigma) -- the mesh-extraction query."""
     B, _, H, W, C = planes_nhwc.shape
     assert C == 32 and planes_nhwc.dtype == torch.float32
     impl = impl or render_impl
@@ -224,7 +225,8 @@ def run_model(planes_nhwc, dec, coords, box_warp, impl=None):
     c = _f32c(coords)
     M = c.shape[1]
     dev = planes_nhwc.device
-    rgb = torch.empty(B, M, dec.out_channels, device=dev, dtype=torch.float32)
+    sigma_only = bool(sigma_only) and use_tc
+    rgb = None if sigma_only else torch.empty(B, M, dec.out_channels, device=dev, dtype=torch.float32)
     sigma = torch.empty(B, M, 1, device=dev, dtype=torch.float32)
     masks = (ctypes.c_uint32 * 2)(dec.masks[0], dec.masks[1])
     with torch.cuda.device(dev):

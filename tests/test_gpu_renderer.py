@@ -171,6 +171,9 @@ def test_run_model_tc_dense_grid_and_strided_planes():
     assert rel_err(sigma.cpu().numpy(), sigma2.cpu().numpy()) < TIGHT
     part, sp = native.run_model(view[1:], dec, grid[1:, 1000:1777], 1.0, impl='tc')
     assert torch.equal(part, rgb[1:, 1000:1777]) and torch.equal(sp, sigma[1:, 1000:1777])
+    # densities only (what extract_mesh keeps): same sigma bit for bit, no colour buffer
+    none, so = native.run_model(view, dec, grid, 1.0, impl='tc', sigma_only=True)
+    assert none is None and torch.equal(so, sigma)
 
 
 def test_ray_march_standalone_matches_oracle():

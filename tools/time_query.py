@@ -49,6 +49,17 @@ def main():
             torch.cuda.synchronize()
             ms = ev[0].elapsed_time(ev[1]) / args.iters
             out[f'{pattern}_{impl}'] = {'points': pts.shape[1], 'ms': round(ms, 4), 'Mpoints_per_s': round(pts.shape[1] / ms / 1e3, 1)}
+        for _ in range(3):
+            native.run_model(planes, packed, pts, 1.0, impl='tc', sigma_only=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(args.iters):
+            native.run_model(planes, packed, pts, 1.0, impl='tc', sigma_only=True)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / args.iters
+        out[f'{pattern}_tc_sigma_only'] = {'ms': round(ms, 4), 'Mpoints_per_s': round(pts.shape[1] / ms / 1e3, 1)}
     print(json.dumps({'nets': args.nets, **out}))
 
 
