@@ -139,6 +139,12 @@ int p3d_run_model_tc(const float* planes_nhwc, const int64_t plane_strides[3], c
 int p3d_sample_from_planes(const float* planes_nhwc, const float* coords, int B, int M, int H, int W,
                            float coord_scale, float* out_features, p3d_stream_t stream);
 
+/* Gradient of sample_from_planes w.r.t. the planes (what autograd derives from F.grid_sample at renderer.py:64):
+ * grad_features [B,3,M,32] -> grad_planes_nhwc [B,3,H,W,32] (zeroed here, then the bilinear taps are scattered with
+ * vector atomics). Coordinates carry no gradient in the reference's pipeline. */
+int p3d_sample_from_planes_bwd(const float* grad_features, const float* coords, int B, int64_t M, int H, int W,
+                               float coord_scale, float* grad_planes_nhwc, p3d_stream_t stream);
+
 /* MipRayMarcher2.run_forward on explicit tensors -- ray_marcher.py:25-57.
  * colors [N,S,Cc], densities [N,S], depths [N,S]; out_rgb [N,Cc], out_depth [N] (clamped),
  * out_weights [N,S-1]. N = B*R rays. */
@@ -146,6 +152,15 @@ int p3d_ray_march(const float* colors, const float* densities, const float* dept
                   int N, int S, int Cc, int white_back,
                   float* out_rgb, float* out_depth, float* out_weights,
                   uint32_t* workspace, p3d_stream_t stream);
+
+/* First-order backward of MipRayMarcher2.run_forward (ray_marcher.py:25-57) w.r.t. colours and densities.
+ * grad_rgb [N,Cc]; grad_depth [N] or NULL; grad_weights [N,S-1] or NULL; depth_range[2] = {min, max} of all depths (device
+ * pointer; needed with grad_depth: the clamp at :50 passes the gradient only inside the range, nan_to_num only where the
+ * composite is finite). grad_colors [N,S,Cc], grad_densities [N,S]. Rays whose upstream depth gradient is exactly zero
+ * skip the depth term (autograd would form 0/0 there when the weight sum is zero). */
+int p3d_ray_march_bwd(const float* colors, const float* densities, const float* depths, const float* grad_rgb,
+                      const float* grad_depth, const float* grad_weights, const float* depth_range, int N, int S,
+                      int Cc, int white_back, float* grad_colors, float* grad_densities, p3d_stream_t stream);
 
 /* sample_importance + sample_pdf -- renderer.py:194-253. z_vals [N,S], weights [N,S-1], u [N,Sf];
  * out_samples [N,Sf], out_inds [N,Sf] (may be NULL). */

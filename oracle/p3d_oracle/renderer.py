@@ -330,3 +330,82 @@ def importance_semantic_renderer(planes_texture, planes_semantic, dec_texture, d
     for i in range(w.shape[2]):
         wsum = wsum + w[:, :, i]
     return feat, depth, wsum.astype(f32)
+
+
+# ---------------------------------------------------------------------------------------------
+# First-order gradients of the two differentiable renderer stages (what autograd derives from renderer.py:55-65 and
+# ray_marcher.py:25-57); importance sampling is under no_grad / detached in the reference (renderer.py:198,211).
+# ---------------------------------------------------------------------------------------------
+def sample_from_planes_backward(grad_out, plane_shape, coordinates, box_warp):
+    """grad_out [N,3,M,C] -> gradient w.r.t. planes [N,3,C,H,W]: the bilinear taps scattered back (zero padding)."""
+    g = np.asarray(grad_out, np.float64)
+    n, _, c, h, w = plane_shape
+    coords = f32(2 / box_warp) * np.asarray(coordinates, f32)
+    out = np.zeros(plane_shape, np.float64)
+    for b in range(n):
+        for k, (a0, a1) in enumerate(PLANE_COORDS):
+            gx, gy = coords[b, :, a0], coords[b, :, a1]
+            ix = ((gx + f32(1)) * f32(w) - f32(1)) * f32(0.5)
+            iy = ((gy + f32(1)) * f32(h) - f32(1)) * f32(0.5)
+            x0f, y0f = np.floor(ix), np.floor(iy)
+            ax, bx = (x0f + f32(1)) - ix, ix - x0f
+            ay, by = (y0f + f32(1)) - iy, iy - y0f
+            inside = (ix > -1) & (ix < w) & (iy > -1) & (iy < h)
+            x0 = np.where(inside, x0f, 0).astype(np.int64)
+            y0 = np.where(inside, y0f, 0).astype(np.int64)
+            for dy, dx, wgt in ((0, 0, ax * ay), (0, 1, bx * ay), (1, 0, ax * by), (1, 1, bx * by)):
+                xx, yy = x0 + dx, y0 + dy
+                ok = inside & (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+                wv = np.where(ok, wgt, f32(0)).astype(np.float64)
+                np.add.at(out[b, k], (slice(None), np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)), (wv[:, None] * g[b, k]).T)
+    return out.astype(f32)
+
+
+def ray_march_backward(colors, densities, depths, g_rgb, g_depth, g_weights, white_back=False, clamp_range=None):
+    """Gradients of `ray_march` w.r.t. colors [B,R,S,C] and densities [B,R,S,1] for upstream gradients of its three
+    outputs (g_rgb [B,R,C], g_depth [B,R,1] or None, g_weights [B,R,S-1,1] or None). Depths carry no gradient in the
+    reference's pipeline. The depth term follows autograd: it passes only where the composite depth is finite and inside
+    the clamp range, and is skipped for rays whose upstream depth gradient is exactly zero."""
+    c = np.asarray(colors, np.float64)
+    s = np.asarray(densities, np.float64)[..., 0]
+    z = np.asarray(depths, np.float64)[..., 0]
+    delta = z[:, :, 1:] - z[:, :, :-1]
+    cmid = (c[:, :, :-1] + c[:, :, 1:]) / 2
+    smid = (s[:, :, :-1] + s[:, :, 1:]) / 2
+    zmid = (z[:, :, :-1] + z[:, :, 1:]) / 2
+    x = smid - 1
+    sp = np.where(x > 20, x, np.log1p(np.exp(np.minimum(x, 20))))
+    e = np.exp(-sp * delta)
+    alpha = 1 - e
+    a = 1 - alpha + 1e-10
+    trans = np.concatenate([np.ones_like(a[:, :, :1]), np.cumprod(a, -1)[:, :, :-1]], -1)
+    w = alpha * trans
+    wsum = w.sum(-1)
+    G = 2 * np.asarray(g_rgb, np.float64)
+    gw = np.einsum('brc,bric->bri', G, cmid)
+    if white_back:
+        gw = gw - G.sum(-1)[..., None]
+    if g_weights is not None:
+        gw = gw + np.asarray(g_weights, np.float64)[..., 0]
+    if g_depth is not None:
+        gd = np.asarray(g_depth, np.float64)[..., 0]
+        with np.errstate(divide='ignore', invalid='ignore'):
+            draw = (w * zmid).sum(-1) / wsum
+        lo, hi = (np.asarray(depths, f32).min(), np.asarray(depths, f32).max()) if clamp_range is None else clamp_range
+        ok = np.isfinite(draw) & (draw >= lo) & (draw <= hi) & (gd != 0)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            term = gd[..., None] * (zmid - draw[..., None]) / wsum[..., None]
+        gw = gw + np.where(ok[..., None], term, 0)
+    g_cmid = w[..., None] * G[:, :, None, :]
+    gww = gw * w
+    suffix = np.concatenate([np.cumsum(gww[:, :, ::-1], -1)[:, :, ::-1][:, :, 1:], np.zeros_like(gww[:, :, :1])], -1)
+    g_alpha = gw * trans - suffix / a
+    g_sp = g_alpha * e * delta
+    g_smid = g_sp * np.where(x > 20, 1.0, 1 / (1 + np.exp(-np.clip(x, -80, 80))))
+    g_c = np.zeros_like(c)
+    g_c[:, :, :-1] += g_cmid / 2
+    g_c[:, :, 1:] += g_cmid / 2
+    g_s = np.zeros_like(s)
+    g_s[:, :, :-1] += g_smid / 2
+    g_s[:, :, 1:] += g_smid / 2
+    return g_c.astype(f32), g_s[..., None].astype(f32)

@@ -275,6 +275,39 @@ def ray_march(colors, densities, depths, white_back=False):
     return rgb, depth, weights
 
 
+def sample_from_planes_bwd(grad_features, coords, box_warp, H, W):
+    """grad_features [B,3,M,32] -> gradient w.r.t. channels-last planes [B,3,H,W,32]."""
+    g = _f32c(grad_features)
+    c = _f32c(coords)
+    B, _, M, _ = g.shape
+    out = torch.empty(B, 3, H, W, 32, device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        st = _lib.lib().p3d_sample_from_planes_bwd(_lib.ptr(g), _lib.ptr(c), B, M, H, W, 2.0 / float(box_warp), _lib.ptr(out),
+                                                   _lib.stream_ptr())
+    _lib.check(st, 'p3d_sample_from_planes_bwd')
+    _lib.bump()
+    return out
+
+
+def ray_march_bwd(colors, densities, depths, g_rgb, g_depth, g_weights, depth_range, white_back=False):
+    """Gradients of MipRayMarcher2.run_forward w.r.t. colors [B,R,S,C] and densities [B,R,S,1]."""
+    B, R, S, Cc = colors.shape
+    col, den, dep = _f32c(colors), _f32c(densities), _f32c(depths)
+    grgb = _f32c(g_rgb)
+    gdep = None if g_depth is None else _f32c(g_depth)
+    gw = None if g_weights is None else _f32c(g_weights)
+    rng = None if depth_range is None else _f32c(depth_range)
+    g_col = torch.empty_like(col)
+    g_den = torch.empty_like(den)
+    with torch.cuda.device(col.device):
+        st = _lib.lib().p3d_ray_march_bwd(_lib.ptr(col), _lib.ptr(den), _lib.ptr(dep), _lib.ptr(grgb), _lib.ptr(gdep),
+                                          _lib.ptr(gw), _lib.ptr(rng), B * R, S, Cc, 1 if white_back else 0, _lib.ptr(g_col),
+                                          _lib.ptr(g_den), _lib.stream_ptr())
+    _lib.check(st, 'p3d_ray_march_bwd')
+    _lib.bump()
+    return g_col, g_den
+
+
 def sample_importance(z_vals, weights, u, return_inds=False):
     """z_vals [N,S], weights [N,S-1], u [N,Sf] -> samples [N,Sf] (and searchsorted indices)."""
     z, w, uu = _f32c(z_vals), _f32c(weights), _f32c(u)

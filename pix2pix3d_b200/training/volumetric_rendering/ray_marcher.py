@@ -20,10 +20,38 @@ class MipRayMarcher2(torch.nn.Module):
         no_grad = not (torch.is_grad_enabled() and (colors.requires_grad or densities.requires_grad or depths.requires_grad))
         if colors.device.type == 'cuda' and no_grad:
             return native.ray_march(colors, densities, depths, white_back)
+        if (colors.device.type == 'cuda' and not depths.requires_grad and colors.dtype == torch.float32
+                and colors.shape[2] <= 256 and colors.shape[3] <= 256):
+            return _RayMarch.apply(colors, densities, depths, white_back)     # training: kernels in both directions
         return _march_torch(colors, densities, depths, white_back)
 
     def forward(self, colors, densities, depths, rendering_options):
         return self.run_forward(colors, densities, depths, rendering_options)
+
+
+class _RayMarch(torch.autograd.Function):
+    """p3d_ray_march forward, p3d_ray_march_bwd backward (first order; depths are not differentiated: in the reference they
+    come from the stratified / importance samplers, which carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, colors, densities, depths, white_back):
+        ctx.set_materialize_grads(False)
+        ctx.white_back = white_back
+        ctx.save_for_backward(colors, densities, depths)
+        return native.ray_march(colors.detach(), densities.detach(), depths, white_back)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rgb, g_depth, g_weights):
+        colors, densities, depths = ctx.saved_tensors
+        if g_rgb is None:
+            g_rgb = colors.new_zeros(colors.shape[0], colors.shape[1], colors.shape[3])
+        rng = None
+        if g_depth is not None:
+            lo, hi = torch.aminmax(depths)
+            rng = torch.stack([lo, hi]).float()
+        g_col, g_den = native.ray_march_bwd(colors, densities, depths, g_rgb, g_depth, g_weights, rng, ctx.white_back)
+        return g_col.to(colors.dtype), g_den.to(densities.dtype), None, None
 
 
 def _march_torch(colors, densities, depths, white_back):

@@ -37,14 +37,39 @@ def sample_from_planes(plane_axes, plane_features, coordinates, mode='bilinear',
     n, n_planes, c, h, w = plane_features.shape
     m = coordinates.shape[1]
     no_grad = not (torch.is_grad_enabled() and (plane_features.requires_grad or coordinates.requires_grad))
-    if (plane_features.device.type == 'cuda' and no_grad and mode == 'bilinear' and n_planes == 3 and c == 32
-            and _is_default_axes(plane_axes)):
-        return native.sample_from_planes(native.planes_to_channels_last(plane_features), coordinates, box_warp)
+    if (plane_features.device.type == 'cuda' and mode == 'bilinear' and n_planes == 3 and c == 32
+            and plane_features.dtype == torch.float32 and _is_default_axes(plane_axes)):
+        if no_grad:
+            return native.sample_from_planes(native.planes_to_channels_last(plane_features), coordinates, box_warp)
+        if not coordinates.requires_grad:          # training: gradients reach the planes only (rays come from the camera label)
+            return _SamplePlanes.apply(plane_features, coordinates, float(box_warp))
     feats = plane_features.reshape(n * n_planes, c, h, w)
     coords = (2 / box_warp) * coordinates
     grid = project_onto_planes(plane_axes, coords).unsqueeze(1)
     out = torch.nn.functional.grid_sample(feats, grid.float(), mode=mode, padding_mode=padding_mode, align_corners=False)
     return out.permute(0, 3, 2, 1).reshape(n, n_planes, m, c)
+
+
+class _SamplePlanes(torch.autograd.Function):
+    """Tri-plane lookup with its first-order backward on the kernels: p3d_sample_from_planes forward, p3d_sample_from_planes_bwd
+    (scatter of the bilinear taps) backward. Coordinates are not differentiated."""
+
+    @staticmethod
+    def forward(ctx, plane_features, coordinates, box_warp):
+        ctx.save_for_backward(coordinates)
+        ctx.box_warp = box_warp
+        ctx.plane_shape = tuple(plane_features.shape)
+        return native.sample_from_planes(native.planes_to_channels_last(plane_features.detach()), coordinates, box_warp)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        from ... import tcconv
+        (coordinates,) = ctx.saved_tensors
+        n, p, c, h, w = ctx.plane_shape
+        g_cl = native.sample_from_planes_bwd(grad_out, coordinates, ctx.box_warp, h, w)          # [N,3,H,W,32]
+        g = tcconv.nhwc_to_nchw_f32(g_cl.view(n * p, h, w, c))                                   # [N*3,32,H,W]
+        return g.view(n, p, c, h, w), None, None
 
 
 def sample_from_3dgrid(grid, coordinates):
