@@ -104,6 +104,10 @@ typedef struct {
      * {H*W*96, 32, 96} reads the backbone's NHWC [B,H,W,96] output in place (p3d_render_fwd_tc only; p3d_render_fwd
      * returns P3D_UNSUPPORTED for non-dense planes). */
     int64_t plane_strides[3];
+    /* p3d_render_fwd_tc only: 0 = one 8-ray tile per CTA shared by its three 128-row groups (render_tc.cu); 1 = ray-pair
+     * ownership, groups never synchronise with each other (render_tc2.cu; Sc, Sf <= 64, else P3D_UNSUPPORTED). Same results. */
+    int32_t tc_variant;
+    int32_t reserved0;
 } p3d_render_args_t;
 
 /* ImportanceRenderer.forward for scalar ray limits -- training/volumetric_rendering/renderer.py:88-140:

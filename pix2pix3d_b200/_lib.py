@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libp3d.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -41,6 +41,7 @@ class RenderArgs(ctypes.Structure):  # p3d_render_args_t
         ('dbg_perm', c_void_p), ('dbg_weights_final', c_void_p),
         ('workspace', c_void_p),
         ('plane_strides', ctypes.c_int64 * 3),
+        ('tc_variant', c_int32), ('reserved0', c_int32),
     ]
 
 

@@ -708,7 +708,7 @@ using namespace p3d;
 
 extern "C" {
 
-int p3d_abi_version(void) { return 1; }
+int p3d_abi_version(void) { return 2; }
 const char* p3d_build_info(void) { return "libp3d sm_100a " __DATE__ " " __TIME__; }
 const char* p3d_status_string(int status) {
     if (status == P3D_OK) return "ok";

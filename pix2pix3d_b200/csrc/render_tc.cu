@@ -10,6 +10,7 @@
 //     from TMEM (A-from-TMEM MMA), three passes again; colours come back with tcgen05.ld and are reduced per ray
 //     with warp shuffles using the coefficient form rgb = sum_j c_j (w_{j-1} + w_j)/2.
 //   The sigma-only pre-passes (coarse / fine densities) use layer 1 on the tensor core and a 64-term CUDA-core dot.
+#include <cstdlib>
 #include "render_tc.cuh"
 
 namespace p3d {
@@ -535,6 +536,15 @@ extern "C" int p3d_render_fwd_tc(const p3d_render_args_t* args, p3d_stream_t str
         const int64_t max_off = (int64_t)(a.B - 1) * is + 2 * pls + ((int64_t)a.H * a.W - 1) * pxs + kC;
         if (max_off >= ((int64_t)1 << 32)) return P3D_UNSUPPORTED;
         P.img_stride = (uint32_t)is; P.plane_stride = (uint32_t)pls; P.pix_stride = (uint32_t)pxs;
+    }
+    {
+        // args.tc_variant = 1 (or P3D_RENDER_TC_PAIRS=1 in the environment, for A/B runs of whole programs) selects the
+        // ray-pair variant (render_tc2.cu)
+        static int env_pairs = -1;
+        if (env_pairs < 0) { const char* e = getenv("P3D_RENDER_TC_PAIRS"); env_pairs = (e && e[0] == '1') ? 1 : 0; }
+        if (a.tc_variant == 1 && (a.Sc > 64 || a.Sf > 64)) return P3D_UNSUPPORTED;
+        if ((env_pairs == 1 || a.tc_variant == 1) && a.Sc <= 64 && a.Sf <= 64)
+            return render_fwd_tc_pairs(a, P.img_stride, P.plane_stride, P.pix_stride, (cudaStream_t)stream);
     }
     P3D_CUDA_TRY(cudaMemsetAsync(a.workspace, 0, 4 * sizeof(uint32_t), (cudaStream_t)stream));
     P3D_CUDA_TRY(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

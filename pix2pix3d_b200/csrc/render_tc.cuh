@@ -137,4 +137,8 @@ __device__ __forceinline__ void tc_gather_rows(const TcPlaneView& pv, uint8_t* t
     }
 }
 
+// Ray-pair variant of the fused renderer (render_tc2.cu): groups own whole rays and never synchronise with each other.
+int render_fwd_tc_pairs(const p3d_render_args_t& a, uint32_t img_stride, uint32_t plane_stride, uint32_t pix_stride,
+                        cudaStream_t stream);
+
 }  // namespace p3d

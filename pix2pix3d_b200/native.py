@@ -12,7 +12,8 @@ from . import _lib
 PACKED_FLOATS = 2 * 4260
 TC_PACKED_BYTES = 65536 + 324 * 4
 
-# which fused renderer `render_fwd` uses: 'auto' (tensor-core decoder when the sample counts allow it), 'tc', 'simt'
+# which fused renderer `render_fwd` uses: 'auto' (tensor-core decoder when the sample counts allow it), 'tc', 'simt',
+# 'tc_pairs' (tensor-core decoder, ray-pair ownership: render_tc2.cu; sample counts <= 64)
 render_impl = 'auto'
 
 # when set to a list, render_fwd appends ('render_fwd', start_event, end_event) around its launch (bench.py)
@@ -183,9 +184,10 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
     if kernel_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    use_tc = impl in ('auto', 'tc') and Sc % 8 == 0 and Sf % 8 == 0 and Sc <= 128 and Sf <= 128 and dec.packed_tc is not None
-    if impl == 'tc' and not use_tc:
+    use_tc = impl in ('auto', 'tc', 'tc_pairs') and Sc % 8 == 0 and Sf % 8 == 0 and Sc <= 128 and Sf <= 128 and dec.packed_tc is not None
+    if impl in ('tc', 'tc_pairs') and not use_tc:
         raise ValueError('tensor-core renderer needs sample counts that are multiples of 8')
+    a.tc_variant = 1 if impl == 'tc_pairs' else 0
     with torch.cuda.device(dev):
         if use_tc:
             a.decoder_packed = dec.packed_tc.data_ptr()
@@ -214,7 +216,7 @@ def run_model(planes_nhwc, dec, coords, box_warp, impl=None, sigma_only=False):
     B, _, H, W, C = planes_nhwc.shape
     assert C == 32 and planes_nhwc.dtype == torch.float32
     impl = impl or render_impl
-    use_tc = impl in ('auto', 'tc') and dec.packed_tc is not None
+    use_tc = impl in ('auto', 'tc', 'tc_pairs') and dec.packed_tc is not None
     strides = None
     if not planes_nhwc.is_contiguous():
         st_img, st_plane, st_row, st_pix, st_ch = planes_nhwc.stride()

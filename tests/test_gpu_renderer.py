@@ -47,7 +47,8 @@ def run_fused(g, debug=True, impl='simt'):
     return res, dc, opts
 
 
-IMPL_CASES = [(c, 'simt') for c in RENDER_CASES] + [(c, 'tc') for c in TC_RENDER_CASES]
+IMPL_CASES = ([(c, 'simt') for c in RENDER_CASES] + [(c, 'tc') for c in TC_RENDER_CASES]
+              + [(c, 'tc_pairs') for c in TC_RENDER_CASES])      # every tc fixture has <= 64 samples per pass
 
 
 @pytest.mark.parametrize('case,impl', IMPL_CASES)
@@ -194,7 +195,7 @@ def test_ray_march_standalone_matches_oracle():
         assert depth[0, 0, 0].item() == depths.max()
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_pairs'])
 def test_full_size_properties_config2(impl):
     """BASELINE config 2 sizes (B=4, 128^2 rays, 48+48 samples): size-independent properties."""
     from pix2pix3d_b200 import native
@@ -277,7 +278,7 @@ def test_importance_renderer_module_dispatches_to_fused_kernel():
     assert rel_err(wsum.cpu().numpy(), g['wsum']) < TOL
 
 
-@pytest.mark.parametrize('impl', ['simt', 'tc'])
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_pairs'])
 def test_unsorted_and_tied_coarse_depths_still_merge_like_a_stable_sort(impl):
     """The C-ABI accepts any depths_coarse. The tensor-core kernel takes a shortcut when a ray's coarse depths are
     non-decreasing (what sample_stratified produces); rays that are not, and rays with exact ties, must still produce the
