@@ -32,4 +32,7 @@ def main(reps=3, impl='auto', B=4, H=256, nrr=128, Sc=48, Sf=48):
     print(f'render_fwd[{impl}]: {ms:.3f} ms  {gb / ms * 1e3:.1f} GB/s touched  ({B * R / ms * 1e3:.3e} rays/s)')
 
 if __name__ == '__main__':
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 3, sys.argv[2] if len(sys.argv) > 2 else 'auto')
+    # usage: profile_render.py [reps] [impl] [B nrr Sc Sf]   e.g. `10 tc_pairs 8 64 64 64` for the config-4 sampling
+    extra = [int(v) for v in sys.argv[3:7]]
+    kw = dict(zip(('B', 'nrr', 'Sc', 'Sf'), extra))
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 3, sys.argv[2] if len(sys.argv) > 2 else 'auto', **kw)
