@@ -2,7 +2,7 @@
 on CPU with seeded inputs.
 
 Runs only in the authoring container: the GPU box has no /root/reference, which is why the outputs are committed.
-    python oracle/make_golden.py            # writes tests/golden/{renderer,ops,synthesis}_*.npz
+    python oracle/make_golden.py            # writes tests/golden/{renderer,ops,synthesis}_*.npz and loss_ops.npz
 
 The renderer's two random draws (stratified jitter, renderer.py:190; importance u, renderer.py:237) are captured
 by wrapping torch.rand_like / torch.rand while the reference runs, and stored so that every implementation can be
@@ -361,12 +361,43 @@ def golden_semgen():
         print('semgen', name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def golden_loss_ops():
+    """Loss-side image ops, evaluated by the reference's own functions on CPU: `filtered_resizing`
+    (training/dual_discriminator.py:86-102, all filter modes) with input gradients, and `cross_entropy2d`
+    (training/loss_utils.py:4-18) with and without class weights and with the label-resolution upsample."""
+    from torch_utils.ops import upfirdn2d
+    from training.dual_discriminator import filtered_resizing
+    from training.loss_utils import cross_entropy2d
+    g = torch.Generator().manual_seed(77)
+    save = {}
+    f4 = upfirdn2d.setup_filter([1, 3, 3, 1])
+    for tag, (src, dst) in {'up': (16, 64), 'down': (64, 16), 'odd': (24, 37)}.items():
+        x = torch.randn(2, 3, src, src, generator=g).requires_grad_(True)
+        gy = torch.randn(2, 3, dst, dst, generator=g)
+        save[f'fr_{tag}_x'], save[f'fr_{tag}_gy'] = x.detach(), gy
+        for mode in ('antialiased', 'none', 0.3) + (('classic',) if tag == 'up' else ()):
+            y = filtered_resizing(x, size=dst, f=f4, filter_mode=mode)
+            (gx,) = torch.autograd.grad((y * gy).sum(), x)
+            save[f'fr_{tag}_{mode}_y'], save[f'fr_{tag}_{mode}_gx'] = y.detach(), gx
+    for tag, (c, h, ht) in {'same': (6, 16, 16), 'lowres': (19, 8, 16)}.items():
+        logits = (torch.randn(2, c, h, h, generator=g) * 3).requires_grad_(True)
+        target = torch.randint(0, c, (2, ht, ht), generator=g)
+        wgt = torch.rand(c, generator=g) * 4 + 0.2
+        save[f'ce_{tag}_x'], save[f'ce_{tag}_t'], save[f'ce_{tag}_w'] = logits.detach(), target, wgt
+        for wtag, w in (('plain', None), ('weighted', wgt)):
+            loss = cross_entropy2d(logits, target, weight=w)
+            (gx,) = torch.autograd.grad(loss, logits)
+            save[f'ce_{tag}_{wtag}_loss'], save[f'ce_{tag}_{wtag}_gx'] = loss.detach(), gx
+    np.savez_compressed(os.path.join(OUT, 'loss_ops.npz'), **{k: v.numpy() for k, v in save.items()})
+    print('loss_ops', len(save), 'arrays')
+
+
 if __name__ == '__main__':
     assert os.path.isdir(REF), 'the reference checkout is only available in the authoring container'
     sys.path.insert(0, REF)
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['renderer', 'ops', 'synthesis', 'semgen']
+    which = sys.argv[1:] or ['renderer', 'ops', 'synthesis', 'semgen', 'loss_ops']
     if 'renderer' in which:
         golden_renderer()
     if 'ops' in which:
@@ -375,3 +406,5 @@ if __name__ == '__main__':
         golden_synthesis()
     if 'semgen' in which:
         golden_semgen()
+    if 'loss_ops' in which:
+        golden_loss_ops()

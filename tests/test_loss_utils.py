@@ -75,3 +75,24 @@ def test_cross_entropy_all_ignored_is_nan_like_aten():
     x = torch.randn(1, 4, 8, 8, device='cuda')
     t = torch.full((1, 8, 8), -100, dtype=torch.int64, device='cuda')
     assert torch.isnan(cross_entropy2d(x, t))
+
+
+@pytest.mark.parametrize('wtag', ['plain', 'weighted'])
+def test_oracle_and_mirror_match_reference_cross_entropy2d(wtag):
+    """Fixture produced by the reference's own `cross_entropy2d` (oracle/make_golden.py loss_ops)."""
+    from conftest import load_golden
+    from pix2pix3d_b200.training.loss_utils import cross_entropy2d
+    g = load_golden('loss_ops')
+    for tag in ('same', 'lowres'):
+        x, t, w = g[f'ce_{tag}_x'], g[f'ce_{tag}_t'], g[f'ce_{tag}_w']
+        wgt = w if wtag == 'weighted' else None
+        want, want_gx = float(g[f'ce_{tag}_{wtag}_loss']), g[f'ce_{tag}_{wtag}_gx']
+        xt = torch.from_numpy(x).requires_grad_(True)
+        loss = cross_entropy2d(xt, torch.from_numpy(t), weight=None if wgt is None else torch.from_numpy(wgt))
+        (gx,) = torch.autograd.grad(loss, xt)
+        assert abs(loss.item() - want) <= 1e-6 * max(abs(want), 1)
+        assert rel_err(gx.numpy(), want_gx) < 1e-6
+        if tag == 'same':       # the oracle restates the per-pixel loss (the label upsample of :8-10 stays an ATen call)
+            ol, og = O.ops.cross_entropy2d(x, t, wgt)
+            assert abs(ol - want) <= 2e-6 * max(abs(want), 1)
+            assert rel_err(og, want_gx) < 1e-5

@@ -90,3 +90,27 @@ def test_resize_kernel_gradients_to_second_order():
     # d/dw sum((A^T w)^2) = 2 A A^T w
     ref_gw = 2 * O.networks.bilinear_resize(ref_gx, (64, 64))
     assert rel_err(w.grad.cpu().numpy(), ref_gw) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# fixture produced by the reference's own `filtered_resizing` (oracle/make_golden.py loss_ops)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag,dst', [('up', 64), ('down', 16), ('odd', 37)])
+def test_oracle_and_mirror_match_reference_filtered_resizing(tag, dst):
+    from conftest import load_golden
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    from pix2pix3d_b200.training.dual_discriminator import filtered_resizing
+    g = load_golden('loss_ops')
+    x, gy = g[f'fr_{tag}_x'], g[f'fr_{tag}_gy']
+    # oracle restatement: the two pure-interpolation modes, forward and input gradient
+    for mode, aa in (('antialiased', True), ('none', False)):
+        assert rel_err(O.networks.bilinear_resize(x, (dst, dst), aa), g[f'fr_{tag}_{mode}_y']) < 1e-5
+        assert rel_err(O.networks.bilinear_resize_adjoint(gy, x.shape[2:], aa), g[f'fr_{tag}_{mode}_gx']) < 1e-5
+    # mirror module on CPU tensors: every filter mode of the reference, bit for bit (same ATen calls)
+    f4 = upfirdn2d.setup_filter([1, 3, 3, 1])
+    for mode in ('antialiased', 'none', 0.3) + (('classic',) if tag == 'up' else ()):
+        xt = torch.from_numpy(x).requires_grad_(True)
+        y = filtered_resizing(xt, size=dst, f=f4, filter_mode=mode)
+        (gx,) = torch.autograd.grad((y * torch.from_numpy(gy)).sum(), xt)
+        assert rel_err(y.detach().numpy(), g[f'fr_{tag}_{mode}_y']) < 1e-6
+        assert rel_err(gx.numpy(), g[f'fr_{tag}_{mode}_gx']) < 1e-6
