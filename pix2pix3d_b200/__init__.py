@@ -9,7 +9,7 @@ Layout
                    root, same class / function names and signatures)
 
 `install()` makes the mirror answer to the reference's top-level module names (`training.*`, `torch_utils.*`,
-`dnnlib`, `camera_utils`), so reference callers (applications/generate_samples.py, train.py) and pickles that
+`dnnlib`, `camera_utils`, `legacy`), so reference callers (applications/generate_samples.py, train.py) and pickles that
 refer to those paths resolve to this package.
 """
 import importlib
@@ -19,7 +19,7 @@ import sys
 
 __version__ = '0.1.0'
 
-_ALIASED_ROOTS = ('training', 'torch_utils', 'dnnlib', 'camera_utils')
+_ALIASED_ROOTS = ('training', 'torch_utils', 'dnnlib', 'camera_utils', 'legacy')
 
 
 class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):

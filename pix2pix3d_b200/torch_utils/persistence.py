@@ -1,12 +1,26 @@
 """`persistent_class` decorator with the reference's surface (torch_utils/persistence.py:37-128).
 
 Classes keep a record of their constructor arguments (`init_args`, `init_kwargs`) so that callers such as
-training_loop.py / legacy.py can rebuild them. Embedding module source into pickles (the reference's way of
-shipping code with checkpoints) is checkpoint I/O and out of scope for the hot path; objects pickle by
-reference to this package instead.
+training_loop.py / legacy.py can rebuild them. Objects of this package pickle by reference to the package (no source is
+embedded). Pickles WRITTEN BY THE REFERENCE embed the source of each persistent class's module and name
+`torch_utils.persistence._reconstruct_persistent_obj` as their constructor (reference persistence.py:119-128, 181-204);
+`_reconstruct_persistent_obj` below accepts that format and rebuilds the object as the mirror class of the same name from
+its recorded constructor arguments, then loads the pickled parameters and buffers -- what the reference's callers do by hand
+with `reload_modules` (`generate_samples.py`, `misc.copy_params_and_buffers`) -- so a released checkpoint comes up on the
+kernels of this package without executing the code stored inside it.
 """
 import copy
+import importlib
+import re
 import sys
+
+_version = 6                 # pickle format version of the reference's persistence module (persistence.py:29)
+_import_hooks = []
+# set to True to fall back to executing the module source stored in the pickle (the reference's behaviour) for classes this
+# package has no mirror of
+allow_embedded_source = False
+_MIRROR_MODULES = ('training.networks_stylegan2', 'training.triplane', 'training.triplane_cond', 'training.superresolution',
+                   'training.dual_discriminator')
 
 _decorated = set()
 
@@ -51,5 +65,106 @@ def is_persistent(obj):
     return type(obj) in _decorated
 
 
-def import_hook(hook):  # accepted for API compatibility; no embedded source to rewrite
+def import_hook(hook):
+    """Register `hook(meta) -> meta`, called for every persistent object being unpickled (reference persistence.py:150-176)."""
     assert callable(hook)
+    _import_hooks.append(hook)
+    return hook
+
+
+def _mirror_class(class_name, module_src):
+    """The mirror class for a pickled (class name, module source) pair. Names are unique per module but not across modules
+    (`TriPlaneGenerator` lives in both training/triplane.py and training/triplane_cond.py), so the candidate whose module
+    defines the largest share of the classes declared in the stored source wins."""
+    declared = set(re.findall(r'^class\s+(\w+)', module_src or '', flags=re.M))
+    root = __name__.rsplit('.', 2)[0]
+    best, best_score = None, -1.0
+    for mod_name in _MIRROR_MODULES:
+        mod = importlib.import_module(f'{root}.{mod_name}')
+        cls = getattr(mod, class_name, None)
+        if not isinstance(cls, type):
+            continue
+        own = {k for k, v in vars(mod).items() if isinstance(v, type) and v.__module__ == mod.__name__}
+        score = len(declared & own) / max(len(declared), 1)
+        if score > best_score:
+            best, best_score = cls, score
+    return best
+
+
+def _flatten_state(state, prefix, out):
+    """Parameters and buffers of a pickled torch.nn.Module state (its __dict__), children included."""
+    for kind in ('_parameters', '_buffers'):
+        for k, v in (state.get(kind) or {}).items():
+            if v is not None:
+                out[prefix + k] = v
+    skip = set(state.get('_non_persistent_buffers_set') or ())
+    for k in skip:
+        out.pop(prefix + k, None)
+    for k, child in (state.get('_modules') or {}).items():
+        if child is not None:
+            for name, t in child.state_dict().items():
+                out[f'{prefix}{k}.{name}'] = t
+
+
+def _reconstruct_persistent_obj(meta):
+    """Constructor named by the reference's pickles (persistence.py:181-204)."""
+    from .. import dnnlib
+    meta = dnnlib.EasyDict(meta)
+    meta.state = dnnlib.EasyDict(meta.state)
+    for hook in _import_hooks:
+        meta = hook(meta)
+        assert meta is not None
+    assert meta.version == _version, f'unsupported persistence version {meta.version}'
+    assert meta.type == 'class'
+    cls = _mirror_class(meta.class_name, meta.get('module_src'))
+    if cls is None:
+        if not allow_embedded_source:
+            raise ModuleNotFoundError(f'no mirror of persistent class {meta.class_name!r}; set '
+                                      'torch_utils.persistence.allow_embedded_source = True to execute the source stored in the pickle')
+        return _reconstruct_from_source(meta)
+    import torch
+    if issubclass(cls, torch.nn.Module) and '_init_kwargs' in meta.state:
+        obj = cls(*meta.state.get('_init_args', ()), **meta.state['_init_kwargs'])
+        tensors = {}
+        _flatten_state(meta.state, '', tensors)
+        missing, unexpected = obj.load_state_dict(tensors, strict=False)
+        missing = [k for k in missing if k in dict(obj.named_parameters())]      # buffers may be re-derived constants
+        if missing or unexpected:
+            raise RuntimeError(f'{meta.class_name}: checkpoint does not match the mirror class '
+                               f'(missing {missing[:4]}, unexpected {list(unexpected)[:4]})')
+        obj.train(bool(meta.state.get('training', True)))
+        requires = {k: v.requires_grad for k, v in tensors.items() if hasattr(v, 'requires_grad')}
+        for name, p in obj.named_parameters():
+            if name in requires:
+                p.requires_grad_(requires[name])
+        return obj
+    obj = cls.__new__(cls)
+    setstate = getattr(obj, '__setstate__', None)
+    if callable(setstate):
+        setstate(meta.state)
+    else:
+        obj.__dict__.update(meta.state)
+    return obj
+
+
+_src_modules = {}
+
+
+def _reconstruct_from_source(meta):
+    """The reference's own procedure: run the stored module source and instantiate its class without calling __init__."""
+    import types
+    import uuid
+    module = _src_modules.get(meta.module_src)
+    if module is None:
+        module = types.ModuleType('_imported_module_' + uuid.uuid4().hex)
+        sys.modules[module.__name__] = module
+        _src_modules[meta.module_src] = module
+        exec(meta.module_src, module.__dict__)          # noqa: S102 -- opt-in, see allow_embedded_source
+    cls = persistent_class(module.__dict__[meta.class_name])
+    obj = cls.__new__(cls)
+    setstate = getattr(obj, '__setstate__', None)
+    if callable(setstate):
+        setstate(meta.state)
+    else:
+        obj.__dict__.update(meta.state)
+    return obj
