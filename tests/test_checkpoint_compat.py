@@ -46,8 +46,15 @@ def test_reference_pickle_loads_as_mirror_classes(tmp_path, case_name):
         raw = f.read()
     assert b'_reconstruct_persistent_obj' in raw and b'class SynthesisLayer' in raw      # reference format: embedded source
 
-    from pix2pix3d_b200 import legacy
-    data = legacy.load_network_pkl(io.BytesIO(raw))
+    # the reference's calling sequence (generate_samples.py:93-95) through the aliased import paths
+    import pix2pix3d_b200
+    pix2pix3d_b200.install()
+    import dnnlib
+    import legacy
+    with dnnlib.util.open_url(pkl) as f:
+        data = legacy.load_network_pkl(f)
+    with dnnlib.util.open_url('file://' + pkl) as f:
+        assert f.read(16) == raw[:16]
     G = data['G_ema']
     assert type(G).__module__ == 'pix2pix3d_b200.training.triplane_cond' and type(G).__name__ == SYNTH_CASES[case_name]['cls']
     assert type(data['D']).__module__ == 'pix2pix3d_b200.training.dual_discriminator'
