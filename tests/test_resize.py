@@ -114,3 +114,45 @@ def test_oracle_and_mirror_match_reference_filtered_resizing(tag, dst):
         (gx,) = torch.autograd.grad((y * torch.from_numpy(gy)).sum(), xt)
         assert rel_err(y.detach().numpy(), g[f'fr_{tag}_{mode}_y']) < 1e-6
         assert rel_err(gx.numpy(), g[f'fr_{tag}_{mode}_gx']) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# the kernel's band construction, compiled for the host (tools/probe/resize_bands_host.cu includes csrc/resize.cu)
+# ---------------------------------------------------------------------------------------------
+def _bands(exe, i, o, aa):
+    import subprocess
+    lines = subprocess.run([exe, str(i), str(o), str(aa)], capture_output=True, text=True, check=True).stdout.split('\n')
+    pos, mats = 0, []
+    for transposed in range(2):
+        rows, cap = map(int, lines[pos].split()); pos += 1
+        m = np.zeros((rows, i if transposed == 0 else o), np.float64)
+        for r in range(rows):
+            f = lines[pos].split(); pos += 1
+            start, count = int(f[0]), int(f[1])
+            assert count <= cap                                   # shared-memory band capacity chosen by make_axis
+            for k in range(count):
+                m[r, start + k] += float(f[2 + k])
+        mats.append(m)
+    return mats
+
+
+def test_kernel_band_construction_on_host(tmp_path):
+    """`make_band` / `make_axis` of csrc/resize.cu are __host__ __device__: build them for the CPU and compare the forward
+    bands with the oracle's dense matrix and the transposed bands with its transpose, for up-, down- and odd resampling."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+    exe = str(tmp_path / 'resize_bands_host')
+    r = subprocess.run([nvcc, '-std=c++17', '--expt-relaxed-constexpr', '-Wno-deprecated-gpu-targets', '-o', exe,
+                        os.path.join(root, 'tools', 'probe', 'resize_bands_host.cu')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for aa in (1, 0):
+        for i, o in [(128, 512), (512, 128), (64, 128), (100, 37), (37, 100), (1, 5), (5, 1), (7, 7), (3, 300), (300, 3), (129, 64)]:
+            fwd, tr = _bands(exe, i, o, aa)
+            want = O.networks.resize_matrix(i, o, bool(aa)).astype(np.float64)
+            assert np.abs(fwd - want).max() < 5e-6, (aa, i, o)       # fp32 weights vs the fp64 oracle
+            assert np.abs(tr - fwd.T).max() < 1e-7, (aa, i, o)
