@@ -59,3 +59,15 @@ def test_cuda_ops_fail_loudly_without_library(monkeypatch):
     monkeypatch.setattr(_lib, '_lib', None)
     with pytest.raises(RuntimeError, match='missing'):
         _lib.lib()
+
+
+def test_library_exports_nothing_undeclared():
+    """Every `p3d_*` symbol the shared library exports is declared in include/p3d.h (no entry points outside the documented ABI)."""
+    import shutil
+    import subprocess
+    from pix2pix3d_b200 import _lib
+    if not _lib.available() or not shutil.which('nm'):
+        pytest.skip('needs the built library and nm')
+    out = subprocess.check_output(['nm', '-D', '--defined-only', _lib.LIB_PATH], text=True)
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if ln.split() and re.fullmatch(r'p3d_[a-z0-9_]+', ln.split()[-1])})
+    assert exported == declared_symbols()
