@@ -98,3 +98,21 @@ def test_unknown_persistent_class_is_refused_without_opt_in():
         assert type(obj).__name__ == 'Foo'
     finally:
         persistence.allow_embedded_source = False
+
+
+def test_mirror_networks_pickle_by_reference_and_deepcopy():
+    """Objects of this package pickle without embedded source (by reference to the package) and survive copy.deepcopy, as
+    training_loop.py does for G_ema and the snapshot pickles (training_loop.py:197, 603-615)."""
+    import copy
+    import pickle
+    import pix2pix3d_b200.training.triplane_cond as tc
+    from make_golden import build_generator
+    G = build_generator(tc, SYNTH_CASES['rgb_tiny'])
+    blob = pickle.dumps(dict(G_ema=G))
+    assert b'class SynthesisLayer' not in blob
+    G2 = pickle.loads(blob)['G_ema']
+    assert type(G2) is type(G) and G2.init_kwargs == G.init_kwargs
+    sd, sd2 = G.state_dict(), G2.state_dict()
+    assert sd.keys() == sd2.keys() and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    G3 = copy.deepcopy(G).eval().requires_grad_(False)
+    assert all(torch.equal(a, b) for a, b in zip(G.state_dict().values(), G3.state_dict().values()))
