@@ -393,9 +393,10 @@ def _sr_layers(sr, ws_index):
     return [(layer, ws_index) for block in (sr.block0, sr.block1) for layer in _block_layers(block)]
 
 
-def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=False):
+def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=False, return_block0_image=False):
     """Superresolution*.forward (superresolution.py:48-57) with the feature image as NCHW fp32 and the low-res image as
-    fp32 NHWC; returns the fp32 NHWC output image."""
+    fp32 NHWC; returns the fp32 NHWC output image (and block0's output image on request: a NoUp block0 adds its ToRGB
+    term into the caller's tensor in the reference, superresolution.py:283)."""
     ws = ws.to(torch.float32)
     first_p = tcconv.pad_to(feat_nchw.shape[1], 64)
     specs = _block_specs(sr.block0, force_fp32, first_p, 0) + _block_specs(sr.block1, force_fp32)
@@ -404,9 +405,9 @@ def superresolution(sr, rgb_nhwc, feat_nchw, ws, noise_mode='none', force_fp32=F
     x = tcconv.to_nhwc_f16(feat_nchw, c_padded=tcconv.pad_to(feat_nchw.shape[1], 64), planes=2 if split0 else 1)
     up0 = sr.block0.conv0.up == 2
     n0 = len(_block_layers(sr.block0))
-    x, img = synthesis_block(sr.block0, x, rgb_nhwc, styles[:n0], noise_mode=noise_mode, force_fp32=force_fp32, upsample=up0)
-    x, img = synthesis_block(sr.block1, x, img, styles[n0:], noise_mode=noise_mode, force_fp32=force_fp32, upsample=True)
-    return img
+    x, img0 = synthesis_block(sr.block0, x, rgb_nhwc, styles[:n0], noise_mode=noise_mode, force_fp32=force_fp32, upsample=up0)
+    x, img = synthesis_block(sr.block1, x, img0, styles[n0:], noise_mode=noise_mode, force_fp32=force_fp32, upsample=True)
+    return (img, img0) if return_block0_image else img
 
 
 # ----------------------------------------------------------------------------------------------

@@ -58,5 +58,19 @@ def render_sharded(G, ws, c, gather=False, **synthesis_kwargs):
     out = G.synthesis(ws[lo:hi], c[lo:hi], **synthesis_kwargs) if hi > lo else {}
     if gather and world > 1:
         sizes = [shard_bounds(ws.shape[0], r, world)[1] - shard_bounds(ws.shape[0], r, world)[0] for r in range(world)]
+        if min(sizes) == 0 and max(sizes) > 0:
+            # a rank without images still has to enter every all_gather: it learns the output names / trailing shapes /
+            # dtypes from the first non-empty rank and contributes zero-length tensors
+            out = _empty_like_peer(out, sizes, ws.device)
         out = gather_outputs(out, sizes)
     return out
+
+
+def _empty_like_peer(out, sizes, device):
+    """Ranks with an empty shard receive (name, trailing shape, dtype) of every output from the first non-empty rank."""
+    src = next(r for r, s in enumerate(sizes) if s > 0)
+    meta = [[(k, tuple(v.shape[1:]), str(v.dtype).replace('torch.', '')) for k, v in out.items()]] if dist.get_rank() == src else [None]
+    dist.broadcast_object_list(meta, src=src)
+    if out:
+        return out
+    return {k: torch.zeros((0,) + shape, dtype=getattr(torch, dt), device=device) for k, shape, dt in meta[0]}

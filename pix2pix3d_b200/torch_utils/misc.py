@@ -48,11 +48,16 @@ def copy_params_and_buffers(src_module, dst_module, require_all=False, allow_mis
     """Name-matched tensor copy between modules (reference torch_utils/misc.py:157-176)."""
     src = dict(named_params_and_buffers(src_module))
     for name, tensor in named_params_and_buffers(dst_module):
-        if name not in src:
+        # pix2pix3D addition (:163-165): `superresolution_semantic.*` is initialised from `superresolution.*` when the source
+        # (an EG3D checkpoint) has no semantic branch
+        name_src = name if name in src else name.replace('_semantic', '')
+        if name_src not in src:
             if require_all:
                 raise AssertionError(f'{name} missing in source module')
+            print(f'Warning: {name} not found in source module')
             continue
-        s = src[name].detach()
-        if allow_mismatch and s.shape != tensor.shape:
+        s = src[name_src].detach()
+        if s.shape != tensor.shape and allow_mismatch:
+            print(f'Warning: {name_src} shape mismatch: {tuple(s.shape)} vs {tuple(tensor.shape)}')
             continue
         tensor.copy_(s).requires_grad_(tensor.requires_grad)

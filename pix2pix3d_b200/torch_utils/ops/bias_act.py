@@ -81,7 +81,9 @@ def _launch(x, b, xref, yref, dy, grad, dim, act_idx, alpha, gain, clamp):
         raise ValueError('bias_act: x must be dense')
     for t in (xref, yref, dy):
         if t is not None:
-            assert t.shape == x.shape and t.dtype == x.dtype and t.stride() == x.stride()
+            # same layout = equal strides on every dimension of size >= 2 (has_same_layout, reference bias_act.cpp:17-31)
+            assert t.shape == x.shape and t.dtype == x.dtype
+            assert all(ts == xs for ts, xs, n in zip(t.stride(), x.stride(), x.shape) if n >= 2)
     if b is not None:
         assert b.dtype == x.dtype and b.ndim == 1 and b.shape[0] == x.shape[dim] and b.is_contiguous()
     y = torch.empty_like(x)

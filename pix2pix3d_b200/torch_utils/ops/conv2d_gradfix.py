@@ -1,8 +1,8 @@
 """`conv2d` / `conv_transpose2d` with arbitrarily high order gradients and an opt-out for weight gradients.
 
 Surface of the reference's torch_utils/ops/conv2d_gradfix.py (:23 `enabled`, :26-33 `no_weight_gradients`,
-:37-45 entry points). The dense convolutions of the synthesis path are dispatched to the native
-implicit-GEMM kernels when they apply (see `native_conv`); everything else goes to ATen.
+:37-45 entry points). The forward / data-gradient / weight-gradient convolutions are ATen calls, exactly as in the reference
+(:128-129, :169); the inference path does not go through this module (engine.py drives libp3d's implicit-GEMM kernels).
 """
 import contextlib
 
@@ -94,9 +94,10 @@ def _make_op(transpose, weight_shape, stride, padding, output_padding, dilation,
         def forward(ctx, dy, x):
             ctx.save_for_backward(dy if x.requires_grad else None, x if dy.requires_grad else None)
             ctx.dy_shape, ctx.x_shape = dy.shape, x.shape
-            inp, gout = (dy, x) if transpose else (x, dy)
+            # ATen's convolution_backward takes (grad_output, input) of the op described by `transposed`; no operand
+            # swap for the transposed op (conv2d_gradfix.py:166-169 of the reference does the same)
             grads = torch.ops.aten.convolution_backward(
-                gout, inp, torch.empty(weight_shape, dtype=x.dtype, device=x.device), None,
+                dy, x, torch.empty(weight_shape, dtype=x.dtype, device=x.device), None,
                 list(stride), list(padding), list(dilation), transpose, list(output_padding), groups,
                 [False, True, False])
             return grads[1]

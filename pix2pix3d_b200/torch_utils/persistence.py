@@ -106,6 +106,49 @@ def _flatten_state(state, prefix, out):
                 out[f'{prefix}{k}.{name}'] = t
 
 
+_MODULE_INTERNALS = {'training', '_parameters', '_buffers', '_modules', '_non_persistent_buffers_set', '_init_args',
+                     '_init_kwargs', '_orig_module_src', '_orig_class_name', '_is_full_backward_hook'}
+
+
+def _is_plain(v, depth=0):
+    if v is None or isinstance(v, (bool, int, float, str, bytes)):
+        return True
+    if depth > 6:
+        return False
+    if isinstance(v, (list, tuple, set, frozenset)):
+        return all(_is_plain(e, depth + 1) for e in v)
+    if isinstance(v, dict):
+        return all(_is_plain(k, depth + 1) and _is_plain(e, depth + 1) for k, e in v.items())
+    try:
+        import numpy as np
+        import torch
+        return isinstance(v, (np.ndarray, np.generic, torch.Tensor, torch.dtype, torch.memory_format))
+    except ImportError:
+        return False
+
+
+def _restore_plain_attributes(obj, state):
+    """The reference restores the whole pickled `__dict__` (persistence.py:197-203), so attributes mutated after
+    construction survive a save/load cycle: `G.neural_rendering_resolution` (training_loop.py:558 copies it onto G_ema
+    before every snapshot), `rendering_kwargs`, `_last_planes`. The mirror is rebuilt through its constructor, so those
+    plain (non-module, non-hook) attributes are copied over afterwards, children included."""
+    src = state if isinstance(state, dict) else getattr(state, '__dict__', {})
+    for k, v in src.items():
+        if k in _MODULE_INTERNALS or k.endswith('_hooks') or k.endswith('_hooks_with_kwargs') or k.endswith('_hooks_always_called'):
+            continue
+        if k.startswith('_') and k not in ('_last_planes',):
+            continue
+        cur = obj.__dict__.get(k, None)
+        if k in obj.__dict__ and not _is_plain(cur):
+            continue                                    # helper objects the mirror builds itself (renderer, ray sampler, ...)
+        if _is_plain(v):
+            obj.__dict__[k] = copy.deepcopy(v) if isinstance(v, (dict, list, set)) else v
+    dst_children = obj.__dict__.get('_modules') or {}
+    for k, child in (src.get('_modules') or {}).items():
+        if child is not None and dst_children.get(k) is not None:
+            _restore_plain_attributes(dst_children[k], child.__dict__)
+
+
 def _reconstruct_persistent_obj(meta):
     """Constructor named by the reference's pickles (persistence.py:181-204)."""
     from .. import dnnlib
@@ -132,6 +175,7 @@ def _reconstruct_persistent_obj(meta):
         if missing or unexpected:
             raise RuntimeError(f'{meta.class_name}: checkpoint does not match the mirror class '
                                f'(missing {missing[:4]}, unexpected {list(unexpected)[:4]})')
+        _restore_plain_attributes(obj, meta.state)
         obj.train(bool(meta.state.get('training', True)))
         requires = {k: v.requires_grad for k, v in tensors.items() if hasattr(v, 'requires_grad')}
         for name, p in obj.named_parameters():

@@ -70,8 +70,12 @@ class _TwoBlockSR(torch.nn.Module):
             extra = set(block_kwargs) - {'noise_mode', 'force_fp32', 'fused_modconv', 'update_emas'}
             if (not extra and not engine.grad_needed(self, ws, x, rgb) and engine.block_supported(self.block0, ws, noise_mode, False)
                     and engine.block_supported(self.block1, ws, noise_mode, False)):
-                img = engine.superresolution(self, rgb.float().permute(0, 2, 3, 1).contiguous(), x.float(), ws, noise_mode=noise_mode,
-                                             force_fp32=bool(block_kwargs.get('force_fp32', False)))
+                img, img0 = engine.superresolution(self, rgb.float().permute(0, 2, 3, 1).contiguous(), x.float(), ws, noise_mode=noise_mode,
+                                                   force_fp32=bool(block_kwargs.get('force_fp32', False)), return_block0_image=True)
+                if not self.BLOCK0_UP and not need:
+                    # reference quirk: SynthesisBlockNoUp does `img.add_(y)` on the tensor it was handed (superresolution.py:283),
+                    # i.e. on the caller's image_raw / semantic_raw view; keep the caller's tensor consistent with that
+                    rgb.copy_(img0.permute(0, 3, 1, 2))
                 return tcconv.nhwc_to_nchw_f32(img)
         x, rgb = self.block0(x, rgb, ws, **block_kwargs)
         x, rgb = self.block1(x, rgb, ws, **block_kwargs)

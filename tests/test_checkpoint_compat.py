@@ -27,6 +27,8 @@ WRITER = textwrap.dedent('''
     import training.triplane_cond as tc
     import training.dual_discriminator as dd
     G = build_generator(tc, SYNTH_CASES[{case!r}])
+    G.neural_rendering_resolution = 40          # training_loop.py:558 mutates this before every snapshot
+    G.rendering_kwargs['density_reg'] = 0.125
     torch.manual_seed(5)
     D = dd.DualDiscriminator(c_dim=25, img_resolution=128, img_channels=3, channel_base=1024, channel_max=16,
                              mapping_kwargs={{}}, epilogue_kwargs={{'mbstd_group_size': 2}})
@@ -61,6 +63,8 @@ def test_reference_pickle_loads_as_mirror_classes(tmp_path, case_name):
     assert data['augment_pipe'] is None and data['training_set_kwargs'] == dict(path='none')
     assert not G.training and not any(p.requires_grad for p in G.parameters())             # pickled in eval / frozen state
     assert G.init_kwargs['rendering_kwargs']['depth_resolution'] == SYNTH_CASES[case_name]['Sc']
+    # attributes mutated after construction come back as pickled (reference persistence.py:197-203 restores __dict__)
+    assert G.neural_rendering_resolution == 40 and G.rendering_kwargs['density_reg'] == 0.125
 
     # same outputs as the reference computed for this seed (tests/golden/synthesis_<case>.npz)
     g = load_golden('synthesis_' + case_name)

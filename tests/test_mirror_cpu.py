@@ -124,3 +124,31 @@ def test_filtered_lrelu_and_dual_discriminator_match_reference():
                           epilogue_kwargs={'mbstd_group_size': 2}).eval().requires_grad_(False)
     out = D({'image': t('dd_image'), 'image_raw': t('dd_image_raw')}, t('dd_c').clone())
     assert rel_err(out.numpy(), g['dd_logits']) < 1e-5
+
+
+def test_copy_params_and_buffers_semantic_fallback(capsys):
+    """reference torch_utils/misc.py:157-176: `*_semantic.*` tensors missing in the source are initialised from the
+    same-named tensors without the `_semantic` suffix (resuming from an EG3D checkpoint)."""
+    import torch
+    from pix2pix3d_b200.torch_utils import misc
+
+    class Src(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.superresolution = torch.nn.Linear(3, 2)
+
+    class Dst(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.superresolution = torch.nn.Linear(3, 2)
+            self.superresolution_semantic = torch.nn.Linear(3, 2)
+            self.other = torch.nn.Linear(2, 2)
+
+    src, dst = Src(), Dst()
+    before = dst.other.weight.clone()
+    with torch.no_grad():
+        misc.copy_params_and_buffers(src, dst, require_all=False)
+    assert torch.equal(dst.superresolution_semantic.weight, src.superresolution.weight)
+    assert torch.equal(dst.superresolution.bias, src.superresolution.bias)
+    assert torch.equal(dst.other.weight, before)
+    assert 'other.weight not found in source module' in capsys.readouterr().out

@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, limit=None):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -30,12 +30,14 @@ def _worker(rank, world, port, name, q):
         g = load_golden('synthesis_' + name)
         G = build_generator(tc, case)
         ws, c = torch.from_numpy(g['ws']), torch.from_numpy(g['c'])
+        if limit is not None:
+            ws, c = ws[:limit], c[:limit]
         B = ws.shape[0]
         lo, hi = sharding.shard_bounds(B, rank, world)
         nrr = case['nrr']
         # replay this shard's slice of the reference's renderer noise
-        jit = torch.from_numpy(g['jitter'])[lo:hi]
-        u = torch.from_numpy(g['u']).reshape(B, nrr * nrr, -1)[lo:hi].reshape((hi - lo) * nrr * nrr, -1)
+        jit = torch.from_numpy(g['jitter'])[:B][lo:hi]
+        u = torch.from_numpy(g['u']).reshape(-1, nrr * nrr, g['u'].shape[-1])[:B][lo:hi].reshape((hi - lo) * nrr * nrr, g['u'].shape[-1])
         it = iter([jit, u])
         o_like, o_rand = torch.rand_like, torch.rand
         torch.rand_like = lambda x, *a, **k: next(it)
@@ -59,9 +61,9 @@ def test_sharded_render_matches_unsharded_reference():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get(timeout=600)
+    out = q.get(timeout=240)
     for p in procs:
-        p.join(timeout=600)
+        p.join(timeout=240)
         assert p.exitcode == 0
     g = load_golden('synthesis_' + name)
     for k in ('image', 'semantic', 'image_raw', 'semantic_raw'):
@@ -69,6 +71,25 @@ def test_sharded_render_matches_unsharded_reference():
         assert rel_err(out[k], g['out_' + k]) < 1e-4, k
     # depth is clamped to the LOCAL batch's depth range (ray_marcher.py:50): identical unless the clamp is active
     assert rel_err(out['image_depth'], g['out_image_depth']) < 1e-3
+
+
+def test_gather_with_an_empty_shard_does_not_deadlock():
+    """Batch of 1 over 2 ranks: rank 1 renders nothing but still takes part in the gather."""
+    name = 'seg_tiny'
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q, 1)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    g = load_golden('synthesis_' + name)
+    for k in ('image', 'semantic', 'image_raw', 'semantic_raw'):
+        assert out[k].shape == g['out_' + k][:1].shape
+        assert rel_err(out[k], g['out_' + k][:1]) < 1e-4, k
 
 
 def test_shard_bounds_cover_batch_exactly():
