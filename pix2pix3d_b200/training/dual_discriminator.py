@@ -1,7 +1,7 @@
 """Dual discriminator of EG3D / pix2pix3D: sees the super-resolved image concatenated with the (resized) raw render.
 
 Mirror of the reference's training/dual_discriminator.py (`filtered_resizing` :86-102, `DualDiscriminator` :107-172,
-`SingleDiscriminator` :21-80). Built from the same DiscriminatorBlock / Epilogue modules, whose FIR and bias_act work
+`SingleDiscriminator` :21-80, `DummyDualDiscriminator` :179-245). Built from the same DiscriminatorBlock / Epilogue modules, whose FIR and bias_act work
 runs on the sm_100a kernels; the convolutions go through `conv2d_gradfix`. Only needed by BASELINE config 5 (train step).
 """
 import numpy as np
@@ -106,3 +106,23 @@ class DualDiscriminator(_DiscBase):
         _ = update_emas
         image_raw = filtered_resizing(img['image_raw'], size=img['image'].shape[-1], f=self.resample_filter)
         return self._trunk(torch.cat([img['image'], image_raw], 1), c, block_kwargs, noise_c=self.disc_c_noise)
+
+
+@persistence.persistent_class
+class DummyDualDiscriminator(_DiscBase):
+    """DualDiscriminator whose raw-image half fades out linearly over 500k/32 calls (:179-245; `raw_fade` starts at 1 and
+    loses 32/500000 per forward, the call that reaches 0 and all later ones see a zeroed raw image)."""
+
+    def __init__(self, c_dim, img_resolution, img_channels, architecture='resnet', channel_base=32768, channel_max=512,
+                 num_fp16_res=4, conv_clamp=256, cmap_dim=None, block_kwargs={}, mapping_kwargs={}, epilogue_kwargs={}):
+        super().__init__()
+        self._build(c_dim, img_resolution, img_channels * 2, architecture, channel_base, channel_max, num_fp16_res, conv_clamp,
+                    cmap_dim, block_kwargs, mapping_kwargs, epilogue_kwargs)
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter([1, 3, 3, 1]))
+        self.raw_fade = 1
+
+    def forward(self, img, c, update_emas=False, **block_kwargs):
+        _ = update_emas
+        self.raw_fade = max(0, self.raw_fade - 1 / (500000 / 32))
+        image_raw = filtered_resizing(img['image_raw'], size=img['image'].shape[-1], f=self.resample_filter) * self.raw_fade
+        return self._trunk(torch.cat([img['image'], image_raw], 1), c, block_kwargs)
