@@ -4,7 +4,9 @@ neural-rendering resolution, 48+48 samples per ray).
 
     python bench.py --gpus 1 --steps K --warmup W                     # this repository (CUDA, libp3d.so)
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...                              # CPU port of the reference path (oracle/)
+    python bench.py --impl reference ...          # the UNMODIFIED reference (baseline/_ref) on the host cores, same config
+    python bench.py --impl reference-cuda ...     # the UNMODIFIED reference on the GPU through its own JIT-built plugins
+    python bench.py --workload {seg2cat_smoke,seg2cat_512,seg2face_512,edge2car_128}     # BASELINE.json configs 1-4
 
 A step is one `G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=128)` of
 TriPlaneSemanticEntangleGenerator on a batch of 4 (BASELINE configs[1]); weights are seeded random, inputs synthetic.
@@ -23,8 +25,31 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = 'seg2cat_512'
+WORKLOAD = 'seg2cat_512'           # BASELINE.json configs[1], the configuration the metric is quoted on
 METRIC = 'rendered images/sec (512^2, 128^2 NeRF res, 96 samples/ray)'
+sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+
+
+def metric_name(workload):
+    from pix2pix3d_b200 import configs
+    w = configs.WORKLOADS[workload]
+    rk = configs.generator_kwargs(workload)['rendering_kwargs']
+    if workload == 'seg2cat_512':
+        return METRIC
+    return (f"rendered images/sec ({w['img_resolution']}^2, {w['nrr']}^2 NeRF res, "
+            f"{rk['depth_resolution'] + rk['depth_resolution_importance']} samples/ray)")
+
+
+def workload_config(workload, B, world, extra=None):
+    """`config` object shared by every arm so that the driver can tell the arms ran the same thing."""
+    from pix2pix3d_b200 import configs
+    w = configs.WORKLOADS[workload]
+    rk = configs.generator_kwargs(workload)['rendering_kwargs']
+    cfg = {'workload': workload, 'batch_per_gpu': B, 'global_batch': B * world, 'neural_rendering_resolution': w['nrr'],
+           'samples_per_ray': rk['depth_resolution'] + rk['depth_resolution_importance'], 'img_resolution': w['img_resolution'],
+           'parallelism': f'dp{world} (batch-sharded, no collective)'}
+    cfg.update(extra or {})
+    return cfg
 
 
 # ---------------------------------------------------------------------------------------------
@@ -125,44 +150,126 @@ def cpu_port_state(batch):
 
 
 def run_reference_arm(args):
-    """`--impl reference`: the reference is Python (it cannot be compiled into oracle/_ref and its source tree does not
-    travel to the GPU box), so this arm times the oracle port of the same path on the host cores. One step = one
-    config-2 image (the workload's unit); steps are capped so the run ends within a few minutes."""
+    """`--impl reference`: the UNMODIFIED reference (baseline/_ref, byte-identical copy of /root/reference) on the host
+    cores -- `G.synthesis` of its own TriPlaneSemanticEntangleGenerator, custom ops on their `_ref` branch, fp32, all host
+    threads, same workload / batch / seeds / inputs as the product arm. Steps are capped by a time budget so the run ends
+    within a few minutes. Falls back to the oracle port only if baseline/_ref is absent."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    state = cpu_port_state(1)
-    t0 = time.perf_counter()
-    cpu_port_step(state)                     # warm-up 1 (also sizes the run)
-    t_step = time.perf_counter() - t0
-    warm = max(1, min(args.warmup, int(60 / max(t_step, 1e-3))))
-    for _ in range(warm - 1):
-        cpu_port_step(state)
-    steps = max(1, min(args.steps, int(200 / max(t_step, 1e-3))))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_port_step(state)
-    dt = time.perf_counter() - t0
-    value = steps / dt
+    import ref_harness as rh
+    from pix2pix3d_b200 import configs
+    w = configs.WORKLOADS[args.workload]
+    B = args.batch or w['batch']
     cores = os.cpu_count()
-    sample = 'G.synthesis of 1 image at config-2 shapes (256^2 planes, 128^2 rays x 96 samples, two 8XDC SR stacks), fp32'
+    if rh.available():
+        r = rh.time_synthesis(args.workload, 'cpu', B, args.steps, args.warmup, budget_s=float(os.environ.get('P3D_REF_BUDGET_S', '240')))
+        value, ms_step, steps, warm = r['images_per_s'], r['ms_per_step'], r['steps'], r['warmup']
+        kind = 'reference'
+        sample = (f"{steps} steps x G.synthesis of {B} images ({args.workload}) through the unmodified reference on CPU "
+                  f"(torch {cores} threads, _ref ops, fp32), after {warm} warm-up steps")
+        stages = r['stage_ms_per_step']
+    else:
+        state = cpu_port_state(1)
+        cpu_port_step(state)
+        t0 = time.perf_counter()
+        cpu_port_step(state)
+        dt = time.perf_counter() - t0
+        value, ms_step, steps, warm, kind, stages = 1.0 / dt, 1000 * dt, 1, 1, 'port', None
+        sample = '1 image through oracle/p3d_oracle (baseline/_ref missing)'
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': warm, 'ms_per_step': 1000 * dt / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'batch_per_step': 1, 'device': 'cpu'},
-        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'impl': 'reference', 'metric': metric_name(args.workload), 'value': value, 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args.workload, B, 1, {'device': 'cpu', 'launch': 'reference G.synthesis, eager'}),
+        'cpu_baseline': {'value': value, 'unit': 'images/s', 'cores': cores, 'kind': kind, 'sample': sample,
+                         'stage_ms_per_step': stages},
         'e2e': {'value': value, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def run_reference_cuda_arm(args):
+    """`--impl reference-cuda`: the reference's stock CUDA path on one B200 (BASELINE.md plan item 2, the ">= 5x" baseline):
+    its plugins are JIT-built on first use by its own torch_utils/custom_ops.py:61, convolutions are cuDNN, SR runs in fp16 as
+    shipped; a second measurement uses force_fp32. CUDA events, inputs resident."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    import ref_harness as rh
+    from pix2pix3d_b200 import configs
+    if not rh.available():
+        print(json.dumps({'impl': 'reference-cuda', 'unavailable': 'baseline/_ref missing (run baseline/vendor_reference.py)'}), flush=True)
+        return
+    if not torch.cuda.is_available():
+        print(json.dumps({'impl': 'reference-cuda', 'unavailable': 'no CUDA device'}), flush=True)
+        return
+    w = configs.WORKLOADS[args.workload]
+    B = args.batch or w['batch']
+    sampler = ClockSampler(0)
+    sampler.start()
+    r = rh.time_synthesis(args.workload, 'cuda', B, args.steps, max(args.warmup, 5), log=lambda m: print(m, file=sys.stderr))
+    clocks = sampler.stop()
+    r32 = rh.time_synthesis(args.workload, 'cuda', B, args.steps, max(args.warmup, 5), force_fp32=True, stage_split=False)
+    line = {
+        'impl': 'reference-cuda', 'metric': metric_name(args.workload), 'value': r['images_per_s'], 'unit': 'images/s',
+        'n_gpus': 1, 'steps': r['steps'], 'warmup': r['warmup'], 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': r['dtype'], 'data': 'synthetic',
+        'config': workload_config(args.workload, B, 1, {'device': 'cuda', 'launch': 'reference G.synthesis, eager, stock plugins + cuDNN'}),
+        'stage_ms_per_step': r['stage_ms_per_step'], 'first_step_s': r['first_step_s'],
+        'force_fp32': {'value': r32['images_per_s'], 'ms_per_step': r32['ms_per_step']},
+        'rays_per_s': r['images_per_s'] * w['nrr'] ** 2, 'clocks': clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def stock_cuda_leg(args, B, timeout_s=900):
+    """Run `--impl reference-cuda` in a child process (its module names `training.*` stay out of this process and a JIT
+    failure cannot take the product measurement down) and return its JSON line."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference-cuda', '--workload', args.workload, '--steps', str(args.steps),
+           '--warmup', str(args.warmup), '--batch', str(B)]
+    env = {k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK')}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, env=env)
+    except subprocess.TimeoutExpired:
+        return {'unavailable': f'reference-cuda child exceeded {timeout_s} s'}
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith('{'):
+            try:
+                return json.loads(ln)
+            except ValueError:
+                pass
+    return {'unavailable': 'reference-cuda child printed no JSON line', 'rc': r.returncode, 'stderr_tail': r.stderr[-1500:]}
+
+
+def render_traffic(workload, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused render kernel, from the committed ncu --set full
+    summary (profiles/render_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep)."""
+    path = os.path.join(ROOT, 'profiles', 'render_traffic.json')
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        for e in t['captures']:
+            if e['workload'] == workload and e['batch'] == B:
+                return e['dram_bytes_per_launch'], e.get('source')
+    except (OSError, ValueError, KeyError):
+        pass
+    return None, None
+
+
 # ---------------------------------------------------------------------------------------------
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-cuda'])
+    ap.add_argument('--workload', default=WORKLOAD, choices=['seg2cat_smoke', 'seg2cat_512', 'seg2face_512', 'edge2car_128'],
+                    help='BASELINE.json configs 1-4 (default: configs[1], the metric\'s configuration)')
+    ap.add_argument('--no-stock-cuda', action='store_true', help='skip the reference stock-CUDA leg (child process, ~1-2 min incl. plugin JIT)')
     ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (default: the workload batch, 4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--force-fp32', action='store_true', help='run the SR stacks in fp32 (reference default is fp16)')
@@ -171,6 +278,10 @@ def main():
     if args.impl == 'reference':
         run_reference_arm(args)
         return
+    if args.impl == 'reference-cuda':
+        run_reference_cuda_arm(args)
+        return
+    WORKLOAD = args.workload
     args.warmup = max(args.warmup, 3)
 
     import torch
@@ -197,7 +308,7 @@ def main():
     S = rk['depth_resolution'] + rk['depth_resolution_importance']
     # every rank renders its own batch (weak scaling, no collective on the render path)
     ws_host = configs.synthetic_ws(B, G.backbone.num_ws, 1 + rank).pin_memory()
-    c_host = configs.camera_labels(B, 2 + rank).pin_memory()
+    c_host = configs.camera_labels(B, 2 + rank, w['preset']).pin_memory()
     ws, c = ws_host.to(dev), c_host.to(dev)
     syn_kw = dict(noise_mode='const', neural_rendering_resolution=nrr)
     if args.force_fp32:
@@ -322,14 +433,15 @@ def main():
     peaks, peak_src = measured_peaks()
     alg_bytes = configs.render_algorithmic_bytes(B, nrr * nrr, S)
     roofline = None
+    traffic, traffic_src = render_traffic(WORKLOAD, B)
     if render_ms:
         t_k = sum(render_ms) / len(render_ms) / 1000.0
         achieved = alg_bytes / t_k / 1e9
         roofline = {'kernel': 'render_fwd_tc_kernel' if native.render_impl in ('auto', 'tc') else 'render_fwd_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': achieved / peaks['hbm_gbs'],
-                    # dram__bytes_read + write of this kernel at this workload from the ncu --set full capture summarised in
-                    # profiles/r01_render_fwd_tc_ncu.md (config 2, B=4); not re-measured here
-                    'traffic': 100.1e6 if (WORKLOAD == 'seg2cat_512' and B == 4) else None, 'peak_source': peak_src,
+                    # dram__bytes_read + write per launch of this kernel at this workload, read from the committed ncu --set full
+                    # summary (profiles/render_traffic.json); null when no capture of this workload/batch exists
+                    'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                     'kernel_ms': t_k * 1000, 'algorithmic_bytes': alg_bytes, 'share_of_step': t_k * 1000 / (ms / args.steps),
                     'rays_per_s': B * nrr * nrr / t_k}
 
@@ -348,26 +460,44 @@ def main():
                            'note': 'fp32 backbone layers execute 3 fp16 passes per algorithmic FLOP (hi/lo split); '
                                    'event pairs around single launches in eager steps'}
 
-    # ---- CPU baseline: the oracle port on the host cores, one image ----------------------------
+    # ---- CPU baseline: the unmodified reference on the host cores, same batch, bounded sample ------
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        state = cpu_port_state(1)
-        t0 = time.perf_counter()
-        cpu_port_step(state)
-        dt = time.perf_counter() - t0
-        cpu_baseline = {'value': 1.0 / dt, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
-                        'sample': '1 image of the config-2 workload through oracle/p3d_oracle (numpy + ATen conv), fp32, '
-                                  f'{dt:.1f} s'}
+        import ref_harness as rh
+        if rh.available():
+            r = rh.time_synthesis(WORKLOAD, 'cpu', B, steps=2, warmup=2, budget_s=30)
+            cpu_baseline = {'value': r['images_per_s'], 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                            'sample': f"{r['steps']} steps x G.synthesis of {B} images through the unmodified reference on CPU "
+                                      f"(baseline/_ref, _ref ops, fp32, {os.cpu_count()} torch threads) after {r['warmup']} warm-up steps, "
+                                      f"{r['ms_per_step'] / 1000:.1f} s per step",
+                            'stage_ms_per_step': r['stage_ms_per_step']}
+        else:
+            state = cpu_port_state(1)
+            t0 = time.perf_counter()
+            cpu_port_step(state)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {'value': 1.0 / dt, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+                            'sample': f'1 image through oracle/p3d_oracle (baseline/_ref missing), {dt:.1f} s'}
+
+    # ---- reference stock CUDA path on this GPU (child process) ---------------------------------------
+    stock_cuda, vs_stock = None, None
+    if world == 1 and not args.no_stock_cuda:
+        torch.cuda.empty_cache()
+        sc = stock_cuda_leg(args, B)
+        stock_cuda = {k: sc.get(k) for k in ('value', 'unit', 'ms_per_step', 'steps', 'warmup', 'dtype', 'stage_ms_per_step',
+                                             'force_fp32', 'first_step_s', 'unavailable', 'stderr_tail', 'clocks') if k in sc}
+        if sc.get('value'):
+            vs_stock = {'device_timed': value / sc['value'], 'e2e_over_stock_device_timed': e2e_value / sc['value'],
+                        'vs_force_fp32': value / sc['force_fp32']['value'] if sc.get('force_fp32') else None}
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': metric_name(WORKLOAD), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32' if args.force_fp32 else 'f32 (backbone, renderer) + f16 (super-resolution, as the reference)',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': B * world, 'neural_rendering_resolution': nrr,
-                   'samples_per_ray': S, 'img_resolution': w['img_resolution'], 'parallelism': f'dp{world} (batch-sharded, no collective)',
+        'config': workload_config(WORKLOAD, B, world, {
                    'launch': 'CUDA graph replay of G.synthesis (pix2pix3d_b200.graphs.GraphedSynthesis)' if graphed is not None else 'eager',
-                   'l2_policy': 'no flush: per-step working set (planes 100 MB + SR activations > 2 GB) exceeds the 126 MB L2'},
+                   'l2_policy': 'no flush: per-step working set (planes 100 MB + SR activations > 2 GB) exceeds the 126 MB L2'}),
         'rays_per_s': world * B * nrr * nrr * args.steps / (ms / 1000.0),
         'gpu_launches': launches,
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -375,6 +505,7 @@ def main():
                 'pipeline': 'pinned-host ws/c in and image+semantic out every step; read-back of step i overlaps step i+1 '
                             '(two staging buffers, copy stream); timed region ends after the last read-back'},
         'clocks': clocks, 'roofline': roofline, 'roofline_tensor': roofline_tensor, 'cpu_baseline': cpu_baseline,
+        'stock_cuda': stock_cuda, 'vs_stock_cuda': vs_stock,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -392,6 +392,100 @@ def golden_loss_ops():
     print('loss_ops', len(save), 'arrays')
 
 
+# ---------------------------------------------------------------------------------------------
+# Full-size cases at the BASELINE.json configurations (configs[1], [2] as released = 3b, [3]): the reference's G.synthesis on
+# CPU with the constructor arguments train.py assembles (pix2pix3d_b200.configs.generator_kwargs -- a table of arguments, no
+# code of this repository runs), seeded weights and seeded inputs. Stored: the seeds, a digest of the weights, SUBSAMPLED
+# outputs, and for a ray subset the reference's own importance-sampling indices (torch.searchsorted, renderer.py:240), fine
+# depths (:252) and the sort permutation of unify_samples (:162), so that the GPU tests can score the bookkeeping of the
+# fused kernel against the reference at the metric's scale.
+FULLSIZE_CASES = {
+    'full_seg2cat': dict(workload='seg2cat_512', B=1, seed=0, input_seed=101),
+    'full_seg2face': dict(workload='seg2face_512', B=1, seed=0, input_seed=102),
+    'full_edge2car': dict(workload='edge2car_128', B=2, seed=0, input_seed=103),
+}
+RAY_STRIDE = 61
+
+
+def fullsize_inputs(case, num_ws, nrr, Sc, Sf):
+    """Inputs of a full-size case from its seeds (shared with tests/test_gpu_fullsize.py)."""
+    from pix2pix3d_b200 import configs
+    B, s = case['B'], case['input_seed']
+    preset = configs.WORKLOADS[case['workload']]['preset']
+    ws = configs.synthetic_ws(B, num_ws, s)
+    c = configs.camera_labels(B, s + 1, preset)
+    g = torch.Generator().manual_seed(s + 2)
+    jitter = torch.rand(B, nrr * nrr, Sc, 1, generator=g)
+    u = torch.rand(B * nrr * nrr, Sf, generator=g)
+    return ws, c, jitter, u
+
+
+def golden_fullsize():
+    import training.triplane_cond as ref_tc
+    repo = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+    sys.path.append(repo)
+    from pix2pix3d_b200 import configs
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 else None
+    for name, case in FULLSIZE_CASES.items():
+        if only is not None and name not in only:
+            continue
+        kw = configs.generator_kwargs(case['workload'])
+        kw['mapping_kwargs'] = dict(class_name='training.networks_stylegan2.MappingNetwork', num_layers=2)
+        torch.manual_seed(case['seed'])
+        G = ref_tc.TriPlaneSemanticEntangleGenerator(**kw).eval().requires_grad_(False)
+        gen = torch.Generator().manual_seed(case['seed'] + 1)
+        for pname, p in G.named_parameters():
+            if pname.endswith('noise_strength'):
+                p.copy_(torch.randn([], generator=gen) * 0.1)
+        w = configs.WORKLOADS[case['workload']]
+        rk = kw['rendering_kwargs']
+        nrr, Sc, Sf = w['nrr'], rk['depth_resolution'], rk['depth_resolution_importance']
+        ws, c, jitter, u = fullsize_inputs(case, G.backbone.num_ws, nrr, Sc, Sf)
+        rec = {}
+        R = G.renderer
+        o_imp, o_unify, o_march = R.sample_importance, R.unify_samples, R.ray_marcher.forward
+        o_ss = torch.searchsorted
+        marches, feats = [], []
+
+        def imp(z, wgt, n):
+            out = o_imp(z, wgt, n); rec['depths_fine'] = out.clone(); return out
+
+        def unify(d1, c1, s1, d2, c2, s2):
+            rec['perm'] = torch.sort(torch.cat([d1, d2], -2), dim=-2, stable=True)[1][..., 0].clone()
+            return o_unify(d1, c1, s1, d2, c2, s2)
+
+        def march(colors, dens, depths, ro):
+            out = o_march(colors, dens, depths, ro); marches.append(out[2].clone()); feats.append(out[0].clone()); return out
+
+        def ss(cdf, uu, **k):
+            out = o_ss(cdf, uu, **k); rec['inds'] = out.clone(); return out
+
+        R.sample_importance, R.unify_samples, R.ray_marcher.forward, torch.searchsorted = imp, unify, march, ss
+        it = iter([jitter, u])
+        o_like, o_rand = torch.rand_like, torch.rand
+        torch.rand_like, torch.rand = (lambda x, *a, **k: next(it)), (lambda *a, **k: next(it))
+        try:
+            with torch.no_grad():
+                out = G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=nrr)
+        finally:
+            torch.rand_like, torch.rand, torch.searchsorted = o_like, o_rand, o_ss
+            R.sample_importance, R.unify_samples, R.ray_marcher.forward = o_imp, o_unify, o_march
+        B, Rn = case['B'], nrr * nrr
+        rays = torch.arange(0, Rn, RAY_STRIDE)
+        save = dict(workload=case['workload'], B=B, seed=case['seed'], input_seed=case['input_seed'], ray_stride=RAY_STRIDE,
+                    out_image_sub=out['image'][:, :, 3::8, 5::8].contiguous(), out_semantic_sub=out['semantic'][:, :, 3::8, 5::8].contiguous(),
+                    out_image_raw=out['image_raw'], out_image_depth=out['image_depth'],
+                    out_semantic_raw=out['semantic_raw'][:, :, ::2, ::2].contiguous(),
+                    feat_rays=feats[-1].reshape(B, Rn, -1)[:, rays], weights_coarse_rays=marches[0].reshape(B, Rn, -1)[:, rays],
+                    weights_final_rays=marches[-1].reshape(B, Rn, -1)[:, rays],
+                    depths_fine_rays=rec['depths_fine'].reshape(B, Rn, -1)[:, rays], perm_rays=rec['perm'].reshape(B, Rn, -1)[:, rays].to(torch.int16),
+                    inds_rays=rec['inds'].reshape(B, Rn, -1)[:, rays].to(torch.int16))
+        arrays = {k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in save.items()}
+        arrays['state_digest'] = np.frombuffer(state_digest(G).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, f'{name}.npz'), **arrays)
+        print('fullsize', name, {k: tuple(v.shape) for k, v in out.items()}, os.path.getsize(os.path.join(OUT, f'{name}.npz')) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
     assert os.path.isdir(REF), 'the reference checkout is only available in the authoring container'
     sys.path.insert(0, REF)
@@ -408,3 +502,5 @@ if __name__ == '__main__':
         golden_semgen()
     if 'loss_ops' in which:
         golden_loss_ops()
+    if 'fullsize' in which:
+        golden_fullsize()

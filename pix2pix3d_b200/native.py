@@ -18,6 +18,9 @@ render_impl = 'auto'
 
 # when set to a list, render_fwd appends ('render_fwd', start_event, end_event) around its launch (bench.py)
 kernel_events = None
+# when set to a dict, every render_fwd call also writes the kernel's bookkeeping (importance indices, fine depths, sort
+# permutation, interval weights) and leaves it there: lets tests score the bookkeeping of a whole G.synthesis call
+render_debug_sink = None
 
 
 def _f32c(t):
@@ -166,7 +169,8 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
     a.white_back = 1 if white_back else 0
     a.out_feat, a.out_depth, a.out_wsum = feat.data_ptr(), depth.data_ptr(), wsum.data_ptr()
     dbg = {}
-    if debug:
+    want_debug = debug or render_debug_sink is not None
+    if want_debug:
         S = Sc + Sf
         dbg['weights_final'] = torch.empty(B, R, S - 1, device=dev, dtype=torch.float32)
         dbg['perm'] = torch.empty(B, R, S, device=dev, dtype=torch.int32)
@@ -205,6 +209,8 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
         kernel_events.append(('render_fwd', ev[0], ev[1]))
     _lib.check(st, 'p3d_render_fwd')
     _lib.bump()
+    if render_debug_sink is not None:
+        render_debug_sink.update(dbg, feat=feat, depth=depth, wsum=wsum)
     if debug:
         return feat, depth, wsum, dbg
     return feat, depth, wsum

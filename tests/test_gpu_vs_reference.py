@@ -1,0 +1,99 @@
+"""Live comparison with the reference's own PyTorch/CUDA path (the oracle of record) on the GPU box.
+
+baseline/_ref is a byte-identical copy of the reference (baseline/vendor_reference.py; git-ignored, shipped by gpurun). Its
+modules import under their own names (`training.*`, `torch_utils.*`), the product's under `pix2pix3d_b200.*`, so both
+generators live in one process with identical seeded weights and identical injected renderer noise. The reference's CUDA
+plugins are JIT-built by its own custom_ops.get_plugin on first use (about a minute)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_err
+
+sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+import ref_harness as rh  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not rh.available(), reason='baseline/_ref not vendored')]
+
+
+def _both(workload, batch, force_fp32, seed_in=7):
+    from pix2pix3d_b200 import configs
+    dev = torch.device('cuda')
+    torch.backends.cudnn.allow_tf32 = False          # the reference's fp32 convolutions must be true fp32 for a 1e-3 comparison
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = configs.WORKLOADS[workload]
+    G_ref = rh.build_generator(workload, seed=0, device=dev)
+    G = configs.build_generator(workload, seed=0, device=dev, with_mapping=False)
+    sd_r, sd = G_ref.state_dict(), G.state_dict()
+    assert sd_r.keys() == sd.keys() and all(torch.equal(sd_r[k], sd[k]) for k in sd), 'arms must hold identical weights'
+    rk = G.rendering_kwargs
+    nrr, Sc, Sf = w['nrr'], rk['depth_resolution'], rk['depth_resolution_importance']
+    ws = configs.synthetic_ws(batch, G.backbone.num_ws, seed_in).to(dev)
+    c = configs.camera_labels(batch, seed_in + 1, w['preset']).to(dev)
+    g = torch.Generator().manual_seed(seed_in + 2)
+    jitter = torch.rand(batch, nrr * nrr, Sc, 1, generator=g).to(dev)
+    u = torch.rand(batch * nrr * nrr, Sf, generator=g).to(dev)
+    kw = dict(noise_mode='const', neural_rendering_resolution=nrr, force_fp32=force_fp32)
+    with torch.no_grad():
+        with rh.replay_rand(jitter, u):
+            out_ref = G_ref.synthesis(ws, c, **kw)
+        with rh.replay_rand(jitter, u):
+            out = G.synthesis(ws, c, **kw)
+    return out, out_ref
+
+
+@pytest.mark.parametrize('workload,batch', [('seg2cat_512', 2), ('edge2car_128', 3)])
+def test_synthesis_matches_reference_cuda_path_fp32(workload, batch):
+    out, out_ref = _both(workload, batch, True)
+    errs = {k: rel_err(out[k].float().cpu().numpy(), out_ref[k].float().cpu().numpy()) for k in out_ref}
+    print('VS-REFERENCE-CUDA fp32', workload, errs)
+    for k, e in errs.items():
+        assert e < 1e-3, (k, errs)
+
+
+def test_synthesis_matches_reference_cuda_path_default_dtypes():
+    """SR in fp16 on both sides (superresolution.py:304): the two fp16 paths round differently, so the bound is fp16-sized."""
+    out, out_ref = _both('seg2cat_512', 2, False)
+    errs = {k: rel_err(out[k].float().cpu().numpy(), out_ref[k].float().cpu().numpy()) for k in out_ref}
+    print('VS-REFERENCE-CUDA default dtypes', errs)
+    for k in ('image_raw', 'image_depth', 'semantic_raw'):
+        assert errs[k] < 1e-3, (k, errs)
+    for k in ('image', 'semantic'):
+        assert errs[k] < 2e-2, (k, errs)
+
+
+def test_reference_op_wrappers_run_on_libp3d_plugins():
+    """the reference's own torch_utils/ops/{bias_act,upfirdn2d}.py, unmodified, with this package's
+    `custom_ops.get_plugin` objects in place of the JIT-built pybind modules."""
+    rh.import_reference()
+    import torch_utils.ops.bias_act as r_ba
+    import torch_utils.ops.upfirdn2d as r_up
+    from pix2pix3d_b200.torch_utils import custom_ops as ours
+    dev = torch.device('cuda')
+    saved = (r_ba._plugin, r_up._plugin)
+    r_ba._plugin = ours.get_plugin('bias_act_plugin', sources=['bias_act.cpp', 'bias_act.cu'])
+    r_up._plugin = ours.get_plugin('upfirdn2d_plugin', sources=['upfirdn2d.cpp', 'upfirdn2d.cu'])
+    try:
+        torch.manual_seed(0)
+        x = torch.randn(3, 8, 33, 31, device=dev, requires_grad=True)
+        b = torch.randn(8, device=dev, requires_grad=True)
+        for act in ('lrelu', 'swish', 'linear', 'sigmoid'):
+            y = r_ba.bias_act(x, b, act=act, clamp=1.5, impl='cuda')
+            y_ref = r_ba.bias_act(x, b, act=act, clamp=1.5, impl='ref')
+            assert rel_err(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < 1e-5, act
+            gx, gb = torch.autograd.grad(y.square().sum(), [x, b])
+            gx_r, gb_r = torch.autograd.grad(y_ref.square().sum(), [x, b])
+            assert rel_err(gx.cpu().numpy(), gx_r.cpu().numpy()) < 1e-4 and rel_err(gb.cpu().numpy(), gb_r.cpu().numpy()) < 1e-4, act
+        f = r_up.setup_filter([1, 3, 3, 1], device=dev)
+        for kw in (dict(up=2, padding=[2, 1, 2, 1], gain=4), dict(down=2, padding=[1, 1, 1, 1]), dict(padding=[1, 1, 1, 1], gain=4)):
+            y = r_up.upfirdn2d(x, f, impl='cuda', **kw)
+            y_ref = r_up.upfirdn2d(x, f, impl='ref', **kw)
+            assert rel_err(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < 1e-5, kw
+            (gx,) = torch.autograd.grad(y.square().sum(), [x])
+            (gx_r,) = torch.autograd.grad(y_ref.square().sum(), [x])
+            assert rel_err(gx.cpu().numpy(), gx_r.cpu().numpy()) < 1e-4, kw
+    finally:
+        r_ba._plugin, r_up._plugin = saved
