@@ -9,8 +9,12 @@
 //   * hidden activations go TMEM -> registers (softplus) -> TMEM as packed fp16 hi/lo and feed layer 2 straight
 //     from TMEM (A-from-TMEM MMA), three passes again; colours come back with tcgen05.ld and are reduced per ray
 //     with warp shuffles using the coefficient form rgb = sum_j c_j (w_{j-1} + w_j)/2.
-//   The sigma-only pre-passes (coarse / fine densities) use layer 1 on the tensor core and a 64-term CUDA-core dot.
+//   The density pre-passes (coarse / fine) run layer 1 of the sigma net on the tensor core, take sigma as a 64-term fp32
+//   dot of the hidden row and -- since that net's softplus'd hidden row is in registers anyway -- pack it and issue ITS
+//   layer 2 right there: the 32 colour pre-activations of the sigma net stay parked in TMEM (32 columns per tile) until the
+//   ray's weights are known, so the colour pass evaluates only the OTHER net (64 instead of 128 softplus per sample).
 #include <cstdlib>
+#include <type_traits>
 #include "render_tc.cuh"
 
 namespace p3d {
@@ -97,7 +101,10 @@ struct TcRenderParams {
 
 
 constexpr int kTcThreads = 384;
-constexpr int kTcColsPerGroup = 160;   // D1: [0,128)  D2: [128,160)
+// TMEM columns of a group: D1 [0,64) hidden pre-activations / packed hidden of the net in flight; [64,96) parked colour
+// pre-activations of the sigma net, coarse tile; [96,128) the same for the fine tile; D2 [128,160) colours of the other net
+constexpr int kTcColsPerGroup = 160;
+constexpr int kTcColPark = 64, kTcColD2 = 128;
 
 __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRenderParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -142,8 +149,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
     const uint32_t tmem_row = tmem_grp + ((uint32_t)(q * 32) << 16);      // this thread's lane quarter
     uint32_t bar_phase = 0;
     const uint32_t w1a = tc::smem_u32(smem + kTcW1A), w1b = tc::smem_u32(smem + kTcW1B);
-    const uint32_t idesc_n128 = tc::umma_idesc_f16(128, 128, 0), idesc_n64 = tc::umma_idesc_f16(128, 64, 0),
-                   idesc_n32 = tc::umma_idesc_f16(128, 32, 0);
+    const uint32_t idesc_n64 = tc::umma_idesc_f16(128, 64, 0), idesc_n32 = tc::umma_idesc_f16(128, 32, 0);
     const int sig = a.sigma_net;
 
     // layer 1 on this group's feature tile: D1[:, 0:ncols) = [hi|lo] x W^T   (issued by the group leader)
@@ -157,9 +163,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
         for (int k = 0; k < 2; ++k) tc::umma_f16(tmem_grp, da + 2 * k, dbb + 2 * k, idesc, 1);        // hi*Wlo
         tc::umma_commit(&mma_bar[grp]);
     };
-    // layer 2 for one net: D2 = A2hi*W2hi + A2lo*W2hi + A2hi*W2lo, A2 packed fp16 in TMEM cols [net*64, net*64+64)
-    auto issue_layer2 = [&](int net) {
-        const uint32_t ahi = tmem_grp + net * 64, alo = ahi + 32, d2 = tmem_grp + 128;
+    // layer 2 for one net: D[dcol, dcol+32) = A2hi*W2hi + A2lo*W2hi + A2hi*W2lo, A2 packed fp16 in TMEM cols [0, 64)
+    auto issue_layer2 = [&](int net, int dcol) {
+        const uint32_t ahi = tmem_grp, alo = ahi + 32, d2 = tmem_grp + dcol;
         const uint64_t bh = tc::umma_desc_k128(tc::smem_u32(smem + kTcW2H + net * 8192));
         const uint64_t bl = tc::umma_desc_k128(tc::smem_u32(smem + kTcW2L + net * 8192));
 #pragma unroll
@@ -178,23 +184,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
         const TcPlaneView pv{a.planes_nhwc, a.H, a.W, P.img_stride, P.plane_stride, P.pix_stride};
         tc_gather_rows(pv, feat + tile * 16384, q, lane, valid, b, px, py, pz);
     };
-    // sigma of this thread's row after layer 1 of the sigma net landed in D1[:, 0:64)
-    auto sigma_from_tmem = [&]() -> float {
-        float acc0 = b2s[sig], acc1 = 0.f;
+    // hidden row of `net` (pre-activations in D1[:, 0:64)) -> softplus -> packed fp16 hi (cols 0..31) | lo (cols 32..63) in
+    // place = the A operand of layer 2; with WANT_SIGMA also sigma = the fp32 dot with the sigma row of W2 (returned)
+    auto hidden_to_tmem = [&](int net, auto want_sigma) -> float {
+        constexpr bool kSigma = decltype(want_sigma)::value;
+        uint32_t ph[32], pl[32];
+        float acc0 = kSigma ? b2s[net] : 0.f, acc1 = 0.f;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tc::tmem_ld_32x32(tmem_row + half * 32, v);
+            uint32_t vv[32];
+            tc::tmem_ld_32x32(tmem_row + half * 32, vv);
             tc::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-                const int jj = half * 32 + j;
-                acc0 = fmaf(w2s[sig * 64 + jj], softplus2(__uint_as_float(v[j]) + b1[sig * 64 + jj]), acc0);
-                acc1 = fmaf(w2s[sig * 64 + jj + 1], softplus2(__uint_as_float(v[j + 1]) + b1[sig * 64 + jj + 1]), acc1);
+                const int jj = net * 64 + half * 32 + j;
+                const float h0 = softplus2(__uint_as_float(vv[j]) + b1[jj]);
+                const float h1 = softplus2(__uint_as_float(vv[j + 1]) + b1[jj + 1]);
+                if (kSigma) { acc0 = fmaf(w2s[jj], h0, acc0); acc1 = fmaf(w2s[jj + 1], h1, acc1); }
+                const __half2 hh = __floats2half2_rn(h0, h1);
+                const float2 back = __half22float2(hh);
+                const __half2 ll = __floats2half2_rn(h0 - back.x, h1 - back.y);
+                ph[half * 16 + j / 2] = *reinterpret_cast<const uint32_t*>(&hh);
+                pl[half * 16 + j / 2] = *reinterpret_cast<const uint32_t*>(&ll);
             }
         }
+        tc::tmem_st_32x32(tmem_row, ph);
+        tc::tmem_st_32x32(tmem_row + 32, pl);
+        tc::tmem_st_wait();
         return acc0 + acc1;
     };
+    const std::true_type with_sigma{};
+    const std::false_type no_sigma{};
 
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         const int ray0 = tile * RT;
@@ -212,6 +232,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
 
         // ---- P1/P2: coarse gather + sigma -------------------------------------------------------------
         float dC = 0.f;
+        bool park_pending = false;
         if (grpC) {
             float px = 0.f, py = 0.f, pz = 0.f;
             if (vC) {
@@ -227,8 +248,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             group_sync();
             if (m == 0) issue_layer1(grp, sig * 64, idesc_n64);
             wait_mma();
-            const float sg = sigma_from_tmem();
+            const float sg = hidden_to_tmem(sig, with_sigma);
             if (vC) { rbC[L.o_dC + sC] = dC; rbC[L.o_sC + sC] = sg; }
+            group_sync();                                           // every row of the tile has its packed hidden in TMEM
+            if (m == 0) issue_layer2(sig, kTcColPark);              // colours of the sigma net, parked until the colour pass
+            park_pending = true;                                    // its commit is consumed before the next commit is issued
         }
         tc::tc_fence_before();
         __syncthreads();
@@ -274,11 +298,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
                 }
                 gather_rows(L.tiles_c + grp, vF, bF, px, py, pz);
                 tc::fence_proxy_async();
+                if (park_pending) { wait_mma(); park_pending = false; }     // the coarse tile's parked layer 2 (long done)
                 group_sync();
                 if (m == 0) issue_layer1(L.tiles_c + grp, sig * 64, idesc_n64);
                 wait_mma();
-                const float sg = sigma_from_tmem();
+                const float sg = hidden_to_tmem(sig, with_sigma);
                 if (vF) { rbF[L.o_dF + sF] = dF; rbF[L.o_sF + sF] = sg; }
+                group_sync();
+                if (m == 0) issue_layer2(sig, kTcColPark + 32);
+                park_pending = true;
             }
             tc::tc_fence_before();
             __syncthreads();
@@ -293,7 +321,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             int cnt = 0;
             if (Sf > 0 && scal[4 * rC + 1] != 0.f) cnt = sC;
             else for (int i = 0; i < Sc; ++i) { float v = dc[i]; cnt += (v < dC) || (v == dC && i < sC); }
-            for (int k = 0; k < Sf; ++k) cnt += (df[k] < dC);
+            // sample counts are multiples of 8 and the per-ray arrays 16-byte aligned: four depths per LDS.128
+            const float4* df4 = reinterpret_cast<const float4*>(df);
+            for (int k = 0; k < (Sf >> 2); ++k) {
+                const float4 f = df4[k];
+                cnt += (f.x < dC) + (f.y < dC) + (f.z < dC) + (f.w < dC);
+            }
             rankC = cnt;
             rbC[L.o_sd + cnt] = dC;
             rbC[L.o_ss + cnt] = rbC[L.o_sC + sC];
@@ -311,7 +344,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
             } else {
                 for (int i = 0; i < Sc; ++i) cnt += (dc[i] <= dFv);
             }
-            for (int k = 0; k < Sf; ++k) { float v = df[k]; cnt += (v < dFv) || (v == dFv && k < sF); }
+            // stable rank among the fine samples: #(v < d) over all + #(v == d) over the earlier ones
+            const float4* df4 = reinterpret_cast<const float4*>(df);
+            for (int k = 0; k < (Sf >> 2); ++k) {
+                const float4 f = df4[k];
+                const int k0 = 4 * k;
+                cnt += (f.x < dFv) + (f.y < dFv) + (f.z < dFv) + (f.w < dFv);
+                cnt += ((f.x == dFv) & (k0 < sF)) + ((f.y == dFv) & (k0 + 1 < sF)) + ((f.z == dFv) & (k0 + 2 < sF)) + ((f.w == dFv) & (k0 + 3 < sF));
+            }
             rankF = cnt;
             rbF[L.o_sd + cnt] = dFv;
             rbF[L.o_ss + cnt] = rbF[L.o_sF + sF];
@@ -358,38 +398,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
                 const float wl = rank > 0 ? rb[L.o_w + rank - 1] : 0.f;
                 coef = 0.5f * (wl + rb[L.o_w + rank]);
             }
-            group_sync();      // every row of the group is done with D1/D2 of the previous step
-            if (m == 0) issue_layer1((pass == 0 ? 0 : L.tiles_c) + grp, 0, n_nets == 2 ? idesc_n128 : idesc_n64);
-            wait_mma();
-#pragma unroll 1
-            for (int net = 0; net < n_nets; ++net) {
-                // hidden: D1[:, net*64 .. +64) -> softplus -> packed fp16 hi (32 cols) | lo (32 cols), in place
-                uint32_t ph[32], pl[32];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t vv[32];
-                    tc::tmem_ld_32x32(tmem_row + net * 64 + half * 32, vv);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int jj = net * 64 + half * 32 + j;
-                        const float h0 = softplus2(__uint_as_float(vv[j]) + b1[jj]);
-                        const float h1 = softplus2(__uint_as_float(vv[j + 1]) + b1[jj + 1]);
-                        const __half2 hh = __floats2half2_rn(h0, h1);
-                        const float2 back = __half22float2(hh);
-                        const __half2 ll = __floats2half2_rn(h0 - back.x, h1 - back.y);
-                        ph[half * 16 + j / 2] = *reinterpret_cast<const uint32_t*>(&hh);
-                        pl[half * 16 + j / 2] = *reinterpret_cast<const uint32_t*>(&ll);
-                    }
-                }
-                tc::tmem_st_32x32(tmem_row + net * 64, ph);
-                tc::tmem_st_32x32(tmem_row + net * 64 + 32, pl);
-                tc::tmem_st_wait();
-                group_sync();
-                if (m == 0) issue_layer2(net);
-                wait_mma();
+            // colour pre-activations of one net (32 TMEM columns at `col`) -> bias, sigmoid where masked, x coefficient,
+            // reduction over the rows of a ray segment -> per-segment partial sums in shared memory
+            auto colour_epilogue = [&](int net, int col) {
                 uint32_t cv[32];
-                tc::tmem_ld_32x32(tmem_row + 128, cv);
+                tc::tmem_ld_32x32(tmem_row + col, cv);
                 tc::tmem_ld_wait();
                 const uint32_t smask = a.sigmoid_mask[net];
                 float acc[32];
@@ -428,6 +441,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
                             *reinterpret_cast<float4*>(dst + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
                     }
                 }
+            };
+            if (park_pending) { wait_mma(); park_pending = false; }      // the last parked layer 2 has landed
+            const int oth = 1 - sig;
+            // the other net's layer 1 runs under the epilogue of the parked colours. D1 is free: every row's packed hidden was
+            // consumed by a layer 2 this thread has waited for, and MMAs of one issuer execute in order
+            if (n_nets == 2 && m == 0) issue_layer1((pass == 0 ? 0 : L.tiles_c) + grp, oth * 64, idesc_n64);
+            colour_epilogue(sig, kTcColPark + pass * 32);
+            if (n_nets == 2) {
+                wait_mma();
+                hidden_to_tmem(oth, no_sigma);
+                group_sync();
+                if (m == 0) issue_layer2(oth, kTcColD2);
+                wait_mma();
+                colour_epilogue(oth, kTcColD2);
             }
         }
         tc::tc_fence_before();

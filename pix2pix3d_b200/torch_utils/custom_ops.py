@@ -19,7 +19,7 @@ def _opt(t):
 
 
 class _BiasActPlugin:
-    __name__ = 'bias_act_plugin'
+    plugin_name = 'bias_act_plugin'
 
     @staticmethod
     def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
@@ -29,7 +29,7 @@ class _BiasActPlugin:
 
 
 class _Upfirdn2dPlugin:
-    __name__ = 'upfirdn2d_plugin'
+    plugin_name = 'upfirdn2d_plugin'
 
     @staticmethod
     def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
@@ -39,7 +39,7 @@ class _Upfirdn2dPlugin:
 
 
 class _FilteredLReluPlugin:
-    __name__ = 'filtered_lrelu_plugin'
+    plugin_name = 'filtered_lrelu_plugin'
 
     @staticmethod
     def filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain, slope, clamp, flip_filter, write_signs):
@@ -53,7 +53,7 @@ class _FilteredLReluPlugin:
         return impl._plugin_filtered_lrelu_act_(x, si, int(sx), int(sy), float(gain), float(slope), float(clamp), bool(write_signs))
 
 
-_PLUGINS = {p.__name__: p for p in (_BiasActPlugin, _Upfirdn2dPlugin, _FilteredLReluPlugin)}
+_PLUGINS = {p.plugin_name: p for p in (_BiasActPlugin, _Upfirdn2dPlugin, _FilteredLReluPlugin)}
 
 
 def get_plugin(module_name, sources=None, headers=None, source_dir=None, **build_kwargs):
