@@ -228,6 +228,94 @@ def run_reference_cuda_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def run_train_step_arm(args):
+    """`--workload train_step`: BASELINE.json configs[4] -- one `train.py` iteration of the afhq_seg recipe at 4 images per GPU
+    (G main [+ density reg every 4], D main [+ R1 every 16], D_semantic main [+ R1 every 16], one flat NCCL all-reduce per phase,
+    Adam, G_ema), pix2pix3d_b200/train_step.py. `--impl ours`: the reference's loss class driving this package's modules and
+    kernels through `install()`; `--impl reference-cuda`: the unmodified reference end to end. Weak scaling (4 images per GPU)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    import ref_harness as rh
+    if args.impl == 'ours':
+        import pix2pix3d_b200
+        from pix2pix3d_b200 import _lib
+        _lib.lib()
+        pix2pix3d_b200.install(reference_root=rh.REF_ROOT)       # training.loss etc. come from the reference checkout
+    else:
+        rh.import_reference()
+    from pix2pix3d_b200 import train_step as ts
+    cfg = dict(ts.AFHQ_TRAIN)
+    if args.batch:
+        cfg['batch_gpu'] = args.batch
+        cfg['mbstd_group'] = min(cfg['mbstd_group'], args.batch)
+    st = ts.build(cfg, dev, rank=rank, num_gpus=world, seed=0)
+    batch = ts.synthetic_batch(cfg, dev, 100 + rank)
+    steps = args.steps if args.steps != 20 else 16                 # default: one full lazy-regularisation period
+    warm = max(args.warmup if args.warmup != 5 else 3, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = 0
+    if args.impl == 'ours':
+        from pix2pix3d_b200 import _lib
+    for _ in range(warm):
+        ts.run_iteration(st, batch)
+    st.batch_idx = 0                                               # timed region starts on a regularisation iteration
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    if args.impl == 'ours':
+        launches0 = _lib.launch_count
+    timers = {}
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ts.run_iteration(st, batch, timers if rank == 0 else None)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        phases = {k: {'calls': len(v), 'ms_per_call': sum(a.elapsed_time(b) for a, b in v) / len(v)} for k, v in timers.items()}
+        b = cfg['batch_gpu']
+        value = world * b * steps / (ms / 1000.0)
+        line = {
+            'metric': 'train.py step images/sec (afhq_seg 512^2 / 128^2 rays: G fwd + dual discriminator + R1, 4 images per GPU)',
+            'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': steps, 'warmup': warm, 'ms_per_step': ms / steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 (G backbone, renderer) + f16 (super-resolution, top-4 D resolutions), as train.py', 'data': 'synthetic',
+            'impl': args.impl,
+            'config': {'workload': 'train_step', 'batch_per_gpu': b, 'global_batch': b * world, 'neural_rendering_resolution': cfg['nrr'],
+                       'img_resolution': cfg['img_resolution'], 'parallelism': f'dp{world}: one flat fp32 all-reduce per phase (NCCL)',
+                       'phases': 'Gmain Dmain D_semanticmain every iteration, Greg every 4, Dreg / D_semanticreg every 16',
+                       'l2_policy': 'no flush: activations of a step exceed L2 by orders of magnitude'},
+            'phase_ms': phases, 'allreduce_bytes_per_phase': st.flat_bytes,
+            'peak_mem_gb': torch.cuda.max_memory_allocated() / 2 ** 30, 'clocks': clocks,
+            'gpu_launches': ((_lib.launch_count - launches0) / steps) if args.impl == 'ours' else None,
+            'params_digest': ts.grads_digest(st),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def stock_cuda_leg(args, B, timeout_s=900):
     """Run `--impl reference-cuda` in a child process (its module names `training.*` stay out of this process and a JIT
     failure cannot take the product measurement down) and return its JSON line."""
@@ -270,7 +358,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'reference-cuda'])
-    ap.add_argument('--workload', default=WORKLOAD, choices=['seg2cat_smoke', 'seg2cat_512', 'seg2face_512', 'edge2car_128'],
+    ap.add_argument('--workload', default=WORKLOAD, choices=['seg2cat_smoke', 'seg2cat_512', 'seg2face_512', 'edge2car_128', 'train_step'],
                     help='BASELINE.json configs 1-4 (default: configs[1], the metric\'s configuration)')
     ap.add_argument('--no-stock-cuda', action='store_true', help='skip the reference stock-CUDA leg (child process, ~1-2 min incl. plugin JIT)')
     ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (default: the workload batch, 4)')
@@ -278,6 +366,11 @@ def main():
     ap.add_argument('--force-fp32', action='store_true', help='run the SR stacks in fp32 (reference default is fp16)')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     args = ap.parse_args()
+    if args.workload == 'train_step':
+        if args.impl == 'reference':
+            raise SystemExit('--workload train_step has the arms `ours` and `reference-cuda` (a CPU train step takes minutes per image)')
+        run_train_step_arm(args)
+        return
     if args.impl == 'reference':
         run_reference_arm(args)
         return

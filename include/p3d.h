@@ -107,8 +107,31 @@ typedef struct {
     /* p3d_render_fwd_tc only: 0 = one 8-ray tile per CTA shared by its three 128-row groups (render_tc.cu); 1 = ray-pair
      * ownership, groups never synchronise with each other (render_tc2.cu; Sc, Sf <= 64, else P3D_UNSUPPORTED). Same results. */
     int32_t tc_variant;
-    int32_t reserved0;
+    /* How the coarse depths are obtained (ImportanceRenderer.sample_stratified, renderer.py:169-192):
+     *   0  depths_coarse holds them (any sampling the caller computed);
+     *   1  scalar ray limits (:187-190): d[k] = depth_table[k] + jitter * depth_delta, depth_table = torch.linspace(ray_start,
+     *      ray_end, Sc), depth_delta = (ray_end - ray_start) / (Sc - 1), jitter = the torch.rand_like draw [B,R,Sc];
+     *   2  per-ray limits (`ray_start == 'auto'`, :91-97, :181-186 with math_utils.linspace :101-118):
+     *      d[k] = ray_start[r] + depth_table[k] * (ray_end[r] - ray_start[r]) + jitter * ((ray_end[r] - ray_start[r]) / (Sc - 1)),
+     *      depth_table = arange(Sc) / (Sc - 1).
+     * Products and sums are rounded separately, in the reference's order, so the depths equal the torch results bit for bit.
+     * Neutral at zero: older callers that never set these keep mode 0. */
+    int32_t depth_mode;
+    const float* jitter;         /* [B,R,Sc]  modes 1, 2 */
+    const float* depth_table;    /* [Sc]      modes 1, 2 */
+    const float* ray_start;      /* [B,R]     mode 2 */
+    const float* ray_end;        /* [B,R]     mode 2 */
+    float   depth_delta;         /* mode 1 */
+    int32_t reserved1;
+    /* Optional [B] plane-set index per image: rays of image b gather from plane set plane_index[b] (NULL: b). Lets V camera
+     * views of one latent (applications/generate_video.py:57-69) share ONE resident plane set: planes batch 1, B = V. */
+    const int32_t* plane_index;
 } p3d_render_args_t;
+
+/* math_utils.get_ray_limits_box (training/volumetric_rendering/math_utils.py:46-98): slab test of N rays against the cube of
+ * side `box_side_length` centred at the origin. t_near / t_far [N]; (-1, -2) for rays that miss. */
+int p3d_ray_limits_box(const float* rays_o, const float* rays_d, int64_t N, float box_side_length, float* t_near, float* t_far,
+                       p3d_stream_t stream);
 
 /* ImportanceRenderer.forward for scalar ray limits -- training/volumetric_rendering/renderer.py:88-140:
  * coarse sample+decode -> MipRayMarcher2 weights (ray_marcher.py:25-57) -> sample_importance (:194-253)

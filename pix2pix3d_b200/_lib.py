@@ -10,7 +10,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libp3d.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 
@@ -41,7 +41,9 @@ class RenderArgs(ctypes.Structure):  # p3d_render_args_t
         ('dbg_perm', c_void_p), ('dbg_weights_final', c_void_p),
         ('workspace', c_void_p),
         ('plane_strides', ctypes.c_int64 * 3),
-        ('tc_variant', c_int32), ('reserved0', c_int32),
+        ('tc_variant', c_int32), ('depth_mode', c_int32),
+        ('jitter', c_void_p), ('depth_table', c_void_p), ('ray_start', c_void_p), ('ray_end', c_void_p),
+        ('depth_delta', c_float), ('reserved1', c_int32), ('plane_index', c_void_p),
     ]
 
 
@@ -50,6 +52,7 @@ _SIGNATURES = {
     'p3d_build_info': (ctypes.c_char_p, []),
     'p3d_status_string': (ctypes.c_char_p, [c_int]),
     'p3d_ray_sampler': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'p3d_ray_limits_box': (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
     'p3d_planes_to_channels_last': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'p3d_pack_decoder': (c_int, [ctypes.POINTER(DecoderDesc), c_void_p, c_void_p]),
     'p3d_render_fwd': (c_int, [ctypes.POINTER(RenderArgs), c_void_p]),

@@ -56,6 +56,35 @@ __global__ void pack_decoder_kernel(PackArgs a, float* __restrict__ out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Ray / box slab test (math_utils.py:46-98): thread per ray, the reference's operation order (inverse direction first, then
+// (bound - origin) * inverse), comparisons before the min / max update, misses marked (-1, -2)
+// ---------------------------------------------------------------------------------------------
+__global__ void ray_limits_box_kernel(const float* __restrict__ ro, const float* __restrict__ rd, int64_t n, float half,
+                                      float* __restrict__ t_near, float* __restrict__ t_far) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float tin[3], tout[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const float o = ro[i * 3 + ax], inv = __fdiv_rn(1.f, rd[i * 3 + ax]);
+        const bool neg = inv < 0.f;
+        tin[ax] = __fmul_rn(__fsub_rn(neg ? half : -half, o), inv);
+        tout[ax] = __fmul_rn(__fsub_rn(neg ? -half : half, o), inv);
+    }
+    bool valid = true;
+    float tmin = tin[0], tmax = tout[0];
+#pragma unroll
+    for (int ax = 1; ax < 3; ++ax) {
+        if ((tmin > tout[ax]) || (tin[ax] > tmax)) valid = false;
+        // torch.max / torch.min propagate NaN (a zero direction component against an origin on the slab plane gives 0 * inf)
+        tmin = (tmin != tmin || tin[ax] != tin[ax]) ? __int_as_float(0x7fc00000) : fmaxf(tmin, tin[ax]);
+        tmax = (tmax != tmax || tout[ax] != tout[ax]) ? __int_as_float(0x7fc00000) : fminf(tmax, tout[ax]);
+    }
+    t_near[i] = valid ? tmin : -1.f;
+    t_far[i] = valid ? tmax : -2.f;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Ray sampler (ray_sampler.py:24-62)
 // ---------------------------------------------------------------------------------------------
 __global__ void ray_sampler_kernel(const float* __restrict__ c2w, const float* __restrict__ K, int B, int res,
@@ -293,7 +322,8 @@ __global__ void __launch_bounds__(256, 2) render_fwd_kernel(const RenderParams P
         const bool vC = (rC < RT) && (sC < Sc) && (ray0 + rC < P.total_rays);
         const bool vF = (rF < RT) && (sF < Sf) && (ray0 + rF < P.total_rays);
         const int gC = ray0 + rC, gF = ray0 + rF;     // global ray ids
-        const int bC = vC ? gC / a.R : 0, bF = vF ? gF / a.R : 0;
+        // image of the ray -> plane set it gathers from (p3d_render_args_t::plane_index: V views of one resident plane set)
+        const int bC = vC ? plane_set(a, gC / a.R) : 0, bF = vF ? plane_set(a, gF / a.R) : 0;
         const int rowC = rC * Sc + sC, rowF = RT * Sc + rF * Sf + sF;
         float* rbC = rayb + (rC < RT ? rC : 0) * L.ray_stride;
         float* rbF = rayb + (rF < RT ? rF : 0) * L.ray_stride;
@@ -303,7 +333,7 @@ __global__ void __launch_bounds__(256, 2) render_fwd_kernel(const RenderParams P
         {
             float px = 0.f, py = 0.f, pz = 0.f;
             if (vC) {
-                dC = __ldg(a.depths_coarse + (size_t)gC * Sc + sC);
+                dC = coarse_depth(a, gC, sC, Sc);
                 const float* o = a.ray_origins + (size_t)gC * 3;
                 const float* d = a.ray_dirs + (size_t)gC * 3;
                 px = __fmul_rn(a.coord_scale, __fadd_rn(__ldg(o + 0), __fmul_rn(dC, __ldg(d + 0))));
@@ -708,7 +738,7 @@ using namespace p3d;
 
 extern "C" {
 
-int p3d_abi_version(void) { return 2; }
+int p3d_abi_version(void) { return 3; }
 const char* p3d_build_info(void) { return "libp3d sm_100a " __DATE__ " " __TIME__; }
 const char* p3d_status_string(int status) {
     if (status == P3D_OK) return "ok";
@@ -716,6 +746,18 @@ const char* p3d_status_string(int status) {
     if (status == P3D_BAD_ARG) return "bad argument";
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "unknown";
+}
+
+int p3d_ray_limits_box(const float* rays_o, const float* rays_d, int64_t N, float box_side_length, float* t_near, float* t_far,
+                       p3d_stream_t stream) {
+    if (!rays_o || !rays_d || !t_near || !t_far || N < 0) return P3D_BAD_ARG;
+    if (N == 0) return P3D_OK;
+    const int threads = 256;
+    const int64_t blocks = (N + threads - 1) / threads;
+    if (blocks > INT32_MAX) return P3D_UNSUPPORTED;
+    ray_limits_box_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(rays_o, rays_d, N, box_side_length / 2, t_near, t_far);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
 }
 
 int p3d_ray_sampler(const float* cam2world, const float* intrinsics, int B, int res, float* origins, float* dirs,
@@ -755,7 +797,7 @@ int p3d_pack_decoder(const p3d_decoder_t* dec, float* packed, p3d_stream_t strea
 int p3d_render_fwd(const p3d_render_args_t* args, p3d_stream_t stream) {
     if (!args) return P3D_BAD_ARG;
     const p3d_render_args_t& a = *args;
-    if (!a.planes_nhwc || !a.ray_origins || !a.ray_dirs || !a.depths_coarse || !a.decoder_packed || !a.out_feat ||
+    if (!a.planes_nhwc || !a.ray_origins || !a.ray_dirs || !depth_args_ok(a) || !a.decoder_packed || !a.out_feat ||
         !a.out_depth || !a.out_wsum || !a.workspace)
         return P3D_BAD_ARG;
     if (a.plane_strides[0] || a.plane_strides[1] || a.plane_strides[2]) {

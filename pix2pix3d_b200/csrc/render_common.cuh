@@ -76,6 +76,30 @@ __device__ __forceinline__ float plane_mean(float f0, float f1, float f2) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Coarse depth of sample s of global ray g (sample_stratified, renderer.py:169-192): read, or formed from the jitter draw
+// with the reference's separately rounded operations (p3d_render_args_t::depth_mode)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float coarse_depth(const p3d_render_args_t& a, int g, int s, int Sc) {
+    if (a.depth_mode == 0) return __ldg(a.depths_coarse + (size_t)g * Sc + s);
+    const float j = __ldg(a.jitter + (size_t)g * Sc + s);
+    if (a.depth_mode == 1) return __fadd_rn(__ldg(a.depth_table + s), __fmul_rn(j, a.depth_delta));
+    const float st = __ldg(a.ray_start + g), span = __fsub_rn(__ldg(a.ray_end + g), st);
+    const float base = __fadd_rn(st, __fmul_rn(__ldg(a.depth_table + s), span));         // math_utils.linspace
+    return __fadd_rn(base, __fmul_rn(j, __fdiv_rn(span, (float)(Sc - 1))));
+}
+
+__device__ __forceinline__ int plane_set(const p3d_render_args_t& a, int image) {
+    return a.plane_index ? __ldg(a.plane_index + image) : image;
+}
+
+__host__ inline bool depth_args_ok(const p3d_render_args_t& a) {
+    if (a.depth_mode == 0) return a.depths_coarse != nullptr;
+    if (a.depth_mode == 1) return a.jitter && a.depth_table;
+    if (a.depth_mode == 2) return a.jitter && a.depth_table && a.ray_start && a.ray_end;
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------------
 // MipRayMarcher2 weights for one ray, executed by one warp (ray_marcher.py:26-43)
 //   d[n], s[n] sorted samples in shared memory; writes w[n-1]; returns sum w and sum w*d_mid
 // ---------------------------------------------------------------------------------------------

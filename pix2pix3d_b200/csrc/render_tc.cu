@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
         const bool vC = (rC < RT) && (ray0 + rC < P.total_rays);
         const bool vF = (Sf > 0) && (rF < RT) && (ray0 + rF < P.total_rays);
         const int gC = ray0 + rC, gF = ray0 + rF;
-        const int bC = vC ? gC / a.R : 0, bF = vF ? gF / a.R : 0;
+        // image of the ray -> plane set it gathers from (p3d_render_args_t::plane_index: V views of one resident plane set)
+        const int bC = vC ? plane_set(a, gC / a.R) : 0, bF = vF ? plane_set(a, gF / a.R) : 0;
         float* rbC = rayb + (rC < RT ? rC : 0) * L.ray_stride;
         float* rbF = rayb + (rF < RT ? rF : 0) * L.ray_stride;
         const bool grpC = grp < L.tiles_c, grpF = grp < L.tiles_f;   // does this group own a coarse / fine tile?
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
         if (grpC) {
             float px = 0.f, py = 0.f, pz = 0.f;
             if (vC) {
-                dC = __ldg(a.depths_coarse + (size_t)gC * Sc + sC);
+                dC = coarse_depth(a, gC, sC, Sc);
                 const float* o = a.ray_origins + (size_t)gC * 3;
                 const float* d = a.ray_dirs + (size_t)gC * 3;
                 px = __fmul_rn(a.coord_scale, __fadd_rn(__ldg(o + 0), __fmul_rn(dC, __ldg(d + 0))));
@@ -406,11 +407,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_fwd_tc_kernel(const TcRe
                 tc::tmem_ld_wait();
                 const uint32_t smask = a.sigmoid_mask[net];
                 float acc[32];
+                // the mask is all-or-nothing per net for every shipped decoder (rgb: sigmoid; semantic: raw logits when there are
+                // several classes, triplane_cond.py:1007): branch once per net, not once per channel (a predicated-off sigmoid
+                // still costs its six issue slots)
+                if (smask == 0xffffffffu) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float c = __uint_as_float(cv[i]) + b2c[net * 32 + i];
-                    c = ((smask >> i) & 1u) ? sigmoid_clamp_f(c) : c;
-                    acc[i] = v ? c * coef : 0.f;
+                    for (int i = 0; i < 32; ++i) acc[i] = sigmoid_clamp_f(__uint_as_float(cv[i]) + b2c[net * 32 + i]) * coef;
+                } else if (smask == 0u) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = (__uint_as_float(cv[i]) + b2c[net * 32 + i]) * coef;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float c = __uint_as_float(cv[i]) + b2c[net * 32 + i];
+                        c = ((smask >> i) & 1u) ? sigmoid_clamp_f(c) : c;
+                        acc[i] = c * coef;
+                    }
+                }
+                if (!v) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.f;     // rows beyond the tile's rays may hold NaN garbage: coef 0 is not enough
                 }
                 float* dst = part + ((size_t)(rr < RT ? rr : 0) * (L.NGc + L.NGf) + slot) * P.cout + net * kOut;
                 if (g == 16) {
@@ -526,7 +542,7 @@ extern "C" int p3d_pack_decoder_tc(const p3d_decoder_t* dec, void* packed, p3d_s
 extern "C" int p3d_render_fwd_tc(const p3d_render_args_t* args, p3d_stream_t stream) {
     if (!args) return P3D_BAD_ARG;
     const p3d_render_args_t& a = *args;
-    if (!a.planes_nhwc || !a.ray_origins || !a.ray_dirs || !a.depths_coarse || !a.decoder_packed || !a.out_feat ||
+    if (!a.planes_nhwc || !a.ray_origins || !a.ray_dirs || !depth_args_ok(a) || !a.decoder_packed || !a.out_feat ||
         !a.out_depth || !a.out_wsum || !a.workspace)
         return P3D_BAD_ARG;
     if (a.B <= 0 || a.R <= 0 || a.H <= 0 || a.W <= 0 || a.Sc < 2 || a.Sf < 0) return P3D_BAD_ARG;

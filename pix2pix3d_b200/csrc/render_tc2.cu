@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) render_fwd_tc_pairs_kernel(co
         const int gray = pair * 2 + half;                         // this thread's ray
         const bool rvalid = gray < P.total_rays;
         const bool vC = rvalid && sidx < Sc, vF = rvalid && Sf > 0 && sidx < Sf;
-        const int b = rvalid ? gray / a.R : 0;
+        const int b = rvalid ? plane_set(a, gray / a.R) : 0;
         float* rb = rayb + half * L.ray_stride;
         float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
         if (rvalid) {
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) render_fwd_tc_pairs_kernel(co
         {
             float px = 0.f, py = 0.f, pz = 0.f;
             if (vC) {
-                dC = __ldg(a.depths_coarse + (size_t)gray * Sc + sidx);
+                dC = coarse_depth(a, gray, sidx, Sc);
                 px = __fmul_rn(a.coord_scale, __fadd_rn(ox, __fmul_rn(dC, dx)));
                 py = __fmul_rn(a.coord_scale, __fadd_rn(oy, __fmul_rn(dC, dy)));
                 pz = __fmul_rn(a.coord_scale, __fadd_rn(oz, __fmul_rn(dC, dz)));

@@ -508,8 +508,6 @@ def generator_supported(gen, ws, c, synthesis_kwargs, use_cached_backbone):
     gen.renderer.plane_axes = gen.renderer.plane_axes.to(ws.device)
     if not gen.renderer.fusable_options(gen.decoder, gen.rendering_kwargs):
         return False
-    if gen.rendering_kwargs['ray_start'] == 'auto':
-        return False
     sr_noise = gen.rendering_kwargs['superresolution_noise_mode']
     nrr = gen.neural_rendering_resolution
     srs = [gen.superresolution] + ([gen.superresolution_semantic] if hasattr(gen, 'superresolution_semantic') else [])

@@ -134,9 +134,31 @@ def pack_decoder(decoder):
     return PackedDecoder(packed, len(nets), sigma_net, masks, packed_tc)
 
 
-def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_warp, white_back=False, debug=False, impl=None):
-    """Fused ImportanceRenderer.forward. Returns (feat [B,R,C], depth [B,R,1], wsum [B,R,1][, debug dict])."""
-    B, _, H, W, C = planes_nhwc.shape
+def ray_limits_box(rays_o, rays_d, box_side_length):
+    """math_utils.get_ray_limits_box on CUDA tensors: (t_near, t_far) of shape [..., 1]."""
+    lead = rays_o.shape[:-1]
+    o, d = _f32c(rays_o.detach().reshape(-1, 3)), _f32c(rays_d.detach().reshape(-1, 3))
+    n = o.shape[0]
+    tn = torch.empty(n, device=o.device, dtype=torch.float32)
+    tf = torch.empty(n, device=o.device, dtype=torch.float32)
+    with torch.cuda.device(o.device):
+        st = _lib.lib().p3d_ray_limits_box(_lib.ptr(o), _lib.ptr(d), n, float(box_side_length), _lib.ptr(tn), _lib.ptr(tf), _lib.stream_ptr())
+    _lib.check(st, 'p3d_ray_limits_box')
+    _lib.bump()
+    return tn.reshape(*lead, 1), tf.reshape(*lead, 1)
+
+
+def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_warp, white_back=False, debug=False, impl=None,
+               stratified=None, plane_index=None):
+    """Fused ImportanceRenderer.forward. Returns (feat [B,R,C], depth [B,R,1], wsum [B,R,1][, debug dict]).
+    `stratified` (instead of `depths_coarse`): the ingredients of sample_stratified, combined inside the kernel --
+    dict(jitter=[B,R,Sc] U[0,1) draw, table=[Sc], delta=float) for scalar ray limits or dict(jitter, table, ray_start=[B,R],
+    ray_end=[B,R]) for per-ray limits (p3d_render_args_t::depth_mode 1 / 2).
+    `plane_index` ([B] int32): plane set of each image; lets B views share fewer plane sets (planes batch < B)."""
+    Bp, _, H, W, C = planes_nhwc.shape
+    B = ray_origins.shape[0]
+    if plane_index is None and Bp != B:
+        raise ValueError('planes batch and ray batch differ: pass plane_index')
     assert C == 32 and planes_nhwc.dtype == torch.float32
     impl = impl or render_impl
     # a strided view is read in place by the tensor-core kernel as long as channels are contiguous and rows are W pixels
@@ -148,8 +170,16 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
         strided = False
     R = ray_origins.shape[1]
     o, d = _f32c(ray_origins), _f32c(ray_dirs)
-    dc = _f32c(depths_coarse).reshape(B, R, -1)
-    Sc = dc.shape[-1]
+    keep = []
+    if stratified is not None:
+        jit = _f32c(stratified['jitter']).reshape(B, R, -1)
+        Sc = jit.shape[-1]
+        table = _f32c(stratified['table']).reshape(-1)
+        assert table.numel() == Sc
+        dc = None
+    else:
+        dc = _f32c(depths_coarse).reshape(B, R, -1)
+        Sc = dc.shape[-1]
     Sf = 0 if u is None else int(u.shape[-1])
     uu = None if u is None else _f32c(u)
     dev = planes_nhwc.device
@@ -159,12 +189,26 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
     ws = torch.empty(4, device=dev, dtype=torch.int32)
     a = _lib.RenderArgs()
     a.planes_nhwc, a.ray_origins, a.ray_dirs = planes_nhwc.data_ptr(), o.data_ptr(), d.data_ptr()
-    a.depths_coarse = dc.data_ptr()
+    if dc is not None:
+        a.depths_coarse = dc.data_ptr()
+    else:
+        a.jitter, a.depth_table = jit.data_ptr(), table.data_ptr()
+        if 'ray_start' in stratified:
+            rs, re_ = _f32c(stratified['ray_start']).reshape(B, R), _f32c(stratified['ray_end']).reshape(B, R)
+            keep += [rs, re_]
+            a.depth_mode, a.ray_start, a.ray_end = 2, rs.data_ptr(), re_.data_ptr()
+        else:
+            a.depth_mode, a.depth_delta = 1, float(stratified['delta'])
+    if plane_index is not None:
+        pidx = plane_index.to(device=planes_nhwc.device, dtype=torch.int32).contiguous()
+        assert pidx.numel() == B
+        keep.append(pidx)
+        a.plane_index = pidx.data_ptr()
     a.u_importance = None if uu is None else uu.data_ptr()
     a.decoder_packed = dec.packed.data_ptr()
     a.n_nets, a.sigma_net = dec.n_nets, dec.sigma_net
     a.sigmoid_mask[0], a.sigmoid_mask[1] = dec.masks[0], dec.masks[1]
-    a.B, a.R, a.H, a.W, a.Sc, a.Sf = B, R, H, W, Sc, Sf
+    a.B, a.R, a.H, a.W, a.Sc, a.Sf = B, R, H, W, Sc, Sf         # B = images of rays; plane sets may be fewer (plane_index)
     a.coord_scale = 2.0 / float(box_warp)
     a.white_back = 1 if white_back else 0
     a.out_feat, a.out_depth, a.out_wsum = feat.data_ptr(), depth.data_ptr(), wsum.data_ptr()

@@ -18,6 +18,9 @@ def torch_dot(x, y):
 def get_ray_limits_box(rays_o, rays_d, box_side_length):
     """Slab test of rays against the axis-aligned cube of side `box_side_length` centred at the origin;
     returns (t_near, t_far) of shape [..., 1], (-1, -2) for misses (reference :46-98)."""
+    if rays_o.device.type == 'cuda' and rays_o.dtype == torch.float32:
+        from ... import native
+        return native.ray_limits_box(rays_o, rays_d, box_side_length)
     lead = rays_o.shape[:-1]
     o = rays_o.detach().reshape(-1, 3)
     d = rays_d.detach().reshape(-1, 3)

@@ -95,35 +95,60 @@ class ImportanceRenderer(torch.nn.Module):
         self.plane_axes = generate_planes()
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, planes_channels_last=None):
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options, planes_channels_last=None, plane_index=None):
         """planes [B,3,32,H,W]; rays [B,M,3] -> (features [B,M,C], depth [B,M,1], weight sum [B,M,1]) (:88-140).
         `planes_channels_last` ([B,3,H,W,32] fp32, optional) lets a caller that already holds the gather layout skip the
-        transpose; `planes` may then be None."""
+        transpose; `planes` may then be None. `plane_index` ([B] int32, with `planes_channels_last`): plane set per image,
+        so that several camera views share one resident plane set."""
         self.plane_axes = self.plane_axes.to(ray_origins.device)
         opts = rendering_options
 
-        if opts['ray_start'] == opts['ray_end'] == 'auto':
+        n_importance = opts['depth_resolution_importance']
+        auto = opts['ray_start'] == opts['ray_end'] == 'auto'
+        if auto:
             ray_start, ray_end = math_utils.get_ray_limits_box(ray_origins, ray_directions, box_side_length=opts['box_warp'])
             is_ray_valid = ray_end > ray_start
             if torch.any(is_ray_valid).item():
                 ray_start[~is_ray_valid] = ray_start[is_ray_valid].min()
                 ray_end[~is_ray_valid] = ray_start[is_ray_valid].max()
-            depths_coarse = self.sample_stratified(ray_origins, ray_start, ray_end, opts['depth_resolution'],
-                                                   opts['disparity_space_sampling'])
         else:
-            depths_coarse = self.sample_stratified(ray_origins, opts['ray_start'], opts['ray_end'], opts['depth_resolution'],
-                                                   opts['disparity_space_sampling'])
-        n_importance = opts['depth_resolution_importance']
+            ray_start, ray_end = opts['ray_start'], opts['ray_end']
 
-        if planes_channels_last is not None or self._fusable(planes, decoder, ray_origins, ray_directions, opts):
+        fused = planes_channels_last is not None or self._fusable(planes, decoder, ray_origins, ray_directions, opts)
+        if fused:
             b, r = ray_origins.shape[:2]
-            u = torch.rand(b * r, n_importance, device=ray_origins.device) if n_importance > 0 else None
+            dev = ray_origins.device
+            n_c = opts['depth_resolution']
+            if opts['disparity_space_sampling']:
+                kw = dict(depths_coarse=self.sample_stratified(ray_origins, ray_start, ray_end, n_c, True))
+            else:
+                # sample_stratified (:181-190) inside the kernel: the host only draws the jitter (same generator call, same
+                # order as the reference's torch.rand_like) and hands over the linspace table
+                jitter = torch.rand(b, r, n_c, 1, device=dev)
+                if auto:
+                    table = self._table(('steps', n_c, dev), lambda: torch.arange(n_c, dtype=torch.float32, device=dev) / (n_c - 1))
+                    kw = dict(depths_coarse=None, stratified=dict(jitter=jitter, table=table, ray_start=ray_start, ray_end=ray_end))
+                else:
+                    table = self._table(('lin', float(ray_start), float(ray_end), n_c, dev),
+                                        lambda: torch.linspace(ray_start, ray_end, n_c, device=dev))
+                    kw = dict(depths_coarse=None, stratified=dict(jitter=jitter, table=table, delta=(ray_end - ray_start) / (n_c - 1)))
+            u = torch.rand(b * r, n_importance, device=dev) if n_importance > 0 else None
             dec = native.pack_decoder(decoder)
             planes_cl = planes_channels_last if planes_channels_last is not None else native.planes_to_channels_last(planes)
-            return native.render_fwd(planes_cl, dec, ray_origins, ray_directions, depths_coarse, u, opts['box_warp'],
-                                     white_back=bool(opts.get('white_back', False)))
+            return native.render_fwd(planes_cl, dec, ray_origins, ray_directions, kw.pop('depths_coarse'), u, opts['box_warp'],
+                                     white_back=bool(opts.get('white_back', False)), plane_index=plane_index, **kw)
 
+        depths_coarse = self.sample_stratified(ray_origins, ray_start, ray_end, opts['depth_resolution'],
+                                               opts['disparity_space_sampling'])
         return self._forward_staged(planes, decoder, ray_origins, ray_directions, depths_coarse, n_importance, opts)
+
+    def _table(self, key, fn):
+        """Small constant tensors of the stratified sampling (linspace of the ray limits), built once per configuration."""
+        cache = self.__dict__.setdefault('_tables', {})
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = fn()
+        return t
 
     def fusable_options(self, decoder, opts):
         """True when the rendering options and decoder are covered by the fused kernel (independent of the planes)."""

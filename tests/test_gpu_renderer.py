@@ -303,3 +303,114 @@ def test_unsorted_and_tied_coarse_depths_still_merge_like_a_stable_sort(impl):
     perm = np.argsort(alld, axis=-1, kind='stable')
     assert np.array_equal(dbg['perm'].cpu().numpy(), perm)
     assert torch.isfinite(feat).all() and torch.isfinite(depth).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bookkeeping scored against the REFERENCE's own torch.searchsorted / torch.sort results stored in the fixtures
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case,impl', [ci for ci in IMPL_CASES if ci[0] not in ('coarse_only', 'coarse8')])
+def test_bookkeeping_against_reference_fixture(case, impl):
+    g = load_golden('renderer_' + case)
+    (feat, depth, wsum, dbg), dc, opts = run_fused(g, impl=impl)
+    perm = dbg['perm'].cpu().numpy().reshape(g['perm'].shape)
+    dfine = dbg['depths_fine'].cpu().numpy().reshape(g['depths_fine'].shape)
+    perm_rate = float((perm == g['perm']).mean())
+    print(f'BOOKKEEPING-VS-REFERENCE {case}/{impl}: perm exact {perm_rate:.5f}, depths_fine rel err {rel_err(dfine, g["depths_fine"]):.2e}')
+    assert rel_err(dfine, g['depths_fine']) < 1e-5
+    assert perm_rate >= 0.999
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sample_stratified inside the kernel (depth_mode 1 / 2), ray limits, plane-set indirection
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case,impl', [('seg', 'simt'), ('seg48', 'tc'), ('car64', 'tc_pairs')])
+def test_in_kernel_stratified_depths_are_bit_identical(case, impl):
+    """depth_mode 1: the kernel forms linspace[k] + jitter * delta itself; outputs must equal the run on precomputed depths
+    bit for bit, and the depths the reference's sample_stratified produces (torch ops) must be what it formed."""
+    from pix2pix3d_b200 import native
+    g = load_golden('renderer_' + case)
+    dev = torch.device('cuda')
+    opts = render_opts(g)
+    b, m = g['ray_origins'].shape[:2]
+    sc = opts['depth_resolution']
+    planes_cl = native.planes_to_channels_last(torch.from_numpy(g['planes']).to(dev))
+    dec = native.pack_decoder(torch_decoder(g, dev))
+    o, d = torch.from_numpy(g['ray_origins']).to(dev), torch.from_numpy(g['ray_dirs']).to(dev)
+    u = torch.from_numpy(g['u']).to(dev)
+    jitter = torch.from_numpy(g['jitter']).to(dev)
+    # the reference's own op sequence on the device (renderer.py:187-190)
+    depths = torch.linspace(opts['ray_start'], opts['ray_end'], sc, device=dev).reshape(1, 1, sc, 1).repeat(b, m, 1, 1)
+    depths += jitter * ((opts['ray_end'] - opts['ray_start']) / (sc - 1))
+    ref = native.render_fwd(planes_cl, dec, o, d, depths, u, opts['box_warp'], white_back=opts['white_back'], impl=impl, debug=True)
+    table = torch.linspace(opts['ray_start'], opts['ray_end'], sc, device=dev)
+    got = native.render_fwd(planes_cl, dec, o, d, None, u, opts['box_warp'], white_back=opts['white_back'], impl=impl, debug=True,
+                            stratified=dict(jitter=jitter, table=table, delta=(opts['ray_end'] - opts['ray_start']) / (sc - 1)))
+    for a, r in zip(got[:3], ref[:3]):
+        assert torch.equal(a, r)
+    for k in ('perm', 'inds', 'depths_fine', 'weights_coarse'):
+        assert torch.equal(got[3][k], ref[3][k]), k
+
+
+def test_per_ray_limits_in_kernel_and_ray_box_kernel():
+    """`ray_start == 'auto'` (renderer.py:91-97): the slab test kernel against the mirror's torch formula evaluated on CPU
+    (bit-exact), then depth_mode 2 against the torch evaluation of math_utils.linspace + jitter (bit-exact outputs)."""
+    from pix2pix3d_b200 import native
+    from pix2pix3d_b200.training.volumetric_rendering import math_utils
+    g = load_golden('renderer_far_outside')
+    dev = torch.device('cuda')
+    opts = render_opts(g)
+    o, d = torch.from_numpy(g['ray_origins']), torch.from_numpy(g['ray_dirs'])
+    # rays that miss, graze and hit; one direction component exactly zero
+    d2 = d.clone(); d2[0, :5, 0] = 0.0; d2[0, 5:9] = torch.tensor([0.0, 0.0, 1.0])
+    tn_cpu, tf_cpu = math_utils.get_ray_limits_box(o, d2, box_side_length=1.0)
+    tn, tf = native.ray_limits_box(o.to(dev), d2.to(dev), 1.0)
+    assert torch.equal(torch.nan_to_num(tn.cpu(), nan=-7), torch.nan_to_num(tn_cpu, nan=-7))
+    assert torch.equal(torch.nan_to_num(tf.cpu(), nan=-7), torch.nan_to_num(tf_cpu, nan=-7))
+    assert (tn_cpu == -1).any() and (tn_cpu > 0).any()
+
+    b, m = o.shape[:2]
+    sc = opts['depth_resolution']
+    rs, re_ = native.ray_limits_box(o.to(dev), d.to(dev), 1.0)
+    valid = re_ > rs
+    rs[~valid] = rs[valid].min(); re_[~valid] = rs[valid].max()
+    jitter = torch.from_numpy(g['jitter']).to(dev)
+    depths = math_utils.linspace(rs, re_, sc).permute(1, 2, 0, 3)
+    depths = depths + jitter * ((re_ - rs) / (sc - 1))[..., None]
+    planes_cl = native.planes_to_channels_last(torch.from_numpy(g['planes']).to(dev))
+    dec = native.pack_decoder(torch_decoder(g, dev))
+    u = torch.from_numpy(g['u']).to(dev)
+    for impl in ('simt', 'tc'):
+        if impl == 'tc' and (sc % 8 or int(g['Sf']) % 8):
+            continue
+        ref = native.render_fwd(planes_cl, dec, o.to(dev), d.to(dev), depths, u, opts['box_warp'], impl=impl)
+        table = torch.arange(sc, dtype=torch.float32, device=dev) / (sc - 1)
+        got = native.render_fwd(planes_cl, dec, o.to(dev), d.to(dev), None, u, opts['box_warp'], impl=impl,
+                                stratified=dict(jitter=jitter, table=table, ray_start=rs, ray_end=re_))
+        for a, r in zip(got, ref):
+            assert torch.equal(a, r), impl
+
+
+@pytest.mark.parametrize('impl', ['simt', 'tc', 'tc_pairs'])
+def test_plane_index_shares_one_plane_set_between_views(impl):
+    """V camera views of one plane set (generate_video.py:57-69): rays batch V, planes batch 1 + plane_index == the per-view
+    renders against a replicated plane tensor."""
+    from pix2pix3d_b200 import native
+    g = load_golden('renderer_seg16')
+    dev = torch.device('cuda')
+    opts = render_opts(g)
+    planes = torch.from_numpy(g['planes']).to(dev)               # [2,...]: two plane sets
+    o, d = torch.from_numpy(g['ray_origins']).to(dev), torch.from_numpy(g['ray_dirs']).to(dev)
+    b, m = o.shape[:2]
+    dc = torch.from_numpy(O.renderer.sample_stratified(b, m, opts['ray_start'], opts['ray_end'], opts['depth_resolution'], g['jitter'])).to(dev)
+    u = torch.from_numpy(g['u']).to(dev)
+    dec = native.pack_decoder(torch_decoder(g, dev))
+    # views: image 0 and 1 both look at plane set 1; reference = planes[[1, 1]]
+    ref = native.render_fwd(native.planes_to_channels_last(planes[[1, 1]].contiguous()), dec, o, d, dc, u, opts['box_warp'], impl=impl)
+    got = native.render_fwd(native.planes_to_channels_last(planes[1:2].contiguous()), dec, o, d, dc, u, opts['box_warp'], impl=impl,
+                            plane_index=torch.zeros(2, dtype=torch.int32))
+    for a, r in zip(got, ref):
+        assert torch.equal(a, r)
+    mixed = native.render_fwd(native.planes_to_channels_last(planes), dec, o, d, dc, u, opts['box_warp'], impl=impl,
+                              plane_index=torch.tensor([1, 0], dtype=torch.int32))
+    swap = native.render_fwd(native.planes_to_channels_last(planes[[1, 0]].contiguous()), dec, o, d, dc, u, opts['box_warp'], impl=impl)
+    assert torch.equal(mixed[0], swap[0])

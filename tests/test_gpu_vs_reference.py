@@ -67,33 +67,44 @@ def test_synthesis_matches_reference_cuda_path_default_dtypes():
 
 def test_reference_op_wrappers_run_on_libp3d_plugins():
     """the reference's own torch_utils/ops/{bias_act,upfirdn2d}.py, unmodified, with this package's
-    `custom_ops.get_plugin` objects in place of the JIT-built pybind modules."""
+    `custom_ops.get_plugin` objects in place of the JIT-built pybind modules -- compared with the same wrappers on the
+    reference's stock plugins (forward and first-order gradients; e.g. the stock CUDA path does not clamp the gradient of a
+    clamped `linear` activation, bias_act.py:164-167 saves no `y` for it, and neither may the replacement)."""
     rh.import_reference()
     import torch_utils.ops.bias_act as r_ba
     import torch_utils.ops.upfirdn2d as r_up
     from pix2pix3d_b200.torch_utils import custom_ops as ours
     dev = torch.device('cuda')
-    saved = (r_ba._plugin, r_up._plugin)
-    r_ba._plugin = ours.get_plugin('bias_act_plugin', sources=['bias_act.cpp', 'bias_act.cu'])
-    r_up._plugin = ours.get_plugin('upfirdn2d_plugin', sources=['upfirdn2d.cpp', 'upfirdn2d.cu'])
-    try:
-        torch.manual_seed(0)
-        x = torch.randn(3, 8, 33, 31, device=dev, requires_grad=True)
-        b = torch.randn(8, device=dev, requires_grad=True)
-        for act in ('lrelu', 'swish', 'linear', 'sigmoid'):
+    assert r_ba._init() and r_up._init()                       # JIT-build / load the stock plugins
+    stock = (r_ba._plugin, r_up._plugin)
+    mine = (ours.get_plugin('bias_act_plugin', sources=['bias_act.cpp', 'bias_act.cu']),
+            ours.get_plugin('upfirdn2d_plugin', sources=['upfirdn2d.cpp', 'upfirdn2d.cu']))
+    torch.manual_seed(0)
+    x = torch.randn(3, 8, 33, 31, device=dev, requires_grad=True)
+    b = torch.randn(8, device=dev, requires_grad=True)
+    f = r_up.setup_filter([1, 3, 3, 1], device=dev)
+
+    def run_all():
+        res = []
+        for act in ('lrelu', 'swish', 'linear', 'sigmoid', 'softplus'):
             y = r_ba.bias_act(x, b, act=act, clamp=1.5, impl='cuda')
-            y_ref = r_ba.bias_act(x, b, act=act, clamp=1.5, impl='ref')
-            assert rel_err(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < 1e-5, act
-            gx, gb = torch.autograd.grad(y.square().sum(), [x, b])
-            gx_r, gb_r = torch.autograd.grad(y_ref.square().sum(), [x, b])
-            assert rel_err(gx.cpu().numpy(), gx_r.cpu().numpy()) < 1e-4 and rel_err(gb.cpu().numpy(), gb_r.cpu().numpy()) < 1e-4, act
-        f = r_up.setup_filter([1, 3, 3, 1], device=dev)
+            gx, gb = torch.autograd.grad(y.square().sum(), [x, b], create_graph=True)
+            (ggx,) = torch.autograd.grad(gx.square().sum() + gb.square().sum(), [x], allow_unused=True)
+            res += [('bias_act ' + act, y), ('bias_act dx ' + act, gx), ('bias_act db ' + act, gb)]
+            if ggx is not None:
+                res.append(('bias_act d2 ' + act, ggx))
         for kw in (dict(up=2, padding=[2, 1, 2, 1], gain=4), dict(down=2, padding=[1, 1, 1, 1]), dict(padding=[1, 1, 1, 1], gain=4)):
             y = r_up.upfirdn2d(x, f, impl='cuda', **kw)
-            y_ref = r_up.upfirdn2d(x, f, impl='ref', **kw)
-            assert rel_err(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < 1e-5, kw
             (gx,) = torch.autograd.grad(y.square().sum(), [x])
-            (gx_r,) = torch.autograd.grad(y_ref.square().sum(), [x])
-            assert rel_err(gx.cpu().numpy(), gx_r.cpu().numpy()) < 1e-4, kw
+            res += [(f'upfirdn2d {kw}', y), (f'upfirdn2d dx {kw}', gx)]
+        return [(n, t.detach().float().cpu().numpy()) for n, t in res]
+
+    try:
+        want = run_all()
+        r_ba._plugin, r_up._plugin = mine
+        got = run_all()
     finally:
-        r_ba._plugin, r_up._plugin = saved
+        r_ba._plugin, r_up._plugin = stock
+    assert len(want) == len(got)
+    for (n, w), (_, g) in zip(want, got):
+        assert rel_err(g, w) < 2e-6, n
