@@ -288,6 +288,9 @@ typedef struct {
     const float* residual;
     void* splitk_scratch;     /* optional fp32 scratch (32-byte aligned): lets launches much smaller than the machine split */
     int64_t splitk_scratch_bytes; /* their K range over up to 16 CTAs each (deterministic two-kernel reduction); NULL/0 = never */
+    /* noise_mode='random' (networks_stylegan2.py:320-321): noise is [B, oH*oW], one image per sample; elements between
+     * consecutive samples. 0 = the single [oH*oW] image of noise_mode='const' shared by the batch. */
+    int64_t noise_batch_stride;
 } p3d_conv_args_t;
 
 /* One implicit-GEMM convolution launch (tcgen05 + TMA): 3x3 / 1x1 convolutions and the four phases of a stride-2
@@ -342,19 +345,59 @@ int p3d_nchw_to_nhwc_f16(const void* x, int src_dtype, int N, int C, int H, int 
 int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, int c_stride, int c_offset, float* out,
                          p3d_stream_t stream);
 
+/* Fused filtered leaky ReLU -- the plugin entry `filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, sy, gain,
+ * slope, clamp, flip_filter, writeSigns)` of the reference (torch_utils/ops/filtered_lrelu.cpp:20-213; kernel parameters
+ * filtered_lrelu.h:18-57):  y = downsample_fd( lrelu_clamp( upsample_fu(x + b) * up^2 * gain ) ), everything between x and y
+ * in shared memory. Shapes are {width, height, channels, batch}; strides are in ELEMENTS in the same order.
+ * Filters: fp32, dense; fu_h == 0 / fd_h == 0 marks a separable 1-D filter of fu_w / fd_w taps (applied along x and y).
+ * Sign tensor `s` (uint8, contiguous [N, C, s_shape[1], s_shape[0]], four 2-bit records per byte: 1 = was negative,
+ * 2 = was clamped): sign_mode 0 ignores it, 1 writes it (forward pass that needs gradients), 2 reads it (the gradient pass:
+ * same op with fu / fd swapped, flip inverted; records are looked up at up-sampled coordinate + s_ofs). sw_limit = active
+ * width in bytes. Returns P3D_UNSUPPORTED when no tile of this configuration fits shared memory (filters > 32 taps, ...):
+ * the reference's `rc = -1`, upon which callers compose upfirdn2d + p3d_filtered_lrelu_act + upfirdn2d (filtered_lrelu.py:225-231). */
+typedef struct {
+    const void* x; void* y; const void* b;      /* b: [C] in x's dtype or NULL */
+    unsigned char* s;
+    const float* fu; const float* fd;
+    int32_t dtype;                               /* P3D_F32 or P3D_F16 */
+    int32_t up, down;
+    int32_t fu_w, fu_h, fd_w, fd_h;
+    int32_t px0, px1, py0, py1;                  /* padding with respect to the up-sampled image */
+    float   gain, slope, clamp;                  /* clamp = +inf for none */
+    int32_t flip;                                /* flip_filter: 0 = convolution (filters are mirrored), 1 = correlation */
+    int32_t x_shape[4]; int64_t x_stride[4];
+    int32_t y_shape[4]; int64_t y_stride[4];
+    int64_t b_stride;
+    int32_t s_shape[2];                          /* {width in BYTES, height} */
+    int32_t s_ofs[2];
+    int32_t sw_limit;
+    int32_t sign_mode;
+} p3d_filtered_lrelu_args_t;
+int p3d_filtered_lrelu(const p3d_filtered_lrelu_args_t* args, p3d_stream_t stream);
+
+/* In-place `x = lrelu_clamp(x * gain)` with the same sign contract -- `filtered_lrelu_act_` of the reference
+ * (filtered_lrelu.cpp:217-270, kernel filtered_lrelu.cu:1110-1215), the activation of the generic fallback path.
+ * s_shape = {width in ELEMENTS (multiple of 4), height}. */
+int p3d_filtered_lrelu_act(void* x, unsigned char* s, int dtype, const int32_t x_shape[4], const int64_t x_stride[4],
+                           const int32_t s_shape[2], const int32_t s_ofs[2], float gain, float slope, float clamp,
+                           int sign_mode, p3d_stream_t stream);
+
 /* 4x4 FIR (upfirdn2d up=down=1) + noise + bias + lrelu + gain + clamp on NHWC tensors: the tail of an up=2
  * SynthesisLayer (networks_stylegan2.py:324-331 after conv2d_resample.py:128). in_dtype: P3D_F32 or P3D_F16;
- * out_planes 1 (fp16) or 2 (fp16 hi/lo). x [B,inH,inW,C] -> y [out_planes][B,outH,outW,C]. */
+ * out_planes 1 (fp16) or 2 (fp16 hi/lo). x [B,inH,inW,C] -> y [out_planes][B,outH,outW,C]. noise: [outH*outW] shared by the
+ * batch (noise_batch_stride 0, noise_mode='const') or one image per sample (noise_batch_stride = outH*outW, 'random'). */
 int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
                      int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                     float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
+                     float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                     p3d_stream_t stream);
 
 /* The same operation on a split (hi/lo) fp16 input [2][B][inH][inW][C] whose value is hi + lo (fp32 semantics, no fp16
  * rounding of the filtered value): the FIR in front of the strided convolutions of the down=2 layers
  * (conv2d_resample.py:108-111) when the producer wrote a split tensor. */
 int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noise, const float* bias, void* y,
                            int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                           float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream);
+                           float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                           p3d_stream_t stream);
 
 /* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */
 int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream);

@@ -47,6 +47,18 @@ class RenderArgs(ctypes.Structure):  # p3d_render_args_t
     ]
 
 
+class FilteredLReluArgs(ctypes.Structure):  # p3d_filtered_lrelu_args_t
+    _fields_ = [
+        ('x', c_void_p), ('y', c_void_p), ('b', c_void_p), ('s', c_void_p), ('fu', c_void_p), ('fd', c_void_p),
+        ('dtype', c_int32), ('up', c_int32), ('down', c_int32),
+        ('fu_w', c_int32), ('fu_h', c_int32), ('fd_w', c_int32), ('fd_h', c_int32),
+        ('px0', c_int32), ('px1', c_int32), ('py0', c_int32), ('py1', c_int32),
+        ('gain', c_float), ('slope', c_float), ('clamp', c_float), ('flip', c_int32),
+        ('x_shape', c_int32 * 4), ('x_stride', c_int64 * 4), ('y_shape', c_int32 * 4), ('y_stride', c_int64 * 4),
+        ('b_stride', c_int64), ('s_shape', c_int32 * 2), ('s_ofs', c_int32 * 2), ('sw_limit', c_int32), ('sign_mode', c_int32),
+    ]
+
+
 _SIGNATURES = {
     'p3d_abi_version': (c_int, []),
     'p3d_build_info': (ctypes.c_char_p, []),
@@ -77,6 +89,9 @@ _SIGNATURES = {
     'p3d_sample_importance': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'p3d_bias_act': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                              c_float, c_float, c_int64, c_int, c_int64, c_void_p]),
+    'p3d_filtered_lrelu': (c_int, [ctypes.POINTER(FilteredLReluArgs), c_void_p]),
+    'p3d_filtered_lrelu_act': (c_int, [c_void_p, c_void_p, c_int, ctypes.POINTER(c_int32), ctypes.POINTER(c_int64), ctypes.POINTER(c_int32),
+                                       ctypes.POINTER(c_int32), c_float, c_float, c_float, c_int, c_void_p]),
     'p3d_upfirdn2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.POINTER(c_int32), ctypes.POINTER(c_int64),
                               ctypes.POINTER(c_int32), ctypes.POINTER(c_int64), c_int, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, c_int, c_float, c_void_p]),
@@ -94,9 +109,9 @@ _SIGNATURES = {
     'p3d_nchw_to_nhwc_f16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'p3d_nhwc_to_nchw_f32': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'p3d_fir_act_nhwc': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                 c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_void_p]),
+                                 c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_int64, c_void_p]),
     'p3d_fir_act_nhwc_split': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                       c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_void_p]),
+                                       c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_int64, c_void_p]),
     'p3d_upsample2x_nhwc': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 

@@ -40,6 +40,7 @@ struct ConvKernelArgs {
     void* y; void* y_lo;
     int out_mode;                     // 0: f16, 1: f16 hi/lo split, 2: f32, 3: f32 accumulate (+=)
     const float* bias; const float* noise; const float* dscale;
+    int64_t noise_bstride;            // elements between the noise images of consecutive samples (0: one image for the batch)
     float alpha, clamp, acc_scale;
     int base_aligned;                 // y / y_lo are 32-byte aligned (256-bit stores allowed)
     int splits;                       // split-K: blockIdx.z = b * splits + s; s covers k-steps [s*total/splits, (s+1)*total/splits)
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         const bool pix_ok = (gy < a.gH) && (gx < a.gW);
         const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
         const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
-        const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+        const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
         const int out_mode = a.out_mode;
         // vector path: every 32-channel chunk of this CTA is full and its stores are 32-byte aligned
         const bool vec_ok = a.base_aligned && ((n0 + a.BN) <= a.Cout) && (a.BN % 32 == 0) &&
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
             const bool pix_ok = (gy < a.gH) && (gx < a.gW);
             const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
             const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
-            const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+            const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
             const bool vec_ok = a.base_aligned && ((n0 + a.BN) <= a.Cout) && (a.BN % 32 == 0) &&
                                 (a.out_mode <= 1 ? ((a.y_cstride % 16) == 0 && ((a.y_coff + n0) % 16) == 0)
                                                  : ((a.y_cstride % 8) == 0 && ((a.y_coff + n0) % 8) == 0));
@@ -634,7 +635,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
             const bool pix_ok = (gy < a.gH) && (gx < a.gW);
             const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
             const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
-            const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+            const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
             const bool vec_ok = a.base_aligned && ((n0 + 256) <= a.Cout) &&
                                 (a.out_mode <= 1 ? ((a.y_cstride % 16) == 0 && ((a.y_coff + n0) % 16) == 0)
                                                  : ((a.y_cstride % 8) == 0 && ((a.y_coff + n0) % 8) == 0));
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const ConvKerne
         }
         const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
         const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
-        const float nz = a.noise ? __ldg(a.noise + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+        const float nz = a.noise ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
         const float accv[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -818,6 +819,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     a.Cout = p->Cout; a.y_cstride = p->y_cstride; a.y_coff = p->y_coff;
     a.y = p->y; a.y_lo = p->y_lo; a.out_mode = p->out_mode;
     a.bias = p->bias; a.noise = p->noise; a.dscale = p->dscale;
+    a.noise_bstride = p->noise_batch_stride;
     a.alpha = p->alpha; a.clamp = p->clamp; a.acc_scale = p->acc_scale;
     a.base_aligned = ((((uintptr_t)p->y) | ((uintptr_t)p->y_lo)) & 31) == 0;
     a.up_prev = p->up_prev; a.up_f = p->up_filter; a.round16 = p->round16; a.out_nchw = p->out_nchw;

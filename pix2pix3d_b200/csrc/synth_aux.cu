@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant
                                                            const float* __restrict__ noise, const float* __restrict__ bias,
                                                            __half* __restrict__ y, int out_planes, size_t out_plane_stride,
                                                            int outH, int outW, int C, int padx0, int pady0, float fir_gain,
-                                                           int act, float alpha, float act_gain, float clamp, int B) {
+                                                           int act, float alpha, float act_gain, float clamp, int B, int64_t noise_bstride) {
     extern __shared__ __align__(128) uint4 tile[];   // 209 pixels x 128 bytes (x 2 planes when kSplitIn)
     __shared__ __align__(8) uint64_t bar;
     constexpr int kTileVecs = kFirIH * kFirIW * 8;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant
         for (int j = 0; j < 2; ++j) {
             const int py = ty0 + by + i, px = tx0 + bx + j;
             if (py >= outH || px >= outW) continue;
-            const float nz = noise ? __ldg(noise + (size_t)py * outW + px) : 0.f;
+            const float nz = noise ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
             const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
             __align__(16) __half2 hv[VEC / 2], lv[VEC / 2];
 #pragma unroll
@@ -570,7 +570,7 @@ extern "C" int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, 
 
 static int fir_act_nhwc_impl(bool split_in, const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
                                 int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
+                                float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_bstride, p3d_stream_t stream) {
     if (!x || !f || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
     if (act != 1 && act != 3) return P3D_UNSUPPORTED;
     const size_t ps = (size_t)B * outH * outW * C;
@@ -596,31 +596,33 @@ static int fir_act_nhwc_impl(bool split_in, const void* x, int in_dtype, const f
         P3D_CUDA_TRY(cudaFuncSetAttribute(fir_act_nhwc_kernel<__half, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(2 * tile_bytes)));
         fir_act_nhwc_kernel<__half, 8, true><<<grid, 256, 2 * tile_bytes, (cudaStream_t)stream>>>(
-            tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act, alpha, act_gain, clamp, B);
+            tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act, alpha, act_gain, clamp, B, noise_bstride);
     } else if (in_dtype == P3D_F32)
         fir_act_nhwc_kernel<float, 4><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH,
                                                                                        outW, C, padx0, pady0, fir_gain, act, alpha, act_gain,
-                                                                                       clamp, B);
+                                                                                       clamp, B, noise_bstride);
     else
         fir_act_nhwc_kernel<__half, 8><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH,
                                                                                         outW, C, padx0, pady0, fir_gain, act, alpha,
-                                                                                        act_gain, clamp, B);
+                                                                                        act_gain, clamp, B, noise_bstride);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
 
 extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
                                 int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
+                                float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                                p3d_stream_t stream) {
     return fir_act_nhwc_impl(false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
-                             alpha, act_gain, clamp, stream);
+                             alpha, act_gain, clamp, noise_batch_stride, stream);
 }
 
 extern "C" int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noise, const float* bias, void* y,
                                       int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                      float fir_gain, int act, float alpha, float act_gain, float clamp, p3d_stream_t stream) {
+                                      float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                                      p3d_stream_t stream) {
     return fir_act_nhwc_impl(true, x_hi_lo, P3D_F16, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain,
-                             act, alpha, act_gain, clamp, stream);
+                             act, alpha, act_gain, clamp, noise_batch_stride, stream);
 }
 
 extern "C" int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream) {

@@ -8,8 +8,9 @@ layers, and ToRGB accumulated straight into the upsampled fp32 skip image.
 
 fp32 blocks (the tri-plane backbone, or any block under force_fp32) run on hi/lo split fp16 tensors with three
 tensor-core passes (fp32-level accuracy); fp16 blocks run single pass, rounding where the reference rounds.
-The module classes call into this when the inputs are CUDA tensors, no gradient is required and the noise mode is
-'const' or 'none'; every other case keeps the generic op-by-op formulation.
+The module classes call into this when the inputs are CUDA tensors and no gradient is required (any noise mode: 'random'
+draws one noise image per sample and layer with the reference's own `torch.randn` calls, in its order); every other case
+keeps the generic op-by-op formulation.
 """
 import weakref
 
@@ -27,7 +28,7 @@ enabled = True
 def block_supported(block, ws, noise_mode, need_grad):
     if not enabled or ws.device.type != 'cuda' or need_grad:
         return False
-    if noise_mode not in ('const', 'none'):
+    if noise_mode not in ('const', 'none', 'random'):
         return False
     if block.architecture != 'skip':
         return False
@@ -83,10 +84,16 @@ def _prepared(layer):
     return _cached(layer, 'wprep', [layer.weight], lambda: tcconv.prepare_weights(layer.weight))
 
 
-def _noise(layer, noise_mode):
+def _noise(layer, noise_mode, batch=None):
     if noise_mode == 'const' and layer.use_noise:
         return _cached(layer, 'noise', [layer.noise_const, layer.noise_strength],
                        lambda: (layer.noise_const * layer.noise_strength).detach().float().contiguous())
+    if noise_mode == 'random' and layer.use_noise:
+        # one image per sample, drawn exactly where the reference draws it (networks_stylegan2.py:320-321): same generator call,
+        # same layer order, so the RNG stream is consumed identically
+        res = layer.resolution
+        nz = torch.randn([batch, 1, res, res], device=layer.noise_strength.device) * layer.noise_strength.detach()
+        return nz.float().reshape(batch, res, res).contiguous()
     return None
 
 
@@ -259,7 +266,7 @@ def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0)
         b = styles.shape[0]
         wk = tcconv.modulate_weights(layer.weight, styles, demodulate=True, planes=planes, cin_padded=cin_p, cin_offset=cin_offset,
                                      prepared=_prepared(layer))
-    noise = _noise(layer, noise_mode)
+    noise = _noise(layer, noise_mode, b)
     bias = _bias(layer, cout_p)
     act_gain = layer.act_gain * gain
     clamp = float(layer.conv_clamp * gain) if layer.conv_clamp is not None else -1.0

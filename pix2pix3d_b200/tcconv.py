@@ -30,7 +30,7 @@ class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
         ('acc_scale', ctypes.c_float),
         ('up_prev', ctypes.c_void_p), ('up_filter', ctypes.c_void_p), ('round16', ctypes.c_int32), ('out_nchw', ctypes.c_int32),
         ('stride', ctypes.c_int32), ('reserved0', ctypes.c_int32), ('residual', ctypes.c_void_p),
-        ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64),
+        ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64), ('noise_batch_stride', ctypes.c_int64),
     ]
 
 
@@ -185,6 +185,8 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
         assert out.dtype == torch.float32
     a.bias = None if bias is None else bias.data_ptr()
     a.noise = None if noise is None else noise.data_ptr()
+    # [oH,oW] shared by the batch (noise_mode='const') or [B,oH,oW] (noise_mode='random')
+    a.noise_batch_stride = 0 if (noise is None or noise.ndim == 2) else noise.shape[-2] * noise.shape[-1]
     a.dscale = None if dscale is None else dscale.data_ptr()
     for t in (bias, noise, dscale):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
@@ -251,15 +253,18 @@ def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.
         b, ih, iw, c = x.shape
     oh, ow = out_hw
     y = torch.empty(out_planes, b, oh, ow, c, device=x.device, dtype=torch.float16)
+    nbs = 0 if (noise is None or noise.ndim == 2) else oh * ow          # per-sample noise images (noise_mode='random')
+    if noise is not None:
+        assert noise.is_contiguous() and noise.dtype == torch.float32 and noise.shape[-2:] == (oh, ow)
     with torch.cuda.device(x.device):
         if split_in:
             st = _lib.lib().p3d_fir_act_nhwc_split(_lib.ptr(x), _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b,
                                                    ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha, act_gain, clamp,
-                                                   _lib.stream_ptr())
+                                                   nbs, _lib.stream_ptr())
         else:
             st = _lib.lib().p3d_fir_act_nhwc(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias),
                                              _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha,
-                                             act_gain, clamp, _lib.stream_ptr())
+                                             act_gain, clamp, nbs, _lib.stream_ptr())
     _lib.check(st, 'p3d_fir_act_nhwc')
     _lib.bump()
     return y

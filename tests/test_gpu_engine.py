@@ -45,6 +45,38 @@ def test_synthesis_network_engine_matches_generic_fp32(cfg, noise_mode):
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-5      # three-pass split keeps fp32-level accuracy
 
 
+@pytest.mark.parametrize('cfg', [dict(channel_base=2048, channel_max=64, res=32, img_channels=96),
+                                 dict(channel_base=4096, channel_max=128, res=64, img_channels=3, num_fp16_res=2, conv_clamp=256)])
+def test_synthesis_network_engine_random_noise_consumes_the_same_rng_stream(cfg):
+    """noise_mode='random' (the API default, networks_stylegan2.py:320-321): the engine draws one noise image per sample and
+    layer with the same torch.randn calls in the same order as the op-by-op formulation, so seeding the generator identically
+    gives the same images -- and leaves the generator in the same state."""
+    from pix2pix3d_b200 import _lib, engine
+    net = _net(**cfg)
+    ws = torch.randn(3, net.num_ws, 64, device='cuda')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        engine.enabled = False
+        try:
+            torch.manual_seed(123)
+            ref = net(ws, noise_mode='random')
+            after_ref = torch.rand(4, device='cuda')
+        finally:
+            engine.enabled = True
+        n0 = _lib.launch_count
+        torch.manual_seed(123)
+        out = net(ws, noise_mode='random')
+        after = torch.rand(4, device='cuda')
+        torch.manual_seed(124)
+        other = net(ws, noise_mode='random')
+    assert _lib.launch_count - n0 > 10
+    assert torch.equal(after, after_ref)
+    tol = 2e-5 if not cfg.get('num_fp16_res') else 2e-2
+    assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < tol
+    assert rel_err(other.cpu().numpy(), ref.cpu().numpy()) > 10 * tol       # the noise is live
+
+
 def test_synthesis_network_engine_fp16_blocks():
     """fp16 blocks with conv_clamp (the super-resolution configuration): engine vs the reference-style fp16 path."""
     from pix2pix3d_b200 import engine

@@ -362,11 +362,12 @@ def test_per_ray_limits_in_kernel_and_ray_box_kernel():
     o, d = torch.from_numpy(g['ray_origins']), torch.from_numpy(g['ray_dirs'])
     # rays that miss, graze and hit; one direction component exactly zero
     d2 = d.clone(); d2[0, :5, 0] = 0.0; d2[0, 5:9] = torch.tensor([0.0, 0.0, 1.0])
+    d2[0, 9:13] = torch.nn.functional.normalize(torch.tensor([[1.0, 0.2, 0.1]]), dim=-1)      # looking sideways: misses the cube
     tn_cpu, tf_cpu = math_utils.get_ray_limits_box(o, d2, box_side_length=1.0)
     tn, tf = native.ray_limits_box(o.to(dev), d2.to(dev), 1.0)
     assert torch.equal(torch.nan_to_num(tn.cpu(), nan=-7), torch.nan_to_num(tn_cpu, nan=-7))
     assert torch.equal(torch.nan_to_num(tf.cpu(), nan=-7), torch.nan_to_num(tf_cpu, nan=-7))
-    assert (tn_cpu == -1).any() and (tn_cpu > 0).any()
+    assert (tn_cpu == -1).any() and (tf_cpu == -2).any() and (tn_cpu > 0).any()
 
     b, m = o.shape[:2]
     sc = opts['depth_resolution']
