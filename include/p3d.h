@@ -3,7 +3,7 @@
  *
  * Every entry point takes plain device pointers, sizes and a CUDA stream; the caller owns all
  * memory (allocates outputs, keeps inputs alive until the stream reaches the call). Nothing is
- * retained past return and there is no global mutable state (the reference's __constant__ filter
+ * retained past return and there is no global mutable state (no environment switches, no cached device properties: every decision follows from the arguments) (the reference's __constant__ filter
  * buffer, torch_utils/ops/filtered_lrelu.cu:81-82, is deliberately not reproduced).
  *
  * Return value: 0 = ok, <0 = p3d status (P3D_UNSUPPORTED: "no kernel for this configuration",
@@ -112,8 +112,9 @@ typedef struct {
      *   1  scalar ray limits (:187-190): d[k] = depth_table[k] + jitter * depth_delta, depth_table = torch.linspace(ray_start,
      *      ray_end, Sc), depth_delta = (ray_end - ray_start) / (Sc - 1), jitter = the torch.rand_like draw [B,R,Sc];
      *   2  per-ray limits (`ray_start == 'auto'`, :91-97, :181-186 with math_utils.linspace :101-118):
-     *      d[k] = ray_start[r] + depth_table[k] * (ray_end[r] - ray_start[r]) + jitter * ((ray_end[r] - ray_start[r]) / (Sc - 1)),
-     *      depth_table = arange(Sc) / (Sc - 1).
+     *      d[k] = ray_start[r] + depth_table[k] * (ray_end[r] - ray_start[r]) + jitter * ((ray_end[r] - ray_start[r]) * depth_delta),
+     *      depth_table = arange(Sc) / (Sc - 1), depth_delta = fp32(1) / fp32(Sc - 1) (torch's CUDA `tensor / scalar` multiplies
+     *      by the reciprocal).
      * Products and sums are rounded separately, in the reference's order, so the depths equal the torch results bit for bit.
      * Neutral at zero: older callers that never set these keep mode 0. */
     int32_t depth_mode;
@@ -121,7 +122,7 @@ typedef struct {
     const float* depth_table;    /* [Sc]      modes 1, 2 */
     const float* ray_start;      /* [B,R]     mode 2 */
     const float* ray_end;        /* [B,R]     mode 2 */
-    float   depth_delta;         /* mode 1 */
+    float   depth_delta;         /* modes 1, 2 */
     int32_t reserved1;
     /* Optional [B] plane-set index per image: rays of image b gather from plane set plane_index[b] (NULL: b). Lets V camera
      * views of one latent (applications/generate_video.py:57-69) share ONE resident plane set: planes batch 1, B = V. */
@@ -282,7 +283,8 @@ typedef struct {
     int32_t round16, out_nchw;
     /* strided convolutions (conv2d_resample.py:108-111, the down=2 layers of DiscriminatorBlock / the label-map Encoder):
      * output pixel (y, x) reads input pixels (stride*y + dy, stride*x + dx); stride 0/1 = dense, 2 supported. */
-    int32_t stride, reserved0;
+    int32_t stride;
+    int32_t launch_flags;     /* A/B switches, results unchanged: bit 0 = never the persistent kernel, bit 1 = never CTA pairs */
     /* resnet skip connection (networks_stylegan2.py:524-528): fp32 [B, oH, oW, Cout] (32-byte aligned, Cout % 8 == 0 for the
      * vector path) added after activation / gain / clamp; out_mode 0-2 with the identity output map. NULL = none. */
     const float* residual;

@@ -752,20 +752,18 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         if (area_out) *area_out = best;
         return bw_best;
     };
-    // persistent 256-pixel tiles when there is at least one tile per SM (P3D_CONV_PERSIST=0 disables, for A/B runs)
+    // persistent 256-pixel tiles when there is at least one tile per SM (launch_flags bit 0 disables, for A/B runs)
     bool persist = false, pair = false;
     int BW = pick_bw(1, nullptr);
     {
-        static int env = -1;
-        if (env < 0) { const char* e = getenv("P3D_CONV_PERSIST"); env = (e && e[0] == '0') ? 0 : 1; }
+        const int env = (p->launch_flags & 1) ? 0 : 1;
         long area2 = 0;
         const int bw2 = pick_bw(2, &area2);
         const long tiles2 = area2 / 256 * ceil_div(p->Cout_padded, BN) * p->B;
         if (env && tiles2 >= sm_count()) { persist = true; BW = bw2; }
         // CTA pairs (cta_group::2) for >= 256 output channels: one 256-pixel x 256-channel tile per pair
-        // (P3D_CONV_PAIR=0 keeps the single-CTA persistent kernel, for A/B runs)
-        static int env_pair = -1;
-        if (env_pair < 0) { const char* e = getenv("P3D_CONV_PAIR"); env_pair = (e && e[0] == '0') ? 0 : 1; }
+        // (launch_flags bit 1 keeps the single-CTA persistent kernel, for A/B runs)
+        const int env_pair = (p->launch_flags & 2) ? 0 : 1;
         const long tiles_pair = area2 / 256 * (p->Cout_padded / 256) * p->B;
         // (launches with a handful of k-steps per tile -- the 1- and 2-tap phases of a narrow transposed convolution -- are
         //  prologue/epilogue-bound and measured slightly slower on pairs)

@@ -721,15 +721,13 @@ __global__ void __launch_bounds__(128) sample_importance_kernel(const float* __r
     }
 }
 
-static int g_sm_count = 0;
+// SMs of the CURRENT device, queried on every call (an attribute read, no cache: the library keeps no state and a process
+// may drive several devices)
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-        g_sm_count = n;
-    }
-    return g_sm_count;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
 }
 
 }  // namespace p3d

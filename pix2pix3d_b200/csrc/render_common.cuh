@@ -85,7 +85,10 @@ __device__ __forceinline__ float coarse_depth(const p3d_render_args_t& a, int g,
     if (a.depth_mode == 1) return __fadd_rn(__ldg(a.depth_table + s), __fmul_rn(j, a.depth_delta));
     const float st = __ldg(a.ray_start + g), span = __fsub_rn(__ldg(a.ray_end + g), st);
     const float base = __fadd_rn(st, __fmul_rn(__ldg(a.depth_table + s), span));         // math_utils.linspace
-    return __fadd_rn(base, __fmul_rn(j, __fdiv_rn(span, (float)(Sc - 1))));
+    // `(ray_end - ray_start) / (N - 1)` is tensor / Python scalar: torch's CUDA kernel multiplies by the fp32 reciprocal
+    // (accscalar_t(1) / b) instead of dividing; depth_delta carries that reciprocal in this mode, so the depths equal the
+    // reference's CUDA path bit for bit (its CPU path divides, a last-ulp difference in the sample spacing)
+    return __fadd_rn(base, __fmul_rn(j, __fmul_rn(span, a.depth_delta)));
 }
 
 __device__ __forceinline__ int plane_set(const p3d_render_args_t& a, int image) {

@@ -581,12 +581,9 @@ extern "C" int p3d_render_fwd_tc(const p3d_render_args_t* args, p3d_stream_t str
         P.img_stride = (uint32_t)is; P.plane_stride = (uint32_t)pls; P.pix_stride = (uint32_t)pxs;
     }
     {
-        // args.tc_variant = 1 (or P3D_RENDER_TC_PAIRS=1 in the environment, for A/B runs of whole programs) selects the
-        // ray-pair variant (render_tc2.cu)
-        static int env_pairs = -1;
-        if (env_pairs < 0) { const char* e = getenv("P3D_RENDER_TC_PAIRS"); env_pairs = (e && e[0] == '1') ? 1 : 0; }
+        // args.tc_variant = 1 selects the ray-pair variant (render_tc2.cu)
         if (a.tc_variant == 1 && (a.Sc > 64 || a.Sf > 64)) return P3D_UNSUPPORTED;
-        if ((env_pairs == 1 || a.tc_variant == 1) && a.Sc <= 64 && a.Sf <= 64)
+        if (a.tc_variant == 1)
             return render_fwd_tc_pairs(a, P.img_stride, P.plane_stride, P.pix_stride, (cudaStream_t)stream);
     }
     P3D_CUDA_TRY(cudaMemsetAsync(a.workspace, 0, 4 * sizeof(uint32_t), (cudaStream_t)stream));

@@ -12,6 +12,7 @@ The module classes call into this when the inputs are CUDA tensors and no gradie
 draws one noise image per sample and layer with the reference's own `torch.randn` calls, in its order); every other case
 keeps the generic op-by-op formulation.
 """
+import logging
 import weakref
 
 import numpy as np
@@ -25,18 +26,33 @@ _SQRT2 = float(np.sqrt(2))
 enabled = True
 
 
+_log = logging.getLogger('pix2pix3d_b200.engine')
+_told = set()
+
+
+def _refuse(reason):
+    """A CUDA call leaves the tensor-core path: say so ONCE per reason (the op-by-op formulation is an order of magnitude
+    slower; a silent drop would look like a performance bug). Needing gradients is the normal training case and stays quiet."""
+    if reason not in _told:
+        _told.add(reason)
+        _log.warning('tensor-core fast path not taken: %s -- running the op-by-op formulation (libp3d ops + ATen convolutions)', reason)
+    return False
+
+
 def block_supported(block, ws, noise_mode, need_grad):
     if not enabled or ws.device.type != 'cuda' or need_grad:
         return False
     if noise_mode not in ('const', 'none', 'random'):
-        return False
+        return _refuse(f'noise_mode={noise_mode!r}')
     if block.architecture != 'skip':
-        return False
+        return _refuse(f"block architecture {block.architecture!r} (only 'skip' is built)")
     for name in ('conv0', 'conv1'):
         layer = getattr(block, name, None)
         if layer is not None and (layer.activation != 'lrelu' or layer.weight.shape[-1] != 3):
-            return False
-    return hasattr(block, 'torgb')
+            return _refuse(f'{name}: activation {layer.activation!r} / kernel {layer.weight.shape[-1]} (lrelu 3x3 is built)')
+    if not hasattr(block, 'torgb'):
+        return _refuse('block without a ToRGB layer')
+    return True
 
 
 def grad_needed(*modules_and_tensors):
@@ -503,22 +519,33 @@ def generator_supported(gen, ws, c, synthesis_kwargs, use_cached_backbone):
     """Can `TriPlane*Generator.synthesis` run end to end on the tensor-core / fused-render path?"""
     if ws.device.type != 'cuda' or grad_needed(gen, ws, c):
         return False
+    if not enabled:
+        return False
     extra = set(synthesis_kwargs) - {'noise_mode', 'force_fp32', 'fused_modconv'}
     if extra:
-        return False
+        return _refuse(f'synthesis kwargs {sorted(extra)} are not understood by the engine')
     noise_mode = synthesis_kwargs.get('noise_mode', 'random')
     net = gen.backbone.synthesis
     if net.img_channels != 96:
-        return False
+        return _refuse(f'backbone emits {net.img_channels} channels (3 x 32 tri-plane channels expected)')
     if not all(block_supported(getattr(net, f'b{r}'), ws, noise_mode, False) for r in net.block_resolutions):
         return False
     gen.renderer.plane_axes = gen.renderer.plane_axes.to(ws.device)
     if not gen.renderer.fusable_options(gen.decoder, gen.rendering_kwargs):
-        return False
+        return _refuse('rendering options / decoder type outside the fused renderer (density_noise, clamp_mode, custom plane '
+                       'axes, > 64 samples per pass or an unknown decoder class)')
     sr_noise = gen.rendering_kwargs['superresolution_noise_mode']
     nrr = gen.neural_rendering_resolution
     srs = [gen.superresolution] + ([gen.superresolution_semantic] if hasattr(gen, 'superresolution_semantic') else [])
-    return all(_sr_supported(sr, ws, sr_noise, nrr) for sr in srs)
+    for sr in srs:
+        if not (hasattr(sr, 'block0') and hasattr(sr, 'block1')):
+            return _refuse(f'super-resolution class {type(sr).__name__} is not a two-block stack')
+        if nrr != sr.input_resolution:
+            return _refuse(f'neural_rendering_resolution {nrr} != super-resolution input {sr.input_resolution}: the resize runs on '
+                           'the generic path (renderer, ops and SR stacks still use their own kernels)')
+        if not _sr_supported(sr, ws, sr_noise, nrr):
+            return False
+    return True
 
 
 def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=False, noise_mode='random', force_fp32=False):
@@ -543,15 +570,23 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
         specs += _block_specs(sr.block0, force_fp32, tcconv.pad_to(nch_feat, 64), nch_feat // 2 if k == 1 else 0)
         specs += _block_specs(sr.block1, force_fp32)
     styles = weight_plan(gen, ('gen', bool(force_fp32)), all_layers, specs).run(ws.to(torch.float32))
+    plane_index = None
     if use_cached_backbone and gen._last_planes is not None:
         # multi-view rendering from one latent (generate_video.py:57-69): the planes cached by an earlier call, kept in the
         # gather layout next to the NCHW tensor the reference API exposes as `_last_planes`
         planes_nchw = gen._last_planes
+        pb = planes_nchw.shape[0]
+        if pb != b:
+            # V camera views against ONE cached plane set: the renderer reads plane set 0 for every image (plane_index), the
+            # planes are neither copied nor re-generated. Same results as V single-view calls.
+            assert pb == 1, 'cached planes must hold one plane set or one per camera'
+            plane_index = torch.zeros(b, dtype=torch.int32, device=ws.device)
         cached = _derived.get(gen, {}).get('planes_cl')
         if cached is not None and cached[0] is planes_nchw and cached[1] == planes_nchw._version:
             planes_cl = cached[2]
         else:
-            planes_cl = native.planes_to_channels_last(planes_nchw.view(b, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
+            planes_cl = native.planes_to_channels_last(planes_nchw.view(pb, 3, 32, planes_nchw.shape[-2], planes_nchw.shape[-1]))
+            _derived.setdefault(gen, {})['planes_cl'] = (planes_nchw, planes_nchw._version, planes_cl)
     else:
         img = _run_network(net, styles[:n_net], noise_mode, force_fp32)                                      # [B,H,W,96]
         h, w = img.shape[1], img.shape[2]
@@ -560,7 +595,7 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
             gen._last_planes = tcconv.nhwc_to_nchw_f32(img)
             _derived.setdefault(gen, {})['planes_cl'] = (gen._last_planes, gen._last_planes._version, planes_cl)
     feats, depth, wsum = gen.renderer(None, gen.decoder, ray_origins, ray_directions, gen.rendering_kwargs,
-                                      planes_channels_last=planes_cl)
+                                      planes_channels_last=planes_cl, plane_index=plane_index)
     nch = feats.shape[-1]
     fimg = feats.view(b, nrr, nrr, nch)                     # [B,R,C] is already NHWC
     depth_image = depth.permute(0, 2, 1).reshape(b, 1, nrr, nrr)

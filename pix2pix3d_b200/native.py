@@ -5,6 +5,7 @@ has a CPU branch.
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -197,6 +198,7 @@ def render_fwd(planes_nhwc, dec, ray_origins, ray_dirs, depths_coarse, u, box_wa
             rs, re_ = _f32c(stratified['ray_start']).reshape(B, R), _f32c(stratified['ray_end']).reshape(B, R)
             keep += [rs, re_]
             a.depth_mode, a.ray_start, a.ray_end = 2, rs.data_ptr(), re_.data_ptr()
+            a.depth_delta = float(np.float32(1.0) / np.float32(Sc - 1))      # what `tensor / (Sc - 1)` multiplies by on CUDA
         else:
             a.depth_mode, a.depth_delta = 1, float(stratified['delta'])
     if plane_index is not None:

@@ -3,6 +3,7 @@
 Tensors on this path are NHWC fp16; a *split* tensor is `[2,B,H,W,C]` (hi, lo) with value hi + lo.
 """
 import ctypes
+import os
 
 import torch
 
@@ -29,9 +30,15 @@ class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
         ('act', ctypes.c_int32), ('alpha', ctypes.c_float), ('gain', ctypes.c_float), ('clamp', ctypes.c_float),
         ('acc_scale', ctypes.c_float),
         ('up_prev', ctypes.c_void_p), ('up_filter', ctypes.c_void_p), ('round16', ctypes.c_int32), ('out_nchw', ctypes.c_int32),
-        ('stride', ctypes.c_int32), ('reserved0', ctypes.c_int32), ('residual', ctypes.c_void_p),
+        ('stride', ctypes.c_int32), ('launch_flags', ctypes.c_int32), ('residual', ctypes.c_void_p),
         ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64), ('noise_batch_stride', ctypes.c_int64),
     ]
+
+
+# A/B switches of the convolution launcher (p3d_conv_args_t::launch_flags; results do not depend on them): bit 0 = never the
+# persistent kernel, bit 1 = never CTA pairs. The environment is read HERE, once, by the host binding -- the library has no
+# process-global switches.
+launch_flags = (1 if os.environ.get('P3D_CONV_PERSIST') == '0' else 0) | (2 if os.environ.get('P3D_CONV_PAIR') == '0' else 0)
 
 
 def pad_to(n, m):
@@ -192,6 +199,7 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
     a.act, a.alpha, a.gain, a.clamp, a.acc_scale = act, alpha, gain, clamp, acc_scale
     a.stride = stride
+    a.launch_flags = launch_flags
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.is_contiguous() and tuple(residual.shape) == (b, grid_hw[0], grid_hw[1], cout)
         a.residual = residual.data_ptr()

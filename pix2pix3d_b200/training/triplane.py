@@ -57,6 +57,10 @@ def render_to_images(gen, ws, c, neural_rendering_resolution, update_emas, cache
     if cache_backbone:
         gen._last_planes = planes
     planes = planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1])
+    if use_cached_backbone and planes.shape[0] == 1 and n > 1:
+        # extension of the cached-backbone call pattern (generate_video.py:57-69 renders 120 views of one latent, one call per
+        # view): a batch of cameras against ONE cached plane set; identical to n calls with one camera each
+        planes = planes.expand(n, -1, -1, -1, -1)
     feats, depth, _ = gen.renderer(planes, gen.decoder, ray_origins, ray_directions, gen.rendering_kwargs)
     h = w = gen.neural_rendering_resolution
     feature_image = feats.permute(0, 2, 1).reshape(n, feats.shape[-1], h, w).contiguous()

@@ -228,6 +228,57 @@ def test_cached_backbone_multi_view_rendering():
     assert rel_err(again['image'].cpu().numpy(), fresh['image'].cpu().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize('fast', [True, False])
+def test_batched_views_against_one_cached_plane_set(fast):
+    """SURVEY 8(f) rank 1, second half: V cameras in ONE call against the plane set cached from one latent
+    (`use_cached_backbone=True` with `_last_planes` of batch 1) == V single-camera calls fed the same renderer noise.
+    fast=True: engine path (plane_index in the fused kernel, no plane copies); False: generic op-by-op path."""
+    import pix2pix3d_b200.training.triplane_cond as tc
+    from make_golden import SYNTH_CASES, build_generator
+    from pix2pix3d_b200 import engine
+    case = dict(SYNTH_CASES['seg_nrr64'])
+    G = build_generator(tc, case).cuda()
+    g = load_golden('synthesis_seg_nrr64')
+    ws, c = torch.from_numpy(g['ws']).cuda(), torch.from_numpy(g['c']).cuda()
+    V, nrr = 3, case['nrr']
+    cv = c.repeat(V, 1)
+    cv[:, 3] += torch.tensor([0.0, 0.05, -0.04], device='cuda')
+    cv[:, 7] += torch.tensor([0.0, -0.03, 0.02], device='cuda')
+    gen = torch.Generator().manual_seed(7)
+    jit = torch.rand(V, nrr * nrr, case['Sc'], 1, generator=gen).cuda()
+    u = torch.rand(V * nrr * nrr, case['Sf'], generator=gen).cuda()
+    # fp32 super-resolution: split-K / algorithm choices depend on the batch size, which moves fp32 sums by an ulp and, in the
+    # fp16 SR stacks, occasionally the fp16 rounding of an activation (1e-3 of the image range); fp32 isolates the geometry
+    kw = dict(noise_mode='const', neural_rendering_resolution=nrr, force_fp32=True)
+
+    def replay(fn, j, uu):
+        it = iter([j, uu])
+        o_like, o_rand = torch.rand_like, torch.rand
+        torch.rand_like, torch.rand = (lambda x, *a, **k: next(it)), (lambda *a, **k: next(it))
+        try:
+            return fn()
+        finally:
+            torch.rand_like, torch.rand = o_like, o_rand
+
+    engine.enabled = fast
+    try:
+        with torch.no_grad():
+            replay(lambda: G.synthesis(ws, c, cache_backbone=True, **kw), jit[:1], u[:nrr * nrr])
+            assert G._last_planes.shape[0] == 1
+            batched = replay(lambda: G.synthesis(ws.expand(V, -1, -1), cv, use_cached_backbone=True, **kw), jit, u)
+            singles = [replay(lambda v=v: G.synthesis(ws, cv[v:v + 1], use_cached_backbone=True, **kw), jit[v:v + 1],
+                              u[v * nrr * nrr:(v + 1) * nrr * nrr]) for v in range(V)]
+    finally:
+        engine.enabled = True
+    for k in batched:
+        assert batched[k].shape[0] == V
+        want = torch.cat([s[k] for s in singles]).float().cpu().numpy()
+        # image_depth is clamped to the depth range of the CALL's batch (ray_marcher.py:50): compare where no clamp is active
+        tol = 1e-3 if k == 'image_depth' else 2e-5
+        assert rel_err(batched[k].float().cpu().numpy(), want) < tol, k
+    assert (batched['image'][0] - batched['image'][1]).abs().max() > 1e-4
+
+
 @pytest.mark.parametrize('res,in_ch', [(64, 6), (256, 1)])
 def test_encoder_engine_matches_generic_path(res, in_ch):
     """Label-map Encoder (triplane_cond.py:66-196) on the tensor-core path -- static-weight 3x3 convs, FIR + stride-2 convs

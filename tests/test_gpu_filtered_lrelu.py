@@ -49,14 +49,17 @@ def test_fused_matches_composition_forward_and_backward(up, down, fu, fd, paddin
     torch.manual_seed(0)
     x = torch.randn(2, 5, 23, 19, device=dev, dtype=dtype)
     b = torch.randn(5, device=dev, dtype=dtype)
+    # fp16 operands make x + b == 0 likely somewhere; at exactly 0 the CUDA op (and the reference's kernel, `v < 0`,
+    # filtered_lrelu.cu:1140) takes the positive branch while autograd of F.leaky_relu takes the slope: keep away from it
+    pre = x.float() + b.float()[None, :, None, None]
+    x = torch.where(pre.abs() < 1e-3, x + 0.0625, x)
     fu_t, fd_t = _filt(fu, dev), _filt(fd, dev)
     kw = dict(up=up, down=down, padding=padding, gain=1.3, slope=0.2, clamp=clamp, flip_filter=flip)
     xr, br = x.double().requires_grad_(True), b.double().requires_grad_(True)
-    ref = fl._filtered_lrelu_ref(xr, fu=None if fu_t is None else fu_t.double(), fd=None if fd_t is None else fd_t.double(), b=br, **kw)
+    ref = fl._filtered_lrelu_ref(xr, fu=fu_t, fd=fd_t, b=br, **kw)          # filters stay fp32, arithmetic in fp64
     xg, bg = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
     n0 = _lib.launch_count
-    with pytest.warns(None) if False else _nullcontext():
-        y = fl.filtered_lrelu(xg, fu_t, fd_t, bg, **kw)
+    y = fl.filtered_lrelu(xg, fu_t, fd_t, bg, **kw)
     assert _lib.launch_count > n0 and y.dtype == dtype and y.shape == ref.shape
     tol = 2e-5 if dtype == torch.float32 else 4e-3
     assert rel_err(y.detach().float().cpu().numpy(), ref.detach().cpu().numpy()) < tol

@@ -108,3 +108,52 @@ def test_reference_op_wrappers_run_on_libp3d_plugins():
     assert len(want) == len(got)
     for (n, w), (_, g) in zip(want, got):
         assert rel_err(g, w) < 2e-6, n
+
+
+def test_reference_filtered_lrelu_wrapper_runs_on_libp3d_plugin():
+    """The reference's torch_utils/ops/filtered_lrelu.py (autograd class, sign-tensor hand-off between forward and backward,
+    fallback on rc = -1) unmodified, once on its stock JIT-built plugin and once on this package's `filtered_lrelu_plugin`."""
+    import scipy.signal
+    rh.import_reference()
+    import torch_utils.ops.filtered_lrelu as r_fl
+    from pix2pix3d_b200.torch_utils import custom_ops as ours
+    dev = torch.device('cuda')
+    assert r_fl._init()
+    stock = r_fl._plugin
+    mine = ours.get_plugin('filtered_lrelu_plugin', sources=['filtered_lrelu.cpp'])
+    torch.manual_seed(0)
+    k12 = torch.as_tensor(scipy.signal.firwin(numtaps=12, cutoff=0.25, width=0.3, fs=2.0), dtype=torch.float32, device=dev)
+    f4 = torch.tensor([1., 3., 3., 1.], device=dev)
+    f4 = torch.outer(f4, f4) / 64
+    cases = [dict(fu=k12, fd=k12, up=2, down=2, padding=[10, 9, 10, 9], gain=1.4, slope=0.2, clamp=256),
+             dict(fu=f4, fd=f4, up=2, down=2, padding=[3, 2, 3, 2], gain=1.0, slope=0.2, clamp=0.8),
+             dict(fu=k12, fd=None, up=2, down=1, padding=[5, 6, 5, 6], gain=2 ** 0.5, slope=0.2, clamp=None, flip_filter=True)]
+
+    def run_all():
+        res = []
+        for kw in cases:
+            # the stock plugin has no fused kernel for 2-D filters at up = down = 2 (filtered_lrelu.cu:1252-1259 lists none):
+            # it composes upfirdn2d + act + upfirdn2d, which in fp16 rounds the up-sampled tensor and so takes other lrelu /
+            # clamp branches than a kernel that keeps fp32 inside; compare that case in fp32 only
+            for dtype in ((torch.float32, torch.float16) if kw['fu'].ndim == 1 else (torch.float32,)):
+                x = torch.randn(2, 6, 25, 20, device=dev, generator=torch.Generator(dev).manual_seed(1)).to(dtype).requires_grad_(True)
+                b = torch.randn(6, device=dev, generator=torch.Generator(dev).manual_seed(2)).to(dtype).requires_grad_(True)
+                y = r_fl.filtered_lrelu(x, b=b, impl='cuda', **kw)
+                gx, gb = torch.autograd.grad(y.float().square().sum(), [x, b])
+                res += [(dtype, y), (dtype, gx), (dtype, gb)]
+        return [(d, t.detach().float().cpu().numpy()) for d, t in res]
+
+    import warnings
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', RuntimeWarning)
+            want = run_all()
+            r_fl._plugin = mine
+            got = run_all()
+    finally:
+        r_fl._plugin = stock
+    for i, ((d, w), (_, g)) in enumerate(zip(want, got)):
+        # fp16: both kernels hold fp32 inside but sum in different orders; an element within rounding of 0 / the clamp may
+        # take the other branch, which moves single gradient entries
+        tol = 2e-5 if d == torch.float32 else 2e-2
+        assert rel_err(g, w) < tol, (i, d, rel_err(g, w))
