@@ -195,9 +195,10 @@ __global__ void __launch_bounds__(kFlThreads) filtered_lrelu_kernel(const FlrPar
 }
 
 // ---- in-place activation with the same sign contract (the reference's fallback path, filtered_lrelu.cu:1110-1215) --------
-template <int MODE>
-__global__ void filtered_lrelu_act_kernel(void* x, unsigned char* s, int dtype, int W, int H, int64_t planes, int C, int64_t st_x, int64_t st_y,
-                                          int64_t st_c, int64_t st_n, int sW_elems, int sH, int sox, int soy, float gain, float slope, float clamp) {
+// T: storage type (__half, float, double); Acc: arithmetic type (float; double for double, as the reference's InternalType)
+template <int MODE, typename T, typename Acc>
+__global__ void filtered_lrelu_act_kernel(T* x, unsigned char* s, int W, int H, int64_t planes, int C, int64_t st_x, int64_t st_y,
+                                          int64_t st_c, int64_t st_n, int sW_elems, int sH, int sox, int soy, Acc gain, Acc slope, Acc clamp) {
     const int ymax = MODE == 1 ? sH : H;
     const int xmax = MODE == 1 ? sW_elems : W;
     const int64_t per_plane = (int64_t)((xmax + 3) >> 2) * ymax;           // one thread per group of four elements (= one sign byte)
@@ -213,21 +214,21 @@ __global__ void filtered_lrelu_act_kernel(void* x, unsigned char* s, int dtype, 
             const int xx = bx * 4 + k;
             if (xx < W && y < H) {
                 const int64_t ix = (int64_t)xx * st_x + (int64_t)y * st_y + (int64_t)c * st_c + (int64_t)n * st_n;
-                float v = flr_load(x, ix, dtype) * gain;
+                Acc v = (Acc)x[ix] * gain;
                 if (MODE == 2) {
                     const uint32_t sx = (uint32_t)(xx + sox), sy = (uint32_t)(y + soy);
                     if (sx < (uint32_t)sW_elems && sy < (uint32_t)sH) {
                         const int rr = s[(sx >> 2) + (int64_t)(sW_elems >> 2) * (sy + (int64_t)sH * q)] >> ((sx & 3) << 1);
                         if (rr & 1) v *= slope;
-                        if (rr & 2) v = 0.f;
+                        if (rr & 2) v = (Acc)0;
                     }
                 } else {
                     uint32_t sg = 0;
-                    if (v < 0.f) { v *= slope; sg = 1; }
-                    if (fabsf(v) > clamp) { v = v < 0.f ? -clamp : clamp; sg = 2; }
+                    if (v < (Acc)0) { v *= slope; sg = 1; }
+                    if ((v < (Acc)0 ? -v : v) > clamp) { v = v < (Acc)0 ? -clamp : clamp; sg = 2; }
                     byte |= sg << (2 * k);
                 }
-                flr_store(x, ix, dtype, v);
+                x[ix] = (T)v;
             }
         }
         if (MODE == 1 && bx * 4 < sW_elems) s[bx + (int64_t)(sW_elems >> 2) * (y + (int64_t)sH * q)] = (unsigned char)byte;
@@ -307,7 +308,7 @@ extern "C" int p3d_filtered_lrelu_act(void* x, unsigned char* s, int dtype, cons
                                       const int32_t s_shape[2], const int32_t s_ofs[2], float gain, float slope, float clamp,
                                       int sign_mode, p3d_stream_t stream) {
     if (!x || !x_shape || !x_stride || sign_mode < 0 || sign_mode > 2 || (sign_mode && (!s || !s_shape))) return P3D_BAD_ARG;
-    if (dtype != P3D_F32 && dtype != P3D_F16) return P3D_UNSUPPORTED;
+    if (dtype != P3D_F32 && dtype != P3D_F16 && dtype != P3D_F64) return P3D_UNSUPPORTED;
     const int W = x_shape[0], H = x_shape[1], C = x_shape[2], N = x_shape[3];
     if (W <= 0 || H <= 0 || C <= 0 || N <= 0) return P3D_BAD_ARG;
     const int sW = sign_mode ? s_shape[0] : 0, sH = sign_mode ? s_shape[1] : 0;       // width in ELEMENTS (multiple of 4)
@@ -320,9 +321,13 @@ extern "C" int p3d_filtered_lrelu_act(void* x, unsigned char* s, int dtype, cons
     if (blocks > 148 * 64) blocks = 148 * 64;
     if (blocks < 1) blocks = 1;
     const int sox = s_ofs ? s_ofs[0] : 0, soy = s_ofs ? s_ofs[1] : 0;
-#define P3D_FLA(M) filtered_lrelu_act_kernel<M><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(                       \
-        x, s, dtype, W, H, planes, C, x_stride[0], x_stride[1], x_stride[2], x_stride[3], sW, sH, sox, soy, gain, slope, clamp)
-    if (sign_mode == 0) P3D_FLA(0); else if (sign_mode == 1) P3D_FLA(1); else P3D_FLA(2);
+#define P3D_FLA(M, T, A) filtered_lrelu_act_kernel<M, T, A><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(               \
+        (T*)x, s, W, H, planes, C, x_stride[0], x_stride[1], x_stride[2], x_stride[3], sW, sH, sox, soy, (A)gain, (A)slope, (A)clamp)
+#define P3D_FLA_T(T, A) do { if (sign_mode == 0) P3D_FLA(0, T, A); else if (sign_mode == 1) P3D_FLA(1, T, A); else P3D_FLA(2, T, A); } while (0)
+    if (dtype == P3D_F16) P3D_FLA_T(__half, float);
+    else if (dtype == P3D_F32) P3D_FLA_T(float, float);
+    else P3D_FLA_T(double, double);
+#undef P3D_FLA_T
 #undef P3D_FLA
     P3D_LAUNCH_CHECK();
     return P3D_OK;

@@ -2,7 +2,9 @@
 
 Surface of the reference's torch_utils/ops/conv2d_gradfix.py (:23 `enabled`, :26-33 `no_weight_gradients`,
 :37-45 entry points). The forward / data-gradient / weight-gradient convolutions are ATen calls, exactly as in the reference
-(:128-129, :169); the inference path does not go through this module (engine.py drives libp3d's implicit-GEMM kernels).
+(:128-129, :169) -- except inside `native_conv.first_order()` regions (the generator's training passes), where fp32 stride-1
+convolutions run forward and input gradient on libp3d's tcgen05 implicit GEMM (native_conv.py). The inference path does not go
+through this module (engine.py drives the same kernels directly).
 """
 import contextlib
 
@@ -31,6 +33,10 @@ def _use_custom(x):
 
 
 def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
+    from . import native_conv
+    if native_conv.applies(input, weight, bias, _pair(stride), _pair(padding), _pair(dilation), groups):
+        # fp32 training convolutions of the generator / label-map encoder: forward + input gradient on p3d_conv_gemm
+        return native_conv.conv2d(input, weight)
     if _use_custom(input):
         return _make_op(False, weight.shape, _pair(stride), _pair(padding), (0, 0), _pair(dilation), groups).apply(
             input, weight, bias)

@@ -149,8 +149,8 @@ def _plugin_filtered_lrelu(x, fu, fd, b, si, up, down, px0, px1, py0, py1, sx, s
 def _plugin_filtered_lrelu_act_(x, si, sx, sy, gain, slope, clamp, write_signs):
     """In place on x; returns the sign tensor when write_signs (filtered_lrelu.cpp:217-270)."""
     assert x.is_cuda and x.ndim == 4 and x.numel() > 0
-    if x.dtype not in (torch.float16, torch.float32):
-        raise TypeError('filtered_lrelu_act_: x must be float16 or float32')
+    if x.dtype not in _lib.DTYPE_CODE:
+        raise TypeError('filtered_lrelu_act_: x must be float16, float32 or float64')
     n, c, h, w = x.shape
     read_signs = si is not None and si.numel() > 0
     so, s = None, si

@@ -1,0 +1,85 @@
+"""fp32 convolutions of the training path on the tcgen05 implicit-GEMM kernel (`p3d_conv_gemm`, three-pass fp16 split = fp32
+accuracy) instead of cuDNN's fp32 SIMT kernels (TF32 is off during training, training_loop.py:278-279, which leaves cuDNN at
+~60 TFLOP/s on a B200).
+
+Scope: what `conv2d_gradfix.conv2d` receives from the non-fused modulated convolutions of the generator and from the label-map
+Encoder when gradients are required (`networks_stylegan2.py:68-75`, `conv2d_resample.py:134-136`): 3x3 (padding 1) and 1x1
+(padding 0), stride 1, dilation 1, groups 1, no bias, fp32 NCHW. Forward and the input gradient run on libp3d (the input
+gradient of a stride-1 convolution is the same convolution with the kernel flipped and its channel axes swapped); the weight
+gradient stays ATen's `convolution_backward` (a tcgen05 wgrad needs MN-major operand tiles: not built). First-order only: the
+node is used where no double backward can follow (inside `first_order()`, which the generator's `mapping` / `synthesis` /
+`sample_mixed` enter; the discriminators, whose R1 penalty differentiates twice, never do).
+"""
+import contextlib
+
+import torch
+
+_depth = 0
+enabled = True             # module switch (tests flip it for A/B)
+min_pixels = 256           # below this the launch is latency-bound either way: leave it to cuDNN
+
+
+@contextlib.contextmanager
+def first_order():
+    """Region in which convolutions are differentiated at most once."""
+    global _depth
+    _depth += 1
+    try:
+        yield
+    finally:
+        _depth -= 1
+
+
+def applies(x, w, bias, stride, padding, dilation, groups):
+    if not (enabled and _depth > 0 and bias is None and isinstance(x, torch.Tensor) and x.is_cuda):
+        return False
+    if x.dtype != torch.float32 or w.dtype != torch.float32 or x.ndim != 4:
+        return False
+    k = w.shape[2]
+    if w.shape[2] != w.shape[3] or k not in (1, 3) or groups != 1:
+        return False
+    if tuple(stride) != (1, 1) or tuple(dilation) != (1, 1) or tuple(padding) != (k // 2, k // 2):
+        return False
+    if x.shape[2] * x.shape[3] < min_pixels or x.shape[0] > 4096:
+        return False
+    return torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
+
+
+def _conv(x, w):
+    """x [B,I,H,W] fp32, w [O,I,k,k] fp32 -> [B,O,H,W] fp32 (stride 1, 'same' padding), three tensor-core passes."""
+    from ... import tcconv
+    b, i, h, wd = x.shape
+    o, _, k, _ = w.shape
+    ip = tcconv.pad_to(i, 64)
+    xh = tcconv.to_nhwc_f16(x.contiguous(), c_padded=ip, planes=2)                      # hi/lo split, channels padded
+    ones = torch.ones(1, i, device=x.device, dtype=torch.float32)
+    wk = tcconv.modulate_weights(w, ones, demodulate=False, pre_scale=1.0, planes=2, cin_padded=ip)   # K-major hi/lo, x WEIGHT_SCALE
+    y = torch.empty(b, h, wd, o, device=x.device, dtype=torch.float32)
+    taps = tcconv.TAPS_3X3 if k == 3 else tcconv.TAPS_1X1
+    tcconv.conv_gemm(xh, wk, o, taps, (h, wd), y, out_mode=2, split=True, act=1, gain=1.0)
+    return tcconv.nhwc_to_nchw_f32(y)
+
+
+class _Conv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return _conv(x, w)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        from . import conv2d_gradfix
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _conv(dy, w.flip([2, 3]).transpose(0, 1).contiguous())
+        if ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled:
+            k = w.shape[2]
+            dw = torch.ops.aten.convolution_backward(dy.contiguous(), x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,
+                                                     [False, True, False])[1]
+        return dx, dw
+
+
+def conv2d(x, w):
+    return _Conv2d.apply(x, w)

@@ -146,3 +146,27 @@ class TriPlaneGenerator(torch.nn.Module):
         ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
         return self.synthesis(ws, c, update_emas=update_emas, neural_rendering_resolution=neural_rendering_resolution,
                               cache_backbone=cache_backbone, use_cached_backbone=use_cached_backbone, **synthesis_kwargs)
+
+
+def mark_first_order(*classes):
+    """The generator is differentiated once per pass in every loss of the reference (training/loss.py: no path-length or other
+    second-order term touches G): run its `mapping` / `synthesis` / `sample` / `sample_mixed` inside
+    `native_conv.first_order()`, which lets the fp32 training convolutions use the tcgen05 implicit GEMM for forward and input
+    gradient (torch_utils/ops/native_conv.py). The discriminators never enter such a region (R1 differentiates twice)."""
+    import functools
+    from ..torch_utils.ops import native_conv
+    for cls in classes:
+        for name in ('mapping', 'synthesis', 'sample', 'sample_mixed'):
+            fn = cls.__dict__.get(name) or getattr(cls, name, None)
+            if fn is None or getattr(fn, '_p3d_first_order', False):
+                continue
+
+            def wrapped(self, *args, __fn=fn, **kwargs):
+                with native_conv.first_order():
+                    return __fn(self, *args, **kwargs)
+            functools.update_wrapper(wrapped, fn)
+            wrapped._p3d_first_order = True
+            setattr(cls, name, wrapped)
+
+
+mark_first_order(TriPlaneGenerator)

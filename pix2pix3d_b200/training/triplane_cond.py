@@ -648,3 +648,8 @@ class TriPlaneSemanticEntangleGenerator_withBG(_CondGeneratorBase):
         depth_bg = torch.ones_like(depth_samples) * rendering_kwargs['ray_end']
         depth_samples = depth_samples + depth_bg * (1 - weights_samples)
         return feature_samples, depth_samples
+
+
+from .triplane import mark_first_order  # noqa: E402
+
+mark_first_order(TriPlaneGenerator, TriPlaneSemanticGenerator, TriPlaneSemanticEntangleGenerator, TriPlaneSemanticEntangleGenerator_withBG)
