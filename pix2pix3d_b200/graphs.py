@@ -15,6 +15,10 @@ class GraphedSynthesis:
 
     def __init__(self, G, ws, c, warmup=2, **synthesis_kwargs):
         assert ws.is_cuda and c.is_cuda
+        if G.rendering_kwargs.get('ray_start') == 'auto':
+            # ImportanceRenderer.forward reads `torch.any(is_ray_valid).item()` for per-ray limits (renderer.py:94): a host
+            # synchronisation, which a stream capture cannot contain
+            raise ValueError("GraphedSynthesis: ray_start='auto' needs a host read-back per call; call G.synthesis directly")
         self.G = G
         self.kwargs = synthesis_kwargs
         self.ws = ws.clone()

@@ -42,6 +42,10 @@ def applies(x, w, bias, stride, padding, dilation, groups):
         return False
     if x.shape[2] * x.shape[3] < min_pixels or x.shape[0] > 4096:
         return False
+    if w.shape[0] > 128 and w.shape[0] % 128:          # beyond one 128-channel tile the kernel wants whole tiles (256, 512, ...)
+        return False
+    if w.shape[1] > 128 and w.shape[1] % 128:          # (the input gradient swaps the channel roles)
+        return False
     return torch.is_grad_enabled() and (x.requires_grad or w.requires_grad)
 
 
@@ -73,7 +77,12 @@ class _Conv2d(torch.autograd.Function):
         x, w = ctx.saved_tensors
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _conv(dy, w.flip([2, 3]).transpose(0, 1).contiguous())
+            # gradients sit far below fp16's normal range (1e-6 and less), where the hi/lo split has no bits left: bring the
+            # tensor's largest magnitude to ~2^10 with a power-of-two scale (exact), undo it on the result. The scale stays on
+            # the device (no host read-back).
+            amax = dy.detach().abs().amax().clamp_min(1e-30)
+            scale = torch.exp2(torch.floor(torch.log2(1024.0 / amax)))
+            dx = _conv(dy * scale, w.flip([2, 3]).transpose(0, 1).contiguous()) / scale
         if ctx.needs_input_grad[1] and not conv2d_gradfix.weight_gradients_disabled:
             k = w.shape[2]
             dw = torch.ops.aten.convolution_backward(dy.contiguous(), x, w, None, [1, 1], [k // 2, k // 2], [1, 1], False, [0, 0], 1,

@@ -78,3 +78,23 @@ def test_no_weight_gradients_skips_dw():
     with cg.no_weight_gradients():
         custom(x, w, None).sum().backward()
     assert w.grad is None and x.grad is not None
+
+
+def test_native_conv_dispatch_is_cuda_only_and_scoped():
+    """native_conv.applies: never for CPU tensors, never outside first_order(); the generator classes enter the region in
+    mapping / synthesis / sample / sample_mixed and leave it again."""
+    from pix2pix3d_b200.torch_utils.ops import native_conv
+    import pix2pix3d_b200.training.triplane_cond as tc
+    x = torch.randn(1, 8, 16, 16, requires_grad=True)
+    w = torch.randn(8, 8, 3, 3, requires_grad=True)
+    with native_conv.first_order():
+        assert native_conv._depth == 1
+        assert not native_conv.applies(x, w, None, (1, 1), (1, 1), (1, 1), 1)
+        y = cg.conv2d(x, w, padding=1)
+    assert native_conv._depth == 0 and y.shape == (1, 8, 16, 16)
+    for cls in (tc.TriPlaneGenerator, tc.TriPlaneSemanticGenerator, tc.TriPlaneSemanticEntangleGenerator,
+                tc.TriPlaneSemanticEntangleGenerator_withBG):
+        for name in ('mapping', 'synthesis', 'sample', 'sample_mixed'):
+            assert getattr(getattr(cls, name), '_p3d_first_order', False), (cls.__name__, name)
+    import pix2pix3d_b200.training.dual_discriminator as dd
+    assert not getattr(dd.DualDiscriminator.forward, '_p3d_first_order', False)      # R1 differentiates D twice

@@ -14,7 +14,7 @@ CASES = [
     (3, 6, 64, 40, 24, 1),          # fromrgb-like: few input channels, non-square, not a multiple of the tile
     (2, 512, 512, 16, 16, 3),
     (2, 128, 3, 64, 64, 1),         # ToRGB-like
-    (1, 96, 200, 17, 19, 3),        # ragged everything
+    (1, 96, 104, 17, 19, 3),        # ragged spatial size, padded input channels, ragged output channels
 ]
 
 
@@ -23,6 +23,7 @@ def test_forward_and_gradients_match_fp64(b, cin, cout, h, w, k):
     from pix2pix3d_b200 import _lib
     from pix2pix3d_b200.torch_utils.ops import conv2d_gradfix, native_conv
     dev = torch.device('cuda')
+    torch.backends.cudnn.allow_tf32 = False                 # the weight gradient is ATen's: keep it true fp32
     torch.manual_seed(0)
     x = torch.randn(b, cin, h, w, device=dev, requires_grad=True)
     wt = (torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5).requires_grad_(True)
@@ -30,7 +31,7 @@ def test_forward_and_gradients_match_fp64(b, cin, cout, h, w, k):
     with native_conv.first_order():
         y = conv2d_gradfix.conv2d(x, wt, padding=k // 2)
     assert _lib.launch_count - n0 >= 3, 'the native node was expected'
-    gy = torch.randn_like(y)
+    gy = torch.randn_like(y) * 1e-6                         # gradients are tiny in practice: the node must not lose them in fp16
     dx, dw = torch.autograd.grad((y * gy).sum(), [x, wt])
     xr, wr = x.detach().double().requires_grad_(True), wt.detach().double().requires_grad_(True)
     yr = torch.nn.functional.conv2d(xr, wr, padding=k // 2)
@@ -41,6 +42,7 @@ def test_forward_and_gradients_match_fp64(b, cin, cout, h, w, k):
 
 
 def test_dispatch_rules():
+    """(also: more than 128 channels must come in whole 128-channel tiles -- 208 goes to ATen)"""
     from pix2pix3d_b200 import _lib
     from pix2pix3d_b200.torch_utils.ops import conv2d_gradfix, native_conv
     dev = torch.device('cuda')
@@ -56,6 +58,8 @@ def test_dispatch_rules():
     with native_conv.first_order():
         assert launches(lambda: conv2d_gradfix.conv2d(x, w, padding=1)) > 0
         assert launches(lambda: conv2d_gradfix.conv2d(x, w, padding=1, stride=2)) == 0          # strided: not covered
+        w208 = torch.randn(208, 64, 3, 3, device=dev, requires_grad=True)
+        assert launches(lambda: conv2d_gradfix.conv2d(x, w208, padding=1)) == 0                # ragged beyond one channel tile
         assert launches(lambda: conv2d_gradfix.conv2d(x.half(), w.half(), padding=1)) == 0      # fp16 layers stay on cuDNN
         assert launches(lambda: conv2d_gradfix.conv2d(x, w, bias=torch.zeros(64, device=dev), padding=1)) == 0
         with torch.no_grad():
