@@ -17,7 +17,7 @@ ARM = textwrap.dedent('''
     import json, sys
     sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + '/baseline')
     import torch
-    torch.set_num_threads(8)
+    torch.set_num_threads(4)
     if {ours}:
         import pix2pix3d_b200
         pix2pix3d_b200.install(reference_root={ref!r})
@@ -37,17 +37,23 @@ ARM = textwrap.dedent('''
 ''')
 
 
-def _run(ours):
+def _start(ours):
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
-    r = subprocess.run([sys.executable, '-c', ARM.format(root=ROOT, ref=REF, ours=ours)], capture_output=True, text=True, timeout=1500, env=env)
-    assert r.returncode == 0, r.stderr[-3000:]
-    line = [ln for ln in r.stdout.splitlines() if ln.startswith('DIGEST ')][-1]
+    return subprocess.Popen([sys.executable, '-c', ARM.format(root=ROOT, ref=REF, ours=ours)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                            text=True, env=env)
+
+
+def _finish(p):
+    out, err = p.communicate(timeout=1500)
+    assert p.returncode == 0, err[-3000:]
+    line = [ln for ln in out.splitlines() if ln.startswith('DIGEST ')][-1]
     return json.loads(line[7:])
 
 
 @pytest.mark.skipif(REF is None, reason='needs a reference checkout (/root/reference or baseline/_ref)')
 def test_training_iteration_matches_reference_on_cpu():
-    ref, ours = _run(False), _run(True)
+    procs = _start(False), _start(True)                      # the two arms run side by side (4 torch threads each)
+    ref, ours = _finish(procs[0]), _finish(procs[1])
     assert ref['phases'] == ours['phases'] == ['Gmain', 'Greg', 'Dmain', 'Dreg', 'D_semanticmain', 'D_semanticreg']
     assert ref['bytes'] == ours['bytes']                       # same flat-gradient size per phase = same parameter sets with grads
     for k in ('G', 'D', 'D_semantic'):
