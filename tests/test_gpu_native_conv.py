@@ -102,3 +102,4 @@ def test_generator_training_gradients_use_the_native_node():
     assert ga.keys() == gb.keys()
     worst = max(rel_err(ga[k].float().cpu().numpy(), gb[k].float().cpu().numpy()) for k in ga if gb[k].abs().max() > 0)
     assert worst < 2e-3, worst
+
