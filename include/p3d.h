@@ -299,6 +299,13 @@ typedef struct {
  * transposed 3x3 convolution are all expressed through the tap list and the output map. */
 int p3d_conv_gemm(const p3d_conv_args_t* args, p3d_stream_t stream);
 
+/* Up to four launches that differ ONLY in their tap list, computed grid (gH, gW) and output offset (oy, ox) -- the four
+ * phases of a stride-2 transposed 3x3 convolution (conv2d_resample.py:114-131) -- as ONE launch whose tile schedule walks all
+ * phases, heaviest first (the 1- and 2-tap phases alone are prologue-bound and leave most of the machine idle at their tails).
+ * Every other field must be equal across phases[0..n_phases); up_prev / residual are not accepted. P3D_BAD_ARG otherwise.
+ * Results are identical to n_phases separate p3d_conv_gemm calls. */
+int p3d_conv_gemm_phases(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t stream);
+
 /* Per-sample modulated (and optionally demodulated) weights, modulated_conv2d lines :58-67:
  *   w'[b,o,i,k] = weight[o,i,k] * styles[b,i];  d[b,o] = rsqrt(sum_{i,k} w'^2 + 1e-8);  out = w' * d * scale
  * written K-major [planes][B][Cout_padded][kh*kw][Cin_padded] as fp16 (planes = 2: hi/lo split). Rows >= Cout and
@@ -400,6 +407,13 @@ int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noi
                            int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                            float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                            p3d_stream_t stream);
+
+/* The previous formulation of both entries above (one tile per CTA, scalar fp32 arithmetic; split_in selects the hi/lo input),
+ * kept for A/B measurements of the persistent fp32-pair kernel: same arguments, bit-identical results. */
+int p3d_fir_act_nhwc_v1(const void* x, int in_dtype, int split_in, const float* f, const float* noise, const float* bias, void* y,
+                        int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                        float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                        p3d_stream_t stream);
 
 /* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */
 int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream);

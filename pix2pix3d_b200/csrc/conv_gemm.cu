@@ -25,17 +25,28 @@ constexpr int kBM = 128;        // pixels per tile (= TMEM lanes)
 constexpr int kBK = 64;         // fp16 elements per k-step (128-byte swizzle span)
 constexpr int kMaxGroups = 27;  // 9 taps x 3 precision passes
 
+// One output phase of a launch. An ordinary convolution has one; a stride-2 transposed convolution run as ONE launch has four
+// (tap subsets of the same weight tensor over the same input, each writing its own parity of the (2H+1) x (2W+1) grid).
+struct ConvPhase {
+    int g0, ng;                       // groups [g0, g0 + ng) of the k-loop tables below
+    int gH, gW, oy, ox;               // computed grid and output offset (Y = y*sy + oy)
+    int tiles_x, tiles_y;             // tiles of this phase's grid
+    int t0;                           // first tile of the phase in the launch's tile order
+    int pad;
+    long long p0;                     // split-K: offset (floats) of the phase's partials [splits][B][gH][gW][Cout_pad]
+};
+
 struct ConvKernelArgs {
     // k-loop: groups of (tap, A plane, B plane); each group covers Cin channels in kc steps
-    int n_groups, kc_steps;
+    int n_phases, kc_steps;
+    ConvPhase ph[4];
     int8_t dy[kMaxGroups], dx[kMaxGroups], a_plane[kMaxGroups], b_plane[kMaxGroups], tap[kMaxGroups];
     int Cin;
     // tiling
-    int BW, BH, tiles_x, tiles_y, BN, w_per_sample;
+    int BW, BH, BN, w_per_sample;
     uint32_t idesc, tmem_cols;
     // epilogue
-    int gH, gW;                       // size of the computed grid (phase grid for transposed conv)
-    int oH, oW, sy, oy, sx, ox;       // output tensor size and affine map (Y = y*sy + oy)
+    int oH, oW, sy, sx;               // output tensor size and the stride of the output map (Y = y*sy + phase.oy)
     int Cout, y_cstride, y_coff;      // valid channels, channel stride of the output tensor, channel offset
     void* y; void* y_lo;
     int out_mode;                     // 0: f16, 1: f16 hi/lo split, 2: f32, 3: f32 accumulate (+=)
@@ -44,7 +55,7 @@ struct ConvKernelArgs {
     float alpha, clamp, acc_scale;
     int base_aligned;                 // y / y_lo are 32-byte aligned (256-bit stores allowed)
     int splits;                       // split-K: blockIdx.z = b * splits + s; s covers k-steps [s*total/splits, (s+1)*total/splits)
-    float* partial;                   // split-K: raw fp32 accumulators [splits][B][gH][gW][Cout_pad] (finished by a second kernel)
+    float* partial;                   // split-K: raw fp32 accumulators, per phase [splits][B][gH][gW][Cout_pad] (finished by a second kernel)
     int Cout_pad;
     // fused ToRGB tail (SynthesisBlock.forward, networks_stylegan2.py:452-458): out = upsample2d(prev, f) + [fp16-rounded] y
     const float* up_prev;             // [B, oH/2, oW/2, Cout] fp32 NHWC skip image of the previous block, or NULL
@@ -54,6 +65,15 @@ struct ConvKernelArgs {
     int round16, out_nchw;            // round y to fp16 first (fp16 blocks); write [B, Cout, oH, oW] instead of NHWC
     float pre_gain, post_gain;        // gain folded into scale/bias/noise (lrelu is positively homogeneous) or applied last
 };
+
+// phase that owns tile `t` of the launch's tile order (phases are consecutive ranges starting at ph[q].t0)
+__device__ __forceinline__ ConvPhase conv_phase_of(const ConvKernelArgs& a, int t) {
+    ConvPhase P = a.ph[0];
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+        if (q < a.n_phases && t >= a.ph[q].t0) P = a.ph[q];
+    return P;
+}
 
 // 256-bit global accesses (sm_100): one full 32-byte sector per lane
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
@@ -104,28 +124,34 @@ __device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32
             }
         const int nvalid = min(32, C - ch0);
         float* yo = reinterpret_cast<float*>(a.y);
-        if (!a.out_nchw && (C & 3) == 0 && nvalid == 32 && a.base_aligned) {
+        if (!a.out_nchw && (C & 7) == 0 && nvalid == 32 && a.base_aligned && ((reinterpret_cast<uintptr_t>(a.up_prev) & 31) == 0)) {
+            // one full 32-byte sector per lane and access: the lanes of a warp are different pixels (C * 4 bytes apart), so the
+            // number of sectors an access touches is what its cost follows
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const int ch = ch0 + 4 * g4;
-                float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int g8 = 0; g8 < 4; ++g8) {
+                const int ch = ch0 + 8 * g8;
+                float u[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) u[t] = 0.f;
 #pragma unroll
                 for (int aa = 0; aa < 2; ++aa)
 #pragma unroll
                     for (int cc = 0; cc < 2; ++cc) {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(pp[aa][cc] + ch));
+                        uint32_t tq[8];
+                        ld_global_256(pp[aa][cc] + ch, tq);
                         const float w = w4[aa][cc];
-                        u.x = fmaf(w, t.x, u.x); u.y = fmaf(w, t.y, u.y); u.z = fmaf(w, t.z, u.z); u.w = fmaf(w, t.w, u.w);
-                    }
-                float r[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    float x = conv_epilogue_act<kAct, kClamp>(fmaf(__uint_as_float(v[4 * g4 + t]), s_scale[c0 + 4 * g4 + t], s_bias[c0 + 4 * g4 + t]) + nz,
+                        for (int t = 0; t < 8; ++t) u[t] = fmaf(w, __uint_as_float(tq[t]), u[t]);
+                    }
+                uint32_t o[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    float x = conv_epilogue_act<kAct, kClamp>(fmaf(__uint_as_float(v[8 * g8 + t]), s_scale[c0 + 8 * g8 + t], s_bias[c0 + 8 * g8 + t]) + nz,
                                                               alpha, post_gain, clampv);
                     if (a.round16) x = __half2float(__float2half_rn(x));
-                    r[t] = x;
+                    o[t] = __float_as_uint(u[t] + x);
                 }
-                *reinterpret_cast<float4*>(yo + off + 4 * g4) = make_float4(u.x + r[0], u.y + r[1], u.z + r[2], u.w + r[3]);
+                st_global_256(yo + off + 8 * g8, o);
             }
         } else {
 #pragma unroll
@@ -243,11 +269,13 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
     float* s_bias = s_scale + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    const int tile_n = blockIdx.y;
+    const ConvPhase P = conv_phase_of(a, (int)blockIdx.x);      // t0 counts spatial tiles here (blockIdx.x)
+    const int tile_m = (int)blockIdx.x - P.t0;
     const int b = blockIdx.z / a.splits, ksplit = blockIdx.z - b * a.splits;
-    const int ty = tile_m / a.tiles_x, tx = tile_m % a.tiles_x;
+    const int ty = tile_m / P.tiles_x, tx = tile_m % P.tiles_x;
     const int n0 = tile_n * a.BN;
-    const int all_k = a.n_groups * a.kc_steps;
+    const int all_k = P.ng * a.kc_steps;
     const int k_begin = (int)((long long)all_k * ksplit / a.splits), k_end = (int)((long long)all_k * (ksplit + 1) / a.splits);
     const int total_k = k_end - k_begin;
 
@@ -285,6 +313,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int g = k_begin / a.kc_steps, kc = k_begin - g * a.kc_steps;
+            g += P.g0;
             for (int k = 0; k < total_k; ++k) {
                 const int x0 = tx * a.BW * a.stride + a.dx[g], y0 = ty * a.BH * a.stride + a.dy[g];
                 const int kb = a.tap[g] * a.Cin;
@@ -320,8 +349,8 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
         const int q = warp & 3;
         const int m = q * 32 + lane;                    // tile row = TMEM lane
         const int gy = ty * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
-        const bool pix_ok = (gy < a.gH) && (gx < a.gW);
-        const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
+        const bool pix_ok = (gy < P.gH) && (gx < P.gW);
+        const int Y = gy * a.sy + P.oy, X = gx * a.sx + P.ox;
         const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
         const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
         const int out_mode = a.out_mode;
@@ -339,7 +368,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
             const int ch0 = n0 + c0;
             if (a.partial) {
                 // split-K: raw accumulators of this k-range; conv_splitk_finish_kernel sums the ranges and applies the epilogue
-                float* pp = a.partial + ((((size_t)ksplit * gridDim.z / a.splits + b) * a.gH + gy) * a.gW + gx) * a.Cout_pad + ch0;
+                float* pp = a.partial + P.p0 + ((((size_t)ksplit * (gridDim.z / a.splits) + b) * P.gH + gy) * P.gW + gx) * a.Cout_pad + ch0;
                 const int ncols = min(32, a.BN - c0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -387,8 +416,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
     float* s_const = reinterpret_cast<float*>(smem + kPStages * stage_bytes + 128);     // [2 parities][scale 128 | bias 128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_k = a.n_groups * a.kc_steps;
-    const int tiles_m = a.tiles_x * a.tiles_y;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -408,10 +435,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
-                const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+                const ConvPhase P = conv_phase_of(a, tile);
+                const int lt = tile - P.t0, tiles_m = P.tiles_x * P.tiles_y;
+                const int tm = lt % tiles_m, tn = (lt / tiles_m) % tiles_n, b = lt / (tiles_m * tiles_n);
+                const int ty = tm / P.tiles_x, tx = tm % P.tiles_x;
                 const int n0 = tn * a.BN;
-                int g = 0, kc = 0;
+                const int total_k = P.ng * a.kc_steps;
+                int g = P.g0, kc = 0;
                 for (int k = 0; k < total_k; ++k) {
                     const int x0 = tx * a.BW * a.stride + a.dx[g], y0 = ty * 2 * a.BH * a.stride + a.dy[g];
                     const int kb = a.tap[g] * a.Cin;
@@ -431,6 +461,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int total_k = conv_phase_of(a, tile).ng * a.kc_steps;
                 tc::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);        // the epilogue drained this accumulator pair
                 tc::tc_fence_after();
                 const uint32_t acc0 = tmem_base + (uint32_t)(as * 256);
@@ -461,8 +492,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
         int as = 0; uint32_t aphase = 0;
         int parity = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
-            const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+            const ConvPhase P = conv_phase_of(a, tile);
+            const int lt = tile - P.t0, tiles_m = P.tiles_x * P.tiles_y;
+            const int tm = lt % tiles_m, tn = (lt / tiles_m) % tiles_n, b = lt / (tiles_m * tiles_n);
+            const int ty = tm / P.tiles_x, tx = tm % P.tiles_x;
             const int n0 = tn * a.BN;
             float* s_scale = s_const + parity * 256;
             float* s_bias = s_scale + 128;
@@ -479,8 +512,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
             }
             tc::named_bar_sync(1, 256);                 // constants of this tile visible to all epilogue warps
             const int gy = (ty * 2 + mt) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
-            const bool pix_ok = (gy < a.gH) && (gx < a.gW);
-            const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
+            const bool pix_ok = (gy < P.gH) && (gx < P.gW);
+            const int Y = gy * a.sy + P.oy, X = gx * a.sx + P.ox;
             const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
             const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
             const bool vec_ok = a.base_aligned && ((n0 + a.BN) <= a.Cout) && (a.BN % 32 == 0) &&
@@ -540,8 +573,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = tc::cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const int total_k = a.n_groups * a.kc_steps;
-    const int tiles_m = a.tiles_x * a.tiles_y;
 
     if (warp == 0 && lane == 0) {
         tc::tma_prefetch_desc(&tmA);
@@ -562,10 +593,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-                const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
-                const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+                const ConvPhase P = conv_phase_of(a, tile);
+                const int lt = tile - P.t0, tiles_m = P.tiles_x * P.tiles_y;
+                const int tm = lt % tiles_m, tn = (lt / tiles_m) % tiles_n, b = lt / (tiles_m * tiles_n);
+                const int ty = tm / P.tiles_x, tx = tm % P.tiles_x;
                 const int n0 = tn * 256 + (int)rank * 128;
-                int g = 0, kc = 0;
+                const int total_k = P.ng * a.kc_steps;
+                int g = P.g0, kc = 0;
                 for (int k = 0; k < total_k; ++k) {
                     const int x0 = tx * a.BW * a.stride + a.dx[g], y0 = (ty * 2 + (int)rank) * a.BH * a.stride + a.dy[g];
                     const int kb = a.tap[g] * a.Cin;
@@ -586,6 +620,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+                const int total_k = conv_phase_of(a, tile).ng * a.kc_steps;
                 tc::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);        // both CTAs' epilogues drained this accumulator
                 tc::tc_fence_after();
                 const uint32_t acc = tmem_base + (uint32_t)(as * 256);
@@ -614,8 +649,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
         int as = 0; uint32_t aphase = 0;
         int parity = 0;
         for (int tile = pair; tile < n_tiles; tile += n_pairs) {
-            const int tm = tile % tiles_m, tn = (tile / tiles_m) % tiles_n, b = tile / (tiles_m * tiles_n);
-            const int ty = tm / a.tiles_x, tx = tm % a.tiles_x;
+            const ConvPhase P = conv_phase_of(a, tile);
+            const int lt = tile - P.t0, tiles_m = P.tiles_x * P.tiles_y;
+            const int tm = lt % tiles_m, tn = (lt / tiles_m) % tiles_n, b = lt / (tiles_m * tiles_n);
+            const int ty = tm / P.tiles_x, tx = tm % P.tiles_x;
             const int n0 = tn * 256;
             float* s_scale = s_const + parity * 512;
             float* s_bias = s_scale + 256;
@@ -632,8 +669,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
             }
             tc::named_bar_sync(1, 256);
             const int gy = (ty * 2 + (int)rank) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
-            const bool pix_ok = (gy < a.gH) && (gx < a.gW);
-            const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
+            const bool pix_ok = (gy < P.gH) && (gx < P.gW);
+            const int Y = gy * a.sy + P.oy, X = gx * a.sx + P.ox;
             const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
             const float nz = (a.noise && pix_ok) ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
             const bool vec_ok = a.base_aligned && ((n0 + 256) <= a.Cout) &&
@@ -670,45 +707,50 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
 // epilogue as the fused path. One thread per (pixel, 4 channels).
 __global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const ConvKernelArgs a, int B, int act) {
     const int cq = a.Cout_pad >> 2;
-    const size_t total = (size_t)B * a.gH * a.gW * cq;
-    const size_t split_stride = (size_t)B * a.gH * a.gW * a.Cout_pad;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(idx % cq) * 4;
-        size_t t = idx / cq;
-        const int gx = (int)(t % a.gW); t /= a.gW;
-        const int gy = (int)(t % a.gH);
-        const int b = (int)(t / a.gH);
-        if (c4 >= a.Cout) continue;
-        const float* pp = a.partial + (((size_t)b * a.gH + gy) * a.gW + gx) * a.Cout_pad + c4;
-        float4 acc = *reinterpret_cast<const float4*>(pp);
-        for (int s = 1; s < a.splits; ++s) {
-            const float4 q = *reinterpret_cast<const float4*>(pp + s * split_stride);
-            acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
-        }
-        const int Y = gy * a.sy + a.oy, X = gx * a.sx + a.ox;
-        const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
-        const float nz = a.noise ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
-        const float accv[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int ch = c4 + k;
-            if (ch >= a.Cout) break;
-            float sc = a.acc_scale * a.pre_gain;
-            if (a.dscale) sc *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
-            const float bi = a.bias ? __ldg(a.bias + ch) * a.pre_gain : 0.f;
-            float x = fmaf(accv[k], sc, bi) + nz;
-            if (act == 1) x = fmaxf(x, x * a.alpha);
-            if (act == 2) x = x > 0.f ? x : x * a.alpha;
-            x *= a.post_gain;
-            if (a.clamp >= 0.f) x = fminf(fmaxf(x, -a.clamp), a.clamp);
-            const size_t off = pix * a.y_cstride + a.y_coff + ch;
-            if (a.out_mode <= 1) {
-                const __half h = __float2half_rn(x);
-                reinterpret_cast<__half*>(a.y)[off] = h;
-                if (a.out_mode == 1) reinterpret_cast<__half*>(a.y_lo)[off] = __float2half_rn(x - __half2float(h));
-            } else {
-                float* yf = reinterpret_cast<float*>(a.y) + off;
-                *yf = (a.out_mode == 3 ? *yf : 0.f) + x;
+    for (int p = 0; p < 4; ++p) {
+        if (p >= a.n_phases) break;
+        const ConvPhase P = a.ph[p];
+        const size_t total = (size_t)B * P.gH * P.gW * cq;
+        const size_t split_stride = (size_t)B * P.gH * P.gW * a.Cout_pad;
+        for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+            const int c4 = (int)(idx % cq) * 4;
+            size_t t = idx / cq;
+            const int gx = (int)(t % P.gW); t /= P.gW;
+            const int gy = (int)(t % P.gH);
+            const int b = (int)(t / P.gH);
+            if (c4 >= a.Cout) continue;
+            const float* pp = a.partial + P.p0 + (((size_t)b * P.gH + gy) * P.gW + gx) * a.Cout_pad + c4;
+            float4 acc = *reinterpret_cast<const float4*>(pp);
+            for (int s = 1; s < a.splits; ++s) {
+                const float4 q = *reinterpret_cast<const float4*>(pp + s * split_stride);
+                acc.x += q.x; acc.y += q.y; acc.z += q.z; acc.w += q.w;
+            }
+            const int Y = gy * a.sy + P.oy, X = gx * a.sx + P.ox;
+            const size_t pix = ((size_t)b * a.oH + Y) * a.oW + X;
+            const float nz = a.noise ? __ldg(a.noise + (size_t)b * a.noise_bstride + (size_t)Y * a.oW + X) * a.pre_gain : 0.f;
+            const float accv[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ch = c4 + k;
+                if (ch >= a.Cout) break;
+                float sc = a.acc_scale * a.pre_gain;
+                if (a.dscale) sc *= __ldg(a.dscale + (size_t)b * a.Cout + ch);
+                const float bi = a.bias ? __ldg(a.bias + ch) * a.pre_gain : 0.f;
+                float x = fmaf(accv[k], sc, bi) + nz;
+                if (act == 1) x = fmaxf(x, x * a.alpha);
+                if (act == 2) x = x > 0.f ? x : x * a.alpha;
+                x *= a.post_gain;
+                if (a.clamp >= 0.f) x = fminf(fmaxf(x, -a.clamp), a.clamp);
+                const size_t off = pix * a.y_cstride + a.y_coff + ch;
+                if (a.out_mode <= 1) {
+                    const __half h = __float2half_rn(x);
+                    reinterpret_cast<__half*>(a.y)[off] = h;
+                    if (a.out_mode == 1) reinterpret_cast<__half*>(a.y_lo)[off] = __float2half_rn(x - __half2float(h));
+                } else {
+                    float* yf = reinterpret_cast<float*>(a.y) + off;
+                    *yf = (a.out_mode == 3 ? *yf : 0.f) + x;
+                }
             }
         }
     }
@@ -726,18 +768,41 @@ static int make_tmap_f16_sw128(CUtensorMap* tm, const void* base, int rank, cons
 
 using namespace p3d;
 
-extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
-    if (!p || !p->x || !p->w || !p->y) return P3D_BAD_ARG;
-    if (p->C % kBK != 0 || p->C <= 0 || p->n_taps < 1 || p->n_taps > 9) return P3D_UNSUPPORTED;
+// phases[0..n_phases): launches that differ only in their tap list, computed grid (gH, gW) and output offset (oy, ox)
+static int conv_launch(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t stream) {
+    if (!phases || n_phases < 1 || n_phases > 4) return P3D_BAD_ARG;
+    const p3d_conv_args_t* p = phases;
+    if (!p->x || !p->w || !p->y) return P3D_BAD_ARG;
+    if (p->C % kBK != 0 || p->C <= 0) return P3D_UNSUPPORTED;
     if (p->x_planes < 1 || p->x_planes > 2 || p->w_planes < 1 || p->w_planes > 2) return P3D_BAD_ARG;
     if (p->split && (p->x_planes != 2 || p->w_planes != 2)) return P3D_BAD_ARG;
     if (p->out_mode < 0 || p->out_mode > 3 || (p->out_mode == 1 && !p->y_lo)) return P3D_BAD_ARG;
     if (p->Cout_padded % 16 != 0 || p->Cout_padded < p->Cout) return P3D_BAD_ARG;
-    if (p->gH <= 0 || p->gW <= 0 || p->B <= 0) return P3D_BAD_ARG;
+    if (p->B <= 0) return P3D_BAD_ARG;
+    const int passes = p->split ? 3 : 1;
+    int taps_total = 0, taps_max = 0, gH_max = 0, gW_max = 0;
+    for (int q = 0; q < n_phases; ++q) {
+        const p3d_conv_args_t* r = phases + q;
+        if (r->n_taps < 1 || r->n_taps > 9 || r->gH <= 0 || r->gW <= 0) return q == 0 ? P3D_UNSUPPORTED : P3D_BAD_ARG;
+        if (q > 0 && (r->x != p->x || r->w != p->w || r->y != p->y || r->y_lo != p->y_lo || r->x_planes != p->x_planes ||
+                      r->w_planes != p->w_planes || r->B != p->B || r->Bw != p->Bw || r->H != p->H || r->W != p->W || r->C != p->C ||
+                      r->Cout != p->Cout || r->Cout_padded != p->Cout_padded || r->n_kblocks != p->n_kblocks || r->split != p->split ||
+                      r->oH != p->oH || r->oW != p->oW || r->sy != p->sy || r->sx != p->sx || r->y_cstride != p->y_cstride ||
+                      r->y_coff != p->y_coff || r->out_mode != p->out_mode || r->bias != p->bias || r->noise != p->noise ||
+                      r->dscale != p->dscale || r->act != p->act || r->alpha != p->alpha || r->gain != p->gain || r->clamp != p->clamp ||
+                      r->acc_scale != p->acc_scale || r->up_prev || p->up_prev || r->residual || p->residual || r->stride != p->stride ||
+                      r->noise_batch_stride != p->noise_batch_stride))
+            return P3D_BAD_ARG;
+        taps_total += r->n_taps;
+        if (r->n_taps > taps_max) taps_max = r->n_taps;
+        if (r->gH > gH_max) gH_max = r->gH;
+        if (r->gW > gW_max) gW_max = r->gW;
+    }
+    if (taps_total * passes > kMaxGroups) return P3D_UNSUPPORTED;
 
     const int BN = p->Cout_padded > 128 ? 128 : p->Cout_padded;
-    // spatial tile BW x BH = 128 pixels: the power-of-two split with the least padded area (ties -> wider rows);
-    // `rows` = sub-tiles stacked in y per CTA tile (2 for the persistent kernel)
+    // spatial tile BW x BH = 128 pixels: the power-of-two split with the least padded area (ties -> wider rows), summed over
+    // the phases (they share the TMA box); `rows` = sub-tiles stacked in y per CTA tile (2 for the persistent kernels)
     const int stride = p->stride > 1 ? p->stride : 1;
     if (stride > 2) return P3D_UNSUPPORTED;
     auto pick_bw = [&](int rows, long* area_out) {
@@ -746,7 +811,8 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         for (int bw = 1; bw <= 64; bw *= 2) {
             int bh = kBM / bw * rows;
             if (bw * stride > 256 || bh * stride > 256) continue;      // TMA box extent (in input pixels) <= 256
-            long area = (long)ceil_div(p->gW, bw) * bw * ceil_div(p->gH, bh) * bh;
+            long area = 0;
+            for (int q = 0; q < n_phases; ++q) area += (long)ceil_div(phases[q].gW, bw) * bw * ceil_div(phases[q].gH, bh) * bh;
             if (best < 0 || area <= best) { best = area; bw_best = bw; }
         }
         if (area_out) *area_out = best;
@@ -766,8 +832,8 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         const int env_pair = (p->launch_flags & 2) ? 0 : 1;
         const long tiles_pair = area2 / 256 * (p->Cout_padded / 256) * p->B;
         // (launches with a handful of k-steps per tile -- the 1- and 2-tap phases of a narrow transposed convolution -- are
-        //  prologue/epilogue-bound and measured slightly slower on pairs)
-        const int k_steps = (p->split ? 3 : 1) * p->n_taps * (p->C / kBK);
+        //  prologue/epilogue-bound and measured slightly slower on pairs; a merged launch is judged by its heaviest phase)
+        const int k_steps = passes * taps_max * (p->C / kBK);
         if (persist && env_pair && p->Cout_padded % 256 == 0 && tiles_pair * 2 >= sm_count() && k_steps >= 8) pair = true;
     }
     const int BH = kBM / BW;
@@ -796,24 +862,37 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
 
     ConvKernelArgs a;
     memset(&a, 0, sizeof(a));
-    int g = 0;
-    const int passes = p->split ? 3 : 1;
     static const int pa[3] = {0, 0, 1}, pb[3] = {0, 1, 0};     // hi*hi, hi*lo, lo*hi
-    for (int pass = 0; pass < passes; ++pass)
-        for (int t = 0; t < p->n_taps; ++t) {
-            a.dy[g] = p->tap_dy[t]; a.dx[g] = p->tap_dx[t]; a.tap[g] = p->tap_k[t];
-            a.a_plane[g] = (int8_t)pa[pass]; a.b_plane[g] = (int8_t)pb[pass];
-            ++g;
-        }
-    a.n_groups = g;
+    const int tiles_n = pair ? p->Cout_padded / 256 : ceil_div(p->Cout_padded, BN);
+    int g = 0, tiles_m_total = 0, max_total_k = 0, min_total_k = 1 << 30;
+    a.n_phases = n_phases;
     a.kc_steps = p->C / kBK;
+    for (int q = 0; q < n_phases; ++q) {
+        const p3d_conv_args_t* r = phases + q;
+        ConvPhase& P = a.ph[q];
+        P.g0 = g;
+        for (int pass = 0; pass < passes; ++pass)
+            for (int t = 0; t < r->n_taps; ++t) {
+                a.dy[g] = r->tap_dy[t]; a.dx[g] = r->tap_dx[t]; a.tap[g] = r->tap_k[t];
+                a.a_plane[g] = (int8_t)pa[pass]; a.b_plane[g] = (int8_t)pb[pass];
+                ++g;
+            }
+        P.ng = g - P.g0;
+        P.gH = r->gH; P.gW = r->gW; P.oy = r->oy; P.ox = r->ox;
+        P.tiles_x = ceil_div(r->gW, BW); P.tiles_y = ceil_div(r->gH, persist ? 2 * BH : BH);
+        // tile order: spatial tiles for the grid kernel (blockIdx.x), whole (spatial, channel, sample) tiles for the persistent ones
+        P.t0 = persist ? tiles_m_total * tiles_n * p->B : tiles_m_total;
+        tiles_m_total += P.tiles_x * P.tiles_y;
+        const int tk = P.ng * a.kc_steps;
+        if (tk > max_total_k) max_total_k = tk;
+        if (tk < min_total_k) min_total_k = tk;
+    }
     a.Cin = p->C;
     a.BW = BW; a.BH = BH;
-    a.tiles_x = ceil_div(p->gW, BW); a.tiles_y = ceil_div(p->gH, persist ? 2 * BH : BH);
     a.BN = BN; a.w_per_sample = p->Bw > 1 ? 1 : 0;
     a.idesc = tc::umma_idesc_f16(kBM, BN, 0);
     a.tmem_cols = BN <= 32 ? 32u : BN <= 64 ? 64u : 128u;
-    a.gH = p->gH; a.gW = p->gW; a.oH = p->oH; a.oW = p->oW; a.sy = p->sy; a.oy = p->oy; a.sx = p->sx; a.ox = p->ox;
+    a.oH = p->oH; a.oW = p->oW; a.sy = p->sy; a.sx = p->sx;
     a.Cout = p->Cout; a.y_cstride = p->y_cstride; a.y_coff = p->y_coff;
     a.y = p->y; a.y_lo = p->y_lo; a.out_mode = p->out_mode;
     a.bias = p->bias; a.noise = p->noise; a.dscale = p->dscale;
@@ -846,14 +925,13 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     // 3 stages (96 KB at BN = 128): two CTAs per SM, so one tile's epilogue / TMA latency hides behind the other's MMAs.
     // Grids that leave at most one CTA per SM anyway (the 4^2..32^2 backbone layers: 16-128 CTAs with 200+ k-steps each)
     // are bound by TMA latency x bytes in flight instead; they get a 6-stage ring (192 KB).
-    dim3 grid(a.tiles_x * a.tiles_y, ceil_div(p->Cout_padded, BN), p->B);
-    const int total_k = a.n_groups * a.kc_steps;
+    dim3 grid(tiles_m_total, ceil_div(p->Cout_padded, BN), p->B);
     const long base_ctas = (long)grid.x * grid.y * grid.z;
     if (pair) {
         a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
         a.BN = 256;
         a.idesc = tc::umma_idesc_f16(256, 256, 0);
-        const int tiles_n = p->Cout_padded / 256, n_tiles = a.tiles_x * a.tiles_y * tiles_n * p->B;
+        const int n_tiles = tiles_m_total * tiles_n * p->B;
         const size_t smem_q = kQStages * (size_t)(kBM * 128 + 128 * 128) + 256 + 2 * 512 * sizeof(float) + 1024;
         int pairs = sm_count() / 2;
         if (pairs > n_tiles) pairs = n_tiles;
@@ -882,7 +960,7 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     }
     if (persist) {
         a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
-        const int tiles_n = (int)grid.y, n_tiles = (int)base_ctas;
+        const int n_tiles = (int)base_ctas;
         const size_t stage_bytes_p = 2 * (size_t)kBM * 128 + (size_t)BN * 128;
         const size_t smem_p = kPStages * stage_bytes_p + 128 + 2 * 256 * sizeof(float) + 1024;
         const int ctas = n_tiles < sm_count() ? n_tiles : sm_count();
@@ -901,21 +979,28 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
     }
     // split-K for grids far smaller than the machine (4^2..16^2 layers: 16-32 CTAs each streaming 100-200 k-steps at
     // the per-SM L2 ingest rate): every k-range becomes its own CTA writing raw fp32 partials into the caller's scratch
-    // buffer; conv_splitk_finish_kernel adds them in a fixed order and applies the epilogue.
+    // buffer; conv_splitk_finish_kernel adds them in a fixed order and applies the epilogue. Two CTAs fit an SM, so the
+    // split count aims at two waves' worth of CTAs; every phase of a merged launch is split the same number of ways.
     a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
-    if (p->splitk_scratch && !p->up_prev && !p->residual && base_ctas * 2 <= sm_count() && total_k >= 8) {
-        int splits = (int)(sm_count() / base_ctas);
-        if (splits > total_k / 4) splits = total_k / 4;
+    if (p->splitk_scratch && !p->up_prev && !p->residual && base_ctas * 2 <= sm_count() && min_total_k >= 8) {
+        int splits = (int)((n_phases > 1 ? 2 * sm_count() : sm_count()) / base_ctas);
+        if (splits > min_total_k / 4) splits = min_total_k / 4;
         if (splits > 16) splits = 16;
-        const size_t per_split = (size_t)p->B * p->gH * p->gW * p->Cout_padded * sizeof(float);
+        size_t per_split = 0;
+        for (int q = 0; q < n_phases; ++q) per_split += (size_t)p->B * phases[q].gH * phases[q].gW * p->Cout_padded * sizeof(float);
         while (splits > 1 && per_split * splits > (size_t)p->splitk_scratch_bytes) --splits;
         if (splits > 1 && (((uintptr_t)p->splitk_scratch) & 31) == 0) {
             a.splits = splits;
             a.partial = reinterpret_cast<float*>(p->splitk_scratch);
             grid.z = p->B * splits;
+            long long off = 0;
+            for (int q = 0; q < n_phases; ++q) {
+                a.ph[q].p0 = off;
+                off += (long long)splits * p->B * phases[q].gH * phases[q].gW * p->Cout_padded;
+            }
         }
     }
-    const bool deep = (long)grid.x * grid.y * grid.z <= sm_count() && total_k / a.splits > 6;
+    const bool deep = (long)grid.x * grid.y * grid.z <= sm_count() && max_total_k / a.splits > 6;
     const size_t stage_bytes = (size_t)kBM * 128 + (size_t)BN * 128;
     const size_t smem = (deep ? 6 : 3) * stage_bytes + 64 + 2 * 128 * sizeof(float) + 1024 + (deep ? 64 : 0);
 #define P3D_LAUNCH_CONV_S(ST, ACT, CL)                                                                                        \
@@ -933,7 +1018,11 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
 #undef P3D_LAUNCH_CONV
     P3D_LAUNCH_CHECK();
     if (a.splits > 1) {
-        const size_t items = (size_t)p->B * p->gH * p->gW * (p->Cout_padded / 4);
+        size_t items = 0;
+        for (int q = 0; q < n_phases; ++q) {
+            const size_t it = (size_t)p->B * phases[q].gH * phases[q].gW * (p->Cout_padded / 4);
+            if (it > items) items = it;
+        }
         size_t blocks = (items + 255) / 256;
         const size_t cap = (size_t)sm_count() * 16;
         if (blocks > cap) blocks = cap;
@@ -941,4 +1030,10 @@ extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) {
         P3D_LAUNCH_CHECK();
     }
     return P3D_OK;
+}
+
+extern "C" int p3d_conv_gemm(const p3d_conv_args_t* p, p3d_stream_t stream) { return conv_launch(p, 1, stream); }
+
+extern "C" int p3d_conv_gemm_phases(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t stream) {
+    return conv_launch(phases, n_phases, stream);
 }

@@ -159,11 +159,10 @@ def _splitk_scratch(device):
     return buf
 
 
-def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
-              noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True,
-              up_prev=None, up_filter=None, round16=False, out_nchw=False, stride=1, residual=None):
-    """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;
-    out: NHWC tensor [B,oH,oW,Cs] (fp16 or fp32); out_map = (sy, oy, sx, ox)."""
+def _conv_args(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
+               noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True,
+               up_prev=None, up_filter=None, round16=False, out_nchw=False, stride=1, residual=None):
+    """The p3d_conv_args_t of one convolution launch (see conv_gemm)."""
     xp, b, h, wd, c = x.shape
     wp, bw, op, kk = w.shape
     assert x.dtype == torch.float16 and w.dtype == torch.float16 and x.is_contiguous() and w.is_contiguous()
@@ -210,21 +209,33 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(
     if split_k:
         scratch = _splitk_scratch(x.device)
         a.splitk_scratch, a.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
+    return a
+
+
+def _launch(device, call, name, flops, split):
+    """Run one libp3d convolution launch; with native.kernel_events set, bracket it with CUDA events (bench.py's tensor roofline)."""
     from . import native
     ev = None
     if native.kernel_events is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    with torch.cuda.device(x.device):
-        st = _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr())
+    with torch.cuda.device(device):
+        st = call()
     if ev is not None:
         ev[1].record()
         # algorithmic FLOPs of the convolution this launch implements (one pass); the fp32 layers execute 3x that on the
         # tensor pipe (hi*hi + hi*lo + lo*hi)
-        flops = 2.0 * b * grid_hw[0] * grid_hw[1] * cout * len(taps) * c
         native.kernel_events.append(('conv_gemm', ev[0], ev[1], flops, flops * (3 if split else 1)))
-    _lib.check(st, 'p3d_conv_gemm')
+    _lib.check(st, name)
     _lib.bump()
+
+
+def conv_gemm(x, w, cout, taps, grid_hw, out, split=False, **kw):
+    """x [xp,B,H,W,C] fp16, w [wp,Bw,Op,nk*C] fp16; taps: list of (dy, dx, kblock); grid_hw: computed grid;
+    out: NHWC tensor [B,oH,oW,Cs] (fp16 or fp32); out_map = (sy, oy, sx, ox)."""
+    a = _conv_args(x, w, cout, taps, grid_hw, out, split=split, **kw)
+    flops = 2.0 * x.shape[1] * grid_hw[0] * grid_hw[1] * cout * len(taps) * x.shape[4]
+    _launch(x.device, lambda: _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr()), 'p3d_conv_gemm', flops, split)
     return out
 
 
@@ -239,16 +250,32 @@ def tconv_phase_taps(py, px):
     return [(-(ky - py) // 2, -(kx - px) // 2, ky * 3 + kx) for ky in kys for kx in kxs]
 
 
+# A/B switch (results do not depend on it): P3D_CONV_MERGE_PHASES=0 launches the four phases of a transposed convolution one by one
+MERGE_PHASES = os.environ.get('P3D_CONV_MERGE_PHASES') != '0'
+
+
 def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SCALE):
-    """Stride-2 transposed 3x3 convolution as four phase GEMMs: x [xp,B,h,w,C] -> out [B,2h+1,2w+1,Cs] (pre-FIR)."""
+    """Stride-2 transposed 3x3 convolution as four phase GEMMs: x [xp,B,h,w,C] -> out [B,2h+1,2w+1,Cs] (pre-FIR). The phases
+    (4, 2, 2 and 1 taps: heaviest first) run as ONE launch whose tile schedule walks all four (p3d_conv_gemm_phases)."""
     _, b, h, wd, c = x.shape
-    for py in (0, 1):
-        for px in (0, 1):
-            gh = h + 1 if py == 0 else h
-            gw = wd + 1 if px == 0 else wd
-            conv_gemm(x, w, cout, tconv_phase_taps(py, px), (gh, gw), out, out_mode=2 if out.dtype == torch.float32 else 0,
-                      out_map=(2, py, 2, px), split=split, acc_scale=acc_scale)
+    mode = 2 if out.dtype == torch.float32 else 0
+    phases = [(py, px, (h + 1 if py == 0 else h, wd + 1 if px == 0 else wd)) for py in (0, 1) for px in (0, 1)]
+    if not MERGE_PHASES:
+        for py, px, ghw in phases:
+            conv_gemm(x, w, cout, tconv_phase_taps(py, px), ghw, out, out_mode=mode, out_map=(2, py, 2, px), split=split,
+                      acc_scale=acc_scale)
+        return out
+    arr = (ConvArgs * 4)()
+    flops = 0.0
+    for k, (py, px, ghw) in enumerate(phases):
+        taps = tconv_phase_taps(py, px)
+        arr[k] = _conv_args(x, w, cout, taps, ghw, out, out_mode=mode, out_map=(2, py, 2, px), split=split, acc_scale=acc_scale)
+        flops += 2.0 * b * ghw[0] * ghw[1] * cout * len(taps) * c
+    _launch(x.device, lambda: _lib.lib().p3d_conv_gemm_phases(arr, 4, _lib.stream_ptr()), 'p3d_conv_gemm_phases', flops, split)
     return out
+
+
+FIR_VARIANT = 1 if os.environ.get('P3D_FIR_VARIANT') == '1' else 0     # read once by the host binding (A/B runs only)
 
 
 def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):
@@ -265,7 +292,11 @@ def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.
     if noise is not None:
         assert noise.is_contiguous() and noise.dtype == torch.float32 and noise.shape[-2:] == (oh, ow)
     with torch.cuda.device(x.device):
-        if split_in:
+        if FIR_VARIANT == 1:        # A/B: the one-tile-per-CTA scalar kernel
+            st = _lib.lib().p3d_fir_act_nhwc_v1(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], int(split_in), _lib.ptr(f), _lib.ptr(noise),
+                                                _lib.ptr(bias), _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain,
+                                                act, alpha, act_gain, clamp, nbs, _lib.stream_ptr())
+        elif split_in:
             st = _lib.lib().p3d_fir_act_nhwc_split(_lib.ptr(x), _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b,
                                                    ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha, act_gain, clamp,
                                                    nbs, _lib.stream_ptr())

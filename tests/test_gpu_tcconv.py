@@ -338,3 +338,84 @@ def test_strided_conv_and_residual_epilogue():
     out = tcconv.fir_act_nhwc(sp, f, None, None, 2, (34, 34), pad0=(2, 2), fir_gain=1.0, act=1, act_gain=1.0)
     refd = upfirdn2d.upfirdn2d(xs, f, padding=[2, 2, 2, 2])
     assert rel_err((out[0].float() + out[1].float()).permute(0, 3, 1, 2).cpu().numpy(), refd.cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize('b,c,cout,hw,split', [
+    (2, 64, 48, (7, 5), False),          # grid kernel, no split-K (Cin 64: 4 k-steps in the heaviest phase)
+    (4, 512, 512, (4, 4), True),         # grid kernel + split-K partials per phase + one finisher for all phases
+    (4, 512, 512, (16, 16), True),       # the b32 up layer: grid kernel, split-K
+    (2, 128, 128, (72, 64), False),      # persistent kernel (one tile schedule over the four phases)
+    (1, 256, 256, (56, 72), True),       # CTA-pair kernel, three-pass split
+])
+def test_merged_transposed_conv_phases_equal_separate_launches(b, c, cout, hw, split, monkeypatch):
+    """p3d_conv_gemm_phases: one launch over the four phases == four p3d_conv_gemm launches, bit for bit, and both match the
+    float64 transposed convolution."""
+    from pix2pix3d_b200 import tcconv
+    torch.manual_seed(21)
+    h, w = hw
+    x = torch.randn(b, c, h, w, device='cuda')
+    wt = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    planes = 2 if split else 1
+    xn = tcconv.to_nhwc_f16(x, planes=planes)
+    wk = _weights_kmajor(wt, planes=planes, scale=tcconv.WEIGHT_SCALE)
+    dt = torch.float32 if split else torch.float16
+    outs = []
+    for merged in (True, False):
+        monkeypatch.setattr(tcconv, 'MERGE_PHASES', merged)
+        out = torch.full((b, 2 * h + 1, 2 * w + 1, cout), float('nan'), device='cuda', dtype=dt)
+        tcconv.conv_transpose3x3_s2(xn, wk, cout, out, split=split)
+        assert torch.isfinite(out).all(), 'every output pixel must be written by exactly one phase'
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    if split:
+        ref = F.conv_transpose2d(x.double().cpu(), wt.double().cpu().transpose(0, 1), stride=2)
+        tol = 2e-5
+    else:
+        ref = F.conv_transpose2d(_h(x).cpu(), (_h(wt * tcconv.WEIGHT_SCALE).cpu() / tcconv.WEIGHT_SCALE).transpose(0, 1), stride=2)
+        tol = 2e-3
+    assert rel_err(outs[0].float().permute(0, 3, 1, 2).cpu().numpy(), ref.numpy()) < tol
+
+
+def test_conv_gemm_phases_rejects_mismatched_phases():
+    import ctypes
+    from pix2pix3d_b200 import tcconv, _lib
+    x = tcconv.to_nhwc_f16(torch.randn(1, 64, 4, 4, device='cuda'))
+    wk = _weights_kmajor(torch.randn(16, 64, 3, 3, device='cuda'))
+    out = torch.zeros(1, 9, 9, 16, device='cuda', dtype=torch.float16)
+    other = torch.zeros(1, 9, 9, 16, device='cuda', dtype=torch.float16)
+    arr = (tcconv.ConvArgs * 2)()
+    arr[0] = tcconv._conv_args(x, wk, 16, tcconv.tconv_phase_taps(0, 0), (5, 5), out, out_map=(2, 0, 2, 0))
+    arr[1] = tcconv._conv_args(x, wk, 16, tcconv.tconv_phase_taps(0, 1), (5, 4), other, out_map=(2, 0, 2, 1))
+    assert _lib.lib().p3d_conv_gemm_phases(arr, 2, _lib.stream_ptr()) == -2
+    assert _lib.lib().p3d_conv_gemm_phases(arr, 5, _lib.stream_ptr()) == -2
+
+
+@pytest.mark.parametrize('dtype,planes,c,hw,noise_mode', [
+    (torch.float16, 1, 128, (96, 80), 'batch'),      # SR layers: fp16 in, fp16 out; more tiles than resident CTAs
+    (torch.float16, 1, 64, (24, 40), 'shared'),
+    (torch.float32, 2, 64, (70, 50), 'batch'),       # backbone layers: fp32 in, hi/lo out; ragged tile edges
+    (torch.float32, 2, 32, (8, 8), None),
+    ('split', 2, 64, (33, 47), None),                # hi/lo input (encoder path), two-slot ring
+])
+def test_fir_ring_kernel_is_bit_identical_to_the_one_tile_kernel(dtype, planes, c, hw, noise_mode, monkeypatch):
+    """The persistent fp32-pair FIR kernel performs the scalar kernel's operations in the same order."""
+    from pix2pix3d_b200 import tcconv
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    torch.manual_seed(5)
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    b = 3
+    oh, ow = hw
+    if dtype == 'split':
+        v = torch.randn(b, oh + 1, ow + 1, c, device='cuda')
+        hi = v.half()
+        x = torch.stack([hi, (v - hi.float()).half()]).contiguous()
+    else:
+        x = torch.randn(b, oh + 1, ow + 1, c, device='cuda').to(dtype)
+    noise = None if noise_mode is None else (torch.randn(oh, ow, device='cuda') if noise_mode == 'shared' else torch.randn(b, oh, ow, device='cuda'))
+    bias = torch.randn(c, device='cuda')
+    got = []
+    for variant in (0, 1):
+        monkeypatch.setattr(tcconv, 'FIR_VARIANT', variant)
+        got.append(tcconv.fir_act_nhwc(x, f, noise, bias, planes, (oh, ow), act_gain=float(np.sqrt(2)), clamp=256.0))
+    assert torch.equal(got[0], got[1])
+    assert torch.isfinite(got[0].float()).all()
