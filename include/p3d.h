@@ -173,6 +173,23 @@ int p3d_sample_from_planes(const float* planes_nhwc, const float* coords, int B,
 int p3d_sample_from_planes_bwd(const float* grad_features, const float* coords, int B, int64_t M, int H, int W,
                                float coord_scale, float* grad_planes_nhwc, p3d_stream_t stream);
 
+/* OSG decoder MLP of the gradient-requiring passes (training/triplane.py:112-135, triplane_cond.py:859-924): for every point
+ *   x = mean over the 3 planes of feats [N,3,M,32];  h = softplus(w1 x + b1);  o = w2 h + b2   (w1 [64,32], w2 [33,64], runtime
+ *   gains of FullyConnectedLayer already applied by the caller, networks_stylegan2.py:111-119; Softplus(beta 1, threshold 20))
+ *   out_sigma [N*M] = o[0];  out_rgb [N*M,32][k] = bit k of sigmoid_mask ? sigmoid(o[1+k]) * 1.002 - 0.001 : o[1+k].
+ * One launch instead of mean + addmm + softplus + addmm + slices + sigmoid + cat. */
+int p3d_decoder_mlp_fwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
+                        const float* b2, uint32_t sigmoid_mask, float* out_rgb, float* out_sigma, p3d_stream_t stream);
+
+/* First-order backward of p3d_decoder_mlp_fwd (what autograd derives from the module's forward): g_rgb [N*M,32] / g_sigma [N*M]
+ * (either may be NULL = zeros) -> g_feats [N,3,M,32] and g_params [4257] = dL/dw1 [64,32] | dL/db1 [64] | dL/dw2 [33,64] |
+ * dL/db2 [33]. The forward is recomputed per point; parameter gradients are accumulated per CTA and added in a fixed order
+ * (deterministic). workspace: fp32 scratch of at least p3d_decoder_mlp_bwd_workspace_floats() elements. */
+int p3d_decoder_mlp_bwd_workspace_floats(void);
+int p3d_decoder_mlp_bwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
+                        const float* b2, uint32_t sigmoid_mask, const float* g_rgb, const float* g_sigma, float* g_feats,
+                        float* g_params, float* workspace, int64_t workspace_floats, p3d_stream_t stream);
+
 /* MipRayMarcher2.run_forward on explicit tensors -- ray_marcher.py:25-57.
  * colors [N,S,Cc], densities [N,S], depths [N,S]; out_rgb [N,Cc], out_depth [N] (clamped),
  * out_weights [N,S-1]. N = B*R rays. */

@@ -377,3 +377,81 @@ def sample_importance(z_vals, weights, u, return_inds=False):
     _lib.check(st, 'p3d_sample_importance')
     _lib.bump()
     return (out, inds) if return_inds else out
+
+
+# ----------------------------------------------------------------------------------------------
+# OSG decoder MLP of the gradient-requiring passes (p3d_decoder_mlp_fwd / _bwd)
+# ----------------------------------------------------------------------------------------------
+DECODER_PARAM_FLOATS = 64 * 32 + 64 + 33 * 64 + 33
+
+
+class _DecoderMLP(torch.autograd.Function):
+    """feats [N,3,M,32] -> (rgb [N,M,32], sigma [N,M,1]) through mean(1) -> FC(32,64) -> softplus -> FC(64,33) [-> sigmoid], forward
+    and first-order backward on libp3d. w1 / b1 / w2 / b2 are the EFFECTIVE parameters (runtime gains applied by the caller under
+    autograd), so their gradients flow on to the module's parameters through ordinary torch ops."""
+
+    @staticmethod
+    def forward(ctx, feats, w1, b1, w2, b2, mask):
+        f, w1c, b1c, w2c, b2c = (_f32c(t.detach()) for t in (feats, w1, b1, w2, b2))
+        n, _, m, _ = f.shape
+        rgb = torch.empty(n, m, 32, device=f.device, dtype=torch.float32)
+        sigma = torch.empty(n, m, 1, device=f.device, dtype=torch.float32)
+        with torch.cuda.device(f.device):
+            st = _lib.lib().p3d_decoder_mlp_fwd(_lib.ptr(f), n, m, _lib.ptr(w1c), _lib.ptr(b1c), _lib.ptr(w2c), _lib.ptr(b2c), int(mask),
+                                                _lib.ptr(rgb), _lib.ptr(sigma), _lib.stream_ptr())
+        _lib.check(st, 'p3d_decoder_mlp_fwd')
+        _lib.bump()
+        ctx.save_for_backward(f, w1c, b1c, w2c, b2c)
+        ctx.mask = int(mask)
+        return rgb, sigma
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rgb, g_sigma):
+        f, w1, b1, w2, b2 = ctx.saved_tensors
+        n, _, m, _ = f.shape
+        gr = None if g_rgb is None else _f32c(g_rgb)
+        gs = None if g_sigma is None else _f32c(g_sigma)
+        g_feats = torch.empty_like(f)
+        g_params = torch.empty(DECODER_PARAM_FLOATS, device=f.device, dtype=torch.float32)
+        with torch.cuda.device(f.device):
+            nws = _lib.lib().p3d_decoder_mlp_bwd_workspace_floats()
+            ws = torch.empty(nws, device=f.device, dtype=torch.float32)
+            st = _lib.lib().p3d_decoder_mlp_bwd(_lib.ptr(f), n, m, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), ctx.mask,
+                                                _lib.ptr(gr), _lib.ptr(gs), _lib.ptr(g_feats), _lib.ptr(g_params), _lib.ptr(ws), nws,
+                                                _lib.stream_ptr())
+        _lib.check(st, 'p3d_decoder_mlp_bwd')
+        _lib.bump(2)
+        gw1, gb1, gw2, gb2 = torch.split(g_params, [64 * 32, 64, 33 * 64, 33])
+        return g_feats, gw1.view(64, 32), gb1, gw2.view(33, 64), gb2, None
+
+
+def _effective_fc(fc):
+    """weight * weight_gain, bias * bias_gain as FullyConnectedLayer.forward forms them (networks_stylegan2.py:111-119)."""
+    w = fc.weight.to(torch.float32) * fc.weight_gain
+    b = fc.bias.to(torch.float32)
+    if fc.bias_gain != 1:
+        b = b * fc.bias_gain
+    return w, b
+
+
+def decoder_mlp_supported(decoder, sampled_features):
+    """True when `decoder(sampled_features, ...)` can run on p3d_decoder_mlp_*: a CUDA fp32 [N,3,M,32] feature tensor and one of the
+    OSG decoder layouts the kernels implement."""
+    f = sampled_features
+    return (f.is_cuda and f.dtype == torch.float32 and f.ndim == 4 and f.shape[1] == 3 and f.shape[3] == 32 and f.numel() > 0
+            and describe_decoder(decoder) is not None)
+
+
+def decoder_mlp(decoder, sampled_features):
+    """The OSG decoder modules' forward ({'rgb', 'sigma'}) on the fused kernels, differentiable to first order w.r.t. the features
+    and the decoder parameters (training/triplane.py:122-135, triplane_cond.py:869-970)."""
+    nets, sigma_net, masks = describe_decoder(decoder)
+    outs = []
+    for net, mask in zip(nets, masks):
+        w1, b1 = _effective_fc(net[0])
+        w2, b2 = _effective_fc(net[2])
+        outs.append(_DecoderMLP.apply(sampled_features, w1, b1, w2, b2, mask))
+    sigma = outs[sigma_net][1]
+    rgb = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs], dim=-1)
+    return {'rgb': rgb, 'sigma': sigma}

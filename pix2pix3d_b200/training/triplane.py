@@ -5,7 +5,7 @@ decodes with; `TriPlaneGenerator` (:19-108) is the unconditional variant (mappin
 """
 import torch
 
-from .. import dnnlib
+from .. import dnnlib, native
 from ..torch_utils import persistence
 from .networks_stylegan2 import FullyConnectedLayer
 from .networks_stylegan2 import Generator as StyleGAN2Backbone
@@ -33,6 +33,8 @@ class OSGDecoder(torch.nn.Module):
         self.net = _decoder_mlp(n_features, self.hidden_dim, 1 + options['decoder_output_dim'], options['decoder_lr_mul'])
 
     def forward(self, sampled_features, ray_directions):
+        if native.decoder_mlp_supported(self, sampled_features):      # CUDA: fused forward / backward kernels
+            return native.decoder_mlp(self, sampled_features)
         x = sampled_features.mean(1)
         n, m, c = x.shape
         x = self.net(x.view(n * m, c)).view(n, m, -1)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .. import dnnlib
+from .. import dnnlib, native
 from ..torch_utils import misc
 from ..torch_utils import persistence
 from .networks_stylegan2 import DiscriminatorBlock, FullyConnectedLayer, SynthesisNetwork, normalize_2nd_moment
@@ -292,6 +292,8 @@ class OSGDecoder_semantic(torch.nn.Module):
         self.final_sigmoid = options['sigmoid']
 
     def forward(self, sampled_features, ray_directions):
+        if native.decoder_mlp_supported(self, sampled_features):      # CUDA: fused forward / backward kernels
+            return native.decoder_mlp(self, sampled_features)
         x = sampled_features.mean(1)
         n, m, c = x.shape
         x = self.net(x.view(n * m, c)).view(n, m, -1)
@@ -310,6 +312,8 @@ class OSGDecoder_semantic_entangle(torch.nn.Module):
         self.semantic_channels = options['semantic_channels']
 
     def forward(self, sampled_features, ray_directions):
+        if native.decoder_mlp_supported(self, sampled_features):      # CUDA: fused forward / backward kernels
+            return native.decoder_mlp(self, sampled_features)
         x = sampled_features.mean(1)
         n, m, c = x.shape
         x = self.net(x.view(n * m, c)).view(n, m, -1)
@@ -332,6 +336,8 @@ class OSGDecoder_semantic_lateSeparate(torch.nn.Module):
         self.semantic_sigmoid = options['sigmoid']
 
     def forward(self, sampled_features, ray_directions):
+        if native.decoder_mlp_supported(self, sampled_features):      # CUDA: fused forward / backward kernels
+            return native.decoder_mlp(self, sampled_features)
         x = sampled_features.mean(1)
         n, m, c = x.shape
         x = x.view(n * m, c)
