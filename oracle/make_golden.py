@@ -253,10 +253,30 @@ SEMGEN_CASES = {
 }
 
 
+# Generator / super-resolution classes no BASELINE configuration instantiates but the reference ships and train.py can select
+# (train.py:389-397, triplane_cond.py:1085-1246): reference outputs only (no oracle restatement); the host-side mirror is
+# checked against them on CPU and on CUDA (tests/test_extra_fixtures.py). `sub` = stored stride of the full-resolution outputs.
+EXTRA_CASES = {
+    'withbg_tiny': dict(seed=41, cls='TriPlaneSemanticEntangleGenerator_withBG', img_resolution=128, semantic_channels=6, nrr=16, Sc=12,
+                        Sf=12, B=2, channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32, sub=1),
+    'withbg_edge': dict(seed=42, cls='TriPlaneSemanticEntangleGenerator_withBG', img_resolution=128, semantic_channels=1, nrr=16, Sc=8,
+                        Sf=8, B=1, channel_base=1024, channel_max=16, ray=(0.1, 2.6, 1.6), mapping='edge', in_res=32, sub=1),
+    'sr8x_rgb': dict(seed=43, cls='TriPlaneGenerator', img_resolution=512, semantic_channels=0, nrr=32, Sc=10, Sf=6, B=1,
+                     channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32, sub=4,
+                     sr_module='training.superresolution.SuperresolutionHybrid8X'),
+    'sr4x_rgb': dict(seed=44, cls='TriPlaneGenerator', img_resolution=256, semantic_channels=0, nrr=32, Sc=10, Sf=6, B=1,
+                     channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32, sub=2,
+                     sr_module='training.superresolution.SuperresolutionHybrid4X'),
+    'sr4x_native': dict(seed=45, cls='TriPlaneGenerator', img_resolution=256, semantic_channels=0, nrr=128, Sc=4, Sf=4, B=1,
+                        channel_base=1024, channel_max=16, ray=(2.25, 3.3, 1), mapping='mask', in_res=32, sub=2,
+                        sr_module='training.superresolution.SuperresolutionHybrid4X'),
+}
+
+
 def synth_kwargs(case):
     sem = case['semantic_channels']
     rk = dict(image_resolution=case['img_resolution'], disparity_space_sampling=False, clamp_mode='softplus',
-              superresolution_module='training.superresolution.SuperresolutionHybrid2X',
+              superresolution_module=case.get('sr_module', 'training.superresolution.SuperresolutionHybrid2X'),
               superresolution_module_semantic='training.superresolution.SuperresolutionHybrid2X_semantic',
               c_gen_conditioning_zero=False, gpc_reg_prob=0.5, c_scale=1.0, superresolution_noise_mode='none',
               density_reg=0.25, density_reg_p_dist=0.004, reg_type='l1', decoder_lr_mul=1.0, sr_antialias=True,
@@ -331,6 +351,30 @@ def golden_synthesis():
         arrays['state_digest'] = np.frombuffer(state_digest(G).encode(), dtype=np.uint8)
         np.savez_compressed(os.path.join(OUT, f'synthesis_{name}.npz'), **arrays)
         print('synthesis', name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+def golden_extra():
+    import training.triplane_cond as ref_tc
+    only = set(sys.argv[2:]) if len(sys.argv) > 2 else None
+    for name, case in EXTRA_CASES.items():
+        if only is not None and name not in only:
+            continue
+        G = build_generator(ref_tc, case)
+        z, c, mask = synth_inputs(case)
+        draws = []
+        with torch.no_grad():
+            ws = G.mapping(z, c, {'mask': mask, 'pose': c})
+            with capture_rand(draws):
+                out = G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=case['nrr'])
+        sub = case['sub']
+        save = dict(z=z, c=c, mask=mask, ws=ws, jitter=draws[0][1], u=draws[1][1])
+        for k, v in out.items():
+            full = v.shape[-1] == case['img_resolution']
+            save['out_' + k] = v[..., ::sub, ::sub].contiguous() if (full and sub > 1) else v
+        arrays = {k: v.detach().numpy() for k, v in save.items()}
+        arrays['state_digest'] = np.frombuffer(state_digest(G).encode(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(OUT, f'extra_{name}.npz'), **arrays)
+        print('extra', name, {k: tuple(v.shape) for k, v in out.items()})
 
 
 def golden_semgen():
@@ -504,3 +548,5 @@ if __name__ == '__main__':
         golden_loss_ops()
     if 'fullsize' in which:
         golden_fullsize()
+    if 'extra' in which:
+        golden_extra()

@@ -1,0 +1,65 @@
+"""Generator / super-resolution classes outside the BASELINE configurations -- TriPlaneSemanticEntangleGenerator_withBG (spherical
+background plane, two-net lateSeparate decoder: triplane_cond.py:1085-1246), SuperresolutionHybrid8X and SuperresolutionHybrid4X
+(superresolution.py:29-89; the 4X stack's SynthesisBlockNoUp with and without the input resize) -- against outputs of the
+reference itself (oracle/make_golden.py extra -> tests/golden/extra_*.npz), on CPU tensors and on CUDA."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from make_golden import EXTRA_CASES, build_generator, state_digest
+
+
+def _replay(g, dev):
+    it = iter([torch.from_numpy(g['jitter']).to(dev), torch.from_numpy(g['u']).to(dev)])
+    return (lambda x, *a, **k: next(it)), (lambda *a, **k: next(it))
+
+
+def _run(name, dev, force_fp32):
+    import pix2pix3d_b200.training.triplane_cond as tc
+    case = EXTRA_CASES[name]
+    g = load_golden('extra_' + name)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    G = build_generator(tc, case)
+    assert state_digest(G) == bytes(g['state_digest']).decode(), 'mirror parameters differ from the reference (construction order)'
+    G = G.to(dev)
+    ws, c = torch.from_numpy(g['ws']).to(dev), torch.from_numpy(g['c']).to(dev)
+    rl, rr = _replay(g, dev)
+    o_like, o_rand = torch.rand_like, torch.rand
+    torch.rand_like, torch.rand = rl, rr
+    try:
+        with torch.no_grad():
+            out = G.synthesis(ws, c, noise_mode='const', neural_rendering_resolution=case['nrr'], force_fp32=force_fp32)
+    finally:
+        torch.rand_like, torch.rand = o_like, o_rand
+    sub = case['sub']
+    res = {}
+    for k, v in out.items():
+        v = v.float().cpu().numpy()
+        if v.shape[-1] == case['img_resolution'] and sub > 1:
+            v = v[..., ::sub, ::sub]
+        res[k] = v
+    assert set(res) == {k[4:] for k in g if k.startswith('out_')}
+    return res, g
+
+
+@pytest.mark.parametrize('name', list(EXTRA_CASES))
+def test_extra_generators_cpu_match_reference(name):
+    res, g = _run(name, torch.device('cpu'), True)
+    for k, v in res.items():
+        assert rel_err(v, g['out_' + k]) < 1e-4, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', list(EXTRA_CASES))
+@pytest.mark.parametrize('force_fp32', [True, False])
+def test_extra_generators_cuda_match_reference(name, force_fp32):
+    from pix2pix3d_b200 import _lib
+    before = _lib.launch_count
+    res, g = _run(name, torch.device('cuda'), force_fp32)
+    assert _lib.launch_count > before, 'native kernels were not used'
+    for k, v in res.items():
+        full = k in ('image', 'semantic')
+        tol = 2e-2 if (full and not force_fp32) else 1e-3        # the SR stacks run fp16 unless force_fp32, as the reference on CUDA
+        assert rel_err(v, g['out_' + k]) < tol, (k, force_fp32)
