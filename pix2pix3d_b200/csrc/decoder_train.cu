@@ -124,14 +124,19 @@ __global__ void __launch_bounds__(128) decoder_mlp_fwd_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: tiles of 128 points per CTA (thread = point), then the CTA turns the tile's rows of (h, dL/da1, dL/do, x) kept in
-// shared memory into parameter-gradient contributions (thread = a row of dW2 / dW1, looping over the tile's points); partial
-// sums stay in registers across the CTA's tiles and are written once per CTA; a second kernel adds the CTAs in a fixed order.
+// backward: tiles of 64 points per CTA of 128 threads. Phase A: a lane PAIR owns a point and splits the 64 hidden units (the
+// two partial output rows / input gradients are exchanged with shuffles), recomputes the forward and forms dL/do, dL/da1, dL/dx.
+// Phase B: the CTA turns the tile's rows of (h, dL/da1, dL/do, x) kept in shared memory into parameter-gradient contributions
+// (thread = half a row of dW2 and dW1, looping over the tile's points); partial sums stay in registers across the CTA's tiles
+// and are written once per CTA; a second kernel adds the CTAs in a fixed order. 70 KB of shared memory per CTA -> 3 CTAs
+// (12 warps) per SM: the per-point chains of dependent FMAs need the other warps to hide their latency.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBwdTile = 128;
-constexpr int kHS = kDecHid + 1;                  // row stride of the h / da1 tiles ([point][unit], +1: conflict-free both ways)
+constexpr int kBwdTile = 64;
+constexpr int kHS = kDecHid + 2;                  // row stride of the h / da1 tiles: unit j lives in column j + (j >= 32), which keeps
+                                                  // the lane pairs' stores and phase B's loads free of bank conflicts
 constexpr int kGS = 36;                           // row stride of the dL/do tile ([point][k])
 constexpr int kXS = 36;                           // row stride of the x tile ([point][i])
+constexpr int kBwdCtasPerSm = 3;
 
 struct DecSmemBwd {
     DecSmemW w;
@@ -141,7 +146,7 @@ struct DecSmemBwd {
     float x[kBwdTile * kXS];
 };
 
-__global__ void __launch_bounds__(128) decoder_mlp_bwd_kernel(const float* __restrict__ feats, int64_t N, int64_t M,
+__global__ void __launch_bounds__(128, kBwdCtasPerSm) decoder_mlp_bwd_kernel(const float* __restrict__ feats, int64_t N, int64_t M,
                                                                const float* __restrict__ w1, const float* __restrict__ b1,
                                                                const float* __restrict__ w2, const float* __restrict__ b2, uint32_t mask,
                                                                const float* __restrict__ g_rgb, const float* __restrict__ g_sigma,
@@ -150,8 +155,10 @@ __global__ void __launch_bounds__(128) decoder_mlp_bwd_kernel(const float* __res
     DecSmemBwd& s = *reinterpret_cast<DecSmemBwd*>(smem_raw);
     dec_load_weights(s.w, w1, b1, w2, b2);
     const int t = threadIdx.x;
-    // parameter-gradient ownership: j = hidden unit, half = which half of the row
-    const int j = t & 63, half = t >> 6;
+    // phase A: point of the tile and half of the hidden units
+    const int pl = t >> 1, q = t & 1, j0 = 32 * q;
+    // phase B: parameter-gradient ownership, j = hidden unit, half = which half of the row
+    const int j = t & 63, half = t >> 6, jc = j + (j >> 5);
     float acc_w2[17], acc_w1[16], acc_b = 0.f;     // dW2[k][j] for k in [16*half, 16*half+16 (+1)), dW1[j][16*half ..), db1[j] / db2[k]
 #pragma unroll
     for (int k = 0; k < 17; ++k) acc_w2[k] = 0.f;
@@ -161,10 +168,10 @@ __global__ void __launch_bounds__(128) decoder_mlp_bwd_kernel(const float* __res
     const int64_t n_tiles = (P + kBwdTile - 1) / kBwdTile;
     __syncthreads();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t pt = tile * kBwdTile + t;
+        const int64_t pt = tile * kBwdTile + pl;
         const bool valid = pt < P;
         const int64_t n = valid ? pt / M : 0, m = valid ? pt % M : 0;
-        // ---- per point: recompute the forward, then dL/do, dL/da1, dL/dx ----
+        // ---- phase A: recompute the forward, then dL/do, dL/da1, dL/dx ----
         float x[kDecIn];
         if (valid) dec_load_mean(feats, n, m, M, x);
         else {
@@ -172,29 +179,36 @@ __global__ void __launch_bounds__(128) decoder_mlp_bwd_kernel(const float* __res
             for (int i = 0; i < kDecIn; ++i) x[i] = 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < kDecIn / 4; ++q)
-            *reinterpret_cast<float4*>(s.x + t * kXS + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        for (int u = 0; u < 4; ++u) {               // each lane of the pair stores half of the row
+            const int c = 16 * q + 4 * u;
+            float4 v;
+            v.x = q ? x[16 + 4 * u] : x[4 * u]; v.y = q ? x[17 + 4 * u] : x[4 * u + 1];
+            v.z = q ? x[18 + 4 * u] : x[4 * u + 2]; v.w = q ? x[19 + 4 * u] : x[4 * u + 3];
+            *reinterpret_cast<float4*>(s.x + pl * kXS + c) = v;
+        }
         float o[kDecOut];
 #pragma unroll
-        for (int k = 0; k < kDecOut; ++k) o[k] = s.w.b2[k];
+        for (int k = 0; k < kDecOut; ++k) o[k] = q ? 0.f : s.w.b2[k];
 #pragma unroll 4
-        for (int jj = 0; jj < kDecHid; ++jj) {
+        for (int jj = 0; jj < 32; ++jj) {
             float dsp;
-            const float h = dec_softplus(dec_hidden_pre(s.w, jj, x), dsp);
-            s.h[t * kHS + jj] = h;
-            s.ga[t * kHS + jj] = dsp;
-            dec_out_accum(s.w, jj, h, o);
+            const float h = dec_softplus(dec_hidden_pre(s.w, j0 + jj, x), dsp);
+            s.h[pl * kHS + j0 + q + jj] = h;
+            s.ga[pl * kHS + j0 + q + jj] = dsp;
+            dec_out_accum(s.w, j0 + jj, h, o);
         }
-        // dL/do (reuses o)
+#pragma unroll
+        for (int k = 0; k < kDecOut; ++k) o[k] += __shfl_xor_sync(0xffffffffu, o[k], 1);
+        // dL/do (reuses o; both lanes of the pair hold it)
         o[0] = (valid && g_sigma) ? __ldg(g_sigma + pt) : 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int qq = 0; qq < 8; ++qq) {
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && g_rgb) g = __ldg(reinterpret_cast<const float4*>(g_rgb + pt * 32) + q);
+            if (valid && g_rgb) g = __ldg(reinterpret_cast<const float4*>(g_rgb + pt * 32) + qq);
             const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int k = 4 * q + u;
+                const int k = 4 * qq + u;
                 float d = gv[u];
                 if ((mask >> k) & 1u) {
                     const float sg = 1.f / (1.f + expf(-o[1 + k]));
@@ -203,56 +217,63 @@ __global__ void __launch_bounds__(128) decoder_mlp_bwd_kernel(const float* __res
                 o[1 + k] = d;
             }
         }
+        if (q == 0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(s.go + t * kGS + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        s.go[t * kGS + 32] = o[32];
+            for (int qq = 0; qq < 8; ++qq)
+                *reinterpret_cast<float4*>(s.go + pl * kGS + 4 * qq) = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+            s.go[pl * kGS + 32] = o[32];
+        }
         float gx[kDecIn];
 #pragma unroll
         for (int i = 0; i < kDecIn; ++i) gx[i] = 0.f;
 #pragma unroll 4
-        for (int jj = 0; jj < kDecHid; ++jj) {
-            const float4* w = reinterpret_cast<const float4*>(s.w.w2t + jj * kW2Stride);
-            float gh = 0.f;
+        for (int jj = 0; jj < 32; ++jj) {
+            const float4* w = reinterpret_cast<const float4*>(s.w.w2t + (j0 + jj) * kW2Stride);
+            float gh0 = 0.f, gh1 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 ww = w[q];
-                gh = fmaf(ww.x, o[4 * q], gh); gh = fmaf(ww.y, o[4 * q + 1], gh); gh = fmaf(ww.z, o[4 * q + 2], gh); gh = fmaf(ww.w, o[4 * q + 3], gh);
+            for (int qq = 0; qq < 8; qq += 2) {
+                const float4 wa = w[qq], wb = w[qq + 1];
+                gh0 = fmaf(wa.x, o[4 * qq], gh0); gh0 = fmaf(wa.y, o[4 * qq + 1], gh0); gh0 = fmaf(wa.z, o[4 * qq + 2], gh0); gh0 = fmaf(wa.w, o[4 * qq + 3], gh0);
+                gh1 = fmaf(wb.x, o[4 * qq + 4], gh1); gh1 = fmaf(wb.y, o[4 * qq + 5], gh1); gh1 = fmaf(wb.z, o[4 * qq + 6], gh1); gh1 = fmaf(wb.w, o[4 * qq + 7], gh1);
             }
-            gh = fmaf(s.w.w2t[jj * kW2Stride + 32], o[32], gh);
-            const float ga = gh * s.ga[t * kHS + jj];
-            s.ga[t * kHS + jj] = ga;
-            const float4* w1r = reinterpret_cast<const float4*>(s.w.w1 + jj * kDecIn);
+            const float gh = fmaf(s.w.w2t[(j0 + jj) * kW2Stride + 32], o[32], gh0 + gh1);
+            const float ga = gh * s.ga[pl * kHS + j0 + q + jj];
+            s.ga[pl * kHS + j0 + q + jj] = ga;
+            const float4* w1r = reinterpret_cast<const float4*>(s.w.w1 + (j0 + jj) * kDecIn);
 #pragma unroll
-            for (int q = 0; q < kDecIn / 4; ++q) {
-                const float4 ww = w1r[q];
-                gx[4 * q] = fmaf(ww.x, ga, gx[4 * q]); gx[4 * q + 1] = fmaf(ww.y, ga, gx[4 * q + 1]);
-                gx[4 * q + 2] = fmaf(ww.z, ga, gx[4 * q + 2]); gx[4 * q + 3] = fmaf(ww.w, ga, gx[4 * q + 3]);
+            for (int qq = 0; qq < kDecIn / 4; ++qq) {
+                const float4 ww = w1r[qq];
+                gx[4 * qq] = fmaf(ww.x, ga, gx[4 * qq]); gx[4 * qq + 1] = fmaf(ww.y, ga, gx[4 * qq + 1]);
+                gx[4 * qq + 2] = fmaf(ww.z, ga, gx[4 * qq + 2]); gx[4 * qq + 3] = fmaf(ww.w, ga, gx[4 * qq + 3]);
             }
         }
+#pragma unroll
+        for (int i = 0; i < kDecIn; ++i) gx[i] = (gx[i] + __shfl_xor_sync(0xffffffffu, gx[i], 1)) * (1.f / 3.f);
         if (valid) {
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-                float4* dst = reinterpret_cast<float4*>(g_feats + ((n * 3 + p) * M + m) * kDecIn);
+            for (int p = 0; p < 3; ++p) {           // each lane of the pair writes half of the channels of every plane
+                float4* dst = reinterpret_cast<float4*>(g_feats + ((n * 3 + p) * M + m) * kDecIn + 16 * q);
 #pragma unroll
-                for (int q = 0; q < kDecIn / 4; ++q)
-                    dst[q] = make_float4(gx[4 * q] * (1.f / 3.f), gx[4 * q + 1] * (1.f / 3.f), gx[4 * q + 2] * (1.f / 3.f), gx[4 * q + 3] * (1.f / 3.f));
+                for (int u = 0; u < 4; ++u)
+                    dst[u] = q ? make_float4(gx[16 + 4 * u], gx[17 + 4 * u], gx[18 + 4 * u], gx[19 + 4 * u])
+                               : make_float4(gx[4 * u], gx[4 * u + 1], gx[4 * u + 2], gx[4 * u + 3]);
             }
         }
         __syncthreads();
-        // ---- parameter gradients of the tile: thread (j, half) walks the tile's points ----
+        // ---- phase B: parameter gradients of the tile, thread (j, half) walks the tile's points ----
+#pragma unroll 2
         for (int p = 0; p < kBwdTile; ++p) {
-            const float hv = s.h[p * kHS + j], gav = s.ga[p * kHS + j];
+            const float hv = s.h[p * kHS + jc], gav = s.ga[p * kHS + jc];
             const float4* gop = reinterpret_cast<const float4*>(s.go + p * kGS + 16 * half);
             const float4* xp = reinterpret_cast<const float4*>(s.x + p * kXS + 16 * half);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 g = gop[q];
-                acc_w2[4 * q] = fmaf(g.x, hv, acc_w2[4 * q]); acc_w2[4 * q + 1] = fmaf(g.y, hv, acc_w2[4 * q + 1]);
-                acc_w2[4 * q + 2] = fmaf(g.z, hv, acc_w2[4 * q + 2]); acc_w2[4 * q + 3] = fmaf(g.w, hv, acc_w2[4 * q + 3]);
-                const float4 xv = xp[q];
-                acc_w1[4 * q] = fmaf(gav, xv.x, acc_w1[4 * q]); acc_w1[4 * q + 1] = fmaf(gav, xv.y, acc_w1[4 * q + 1]);
-                acc_w1[4 * q + 2] = fmaf(gav, xv.z, acc_w1[4 * q + 2]); acc_w1[4 * q + 3] = fmaf(gav, xv.w, acc_w1[4 * q + 3]);
+            for (int qq = 0; qq < 4; ++qq) {
+                const float4 g = gop[qq];
+                acc_w2[4 * qq] = fmaf(g.x, hv, acc_w2[4 * qq]); acc_w2[4 * qq + 1] = fmaf(g.y, hv, acc_w2[4 * qq + 1]);
+                acc_w2[4 * qq + 2] = fmaf(g.z, hv, acc_w2[4 * qq + 2]); acc_w2[4 * qq + 3] = fmaf(g.w, hv, acc_w2[4 * qq + 3]);
+                const float4 xv = xp[qq];
+                acc_w1[4 * qq] = fmaf(gav, xv.x, acc_w1[4 * qq]); acc_w1[4 * qq + 1] = fmaf(gav, xv.y, acc_w1[4 * qq + 1]);
+                acc_w1[4 * qq + 2] = fmaf(gav, xv.z, acc_w1[4 * qq + 2]); acc_w1[4 * qq + 3] = fmaf(gav, xv.w, acc_w1[4 * qq + 3]);
             }
             if (half) acc_w2[16] = fmaf(s.go[p * kGS + 32], hv, acc_w2[16]);
             // biases: threads 0..63 own db1[j]; threads 64..96 own db2[t - 64]
@@ -298,7 +319,7 @@ extern "C" int p3d_decoder_mlp_fwd(const float* feats, int64_t N, int64_t M, con
     return P3D_OK;
 }
 
-extern "C" int p3d_decoder_mlp_bwd_workspace_floats(void) { return sm_count() * kDecParams; }
+extern "C" int p3d_decoder_mlp_bwd_workspace_floats(void) { return sm_count() * kBwdCtasPerSm * kDecParams; }
 
 extern "C" int p3d_decoder_mlp_bwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
                                    const float* b2, uint32_t sigmoid_mask, const float* g_rgb, const float* g_sigma, float* g_feats,
@@ -306,7 +327,7 @@ extern "C" int p3d_decoder_mlp_bwd(const float* feats, int64_t N, int64_t M, con
     if (!feats || !w1 || !b1 || !w2 || !b2 || !g_feats || !g_params || !workspace || N <= 0 || M <= 0) return P3D_BAD_ARG;
     if (((((uintptr_t)feats) | ((uintptr_t)g_feats) | ((uintptr_t)g_rgb)) & 15) != 0) return P3D_BAD_ARG;
     const int64_t P = N * M, n_tiles = (P + kBwdTile - 1) / kBwdTile;
-    int64_t ctas = sm_count();
+    int64_t ctas = (int64_t)sm_count() * kBwdCtasPerSm;
     if (ctas > n_tiles) ctas = n_tiles;
     if (workspace_floats < ctas * kDecParams) return P3D_BAD_ARG;
     const size_t smem = sizeof(DecSmemBwd);

@@ -366,8 +366,10 @@ def test_merged_transposed_conv_phases_equal_separate_launches(b, c, cout, hw, s
         tcconv.conv_transpose3x3_s2(xn, wk, cout, out, split=split)
         assert torch.isfinite(out).all(), 'every output pixel must be written by exactly one phase'
         outs.append(out)
-    if split and c >= 512:       # split-K: the merged launch splits every phase the same number of ways, the separate launches each
-        assert torch.allclose(outs[0], outs[1], rtol=0, atol=2e-6 * float(outs[1].abs().max()))     # their own -> other summation grouping
+    if split:
+        # fp32 accumulators: the merged launch may pick another kernel shape (CTA pairs: M = 256 MMAs) or another split-K factor than
+        # the separate launches do -> another summation grouping, equal to rounding
+        assert torch.allclose(outs[0], outs[1], rtol=0, atol=2e-6 * float(outs[1].abs().max()))
     else:
         assert torch.equal(outs[0], outs[1])
     if split:
