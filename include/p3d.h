@@ -365,6 +365,13 @@ int p3d_modulate_weights_batch(const p3d_modw_desc_t* descs_dev, const int32_t* 
 int p3d_affine_batch(const float* ws, const float* weight, const float* bias, const int32_t* meta, float* out,
                      int B, int num_ws, int w_dim, int rows, p3d_stream_t stream);
 
+/* FullyConnectedLayer.forward (networks_stylegan2.py:111-123) for small batches (mapping networks):
+ *   y[b, o] = act( dot(x[b, :], weight[o, :] * weight_gain) + bias[o] * bias_gain ) * act_gain
+ * x [B, in] fp32, weight [out, in], bias [out] or NULL, y [B, out]; act: 1 linear, 2 relu, 3 lrelu(alpha) (codes of p3d_bias_act).
+ * One launch instead of the weight scaling + addmm / matmul + bias_act; P3D_UNSUPPORTED for other activations. */
+int p3d_fc_bias_act(const float* x, const float* weight, const float* bias, float* y, int B, int in_features, int out_features,
+                    float weight_gain, float bias_gain, int act, float alpha, float act_gain, p3d_stream_t stream);
+
 /* Layout / precision converters between the reference's NCHW tensors and the NHWC fp16 tensors of this path. */
 int p3d_nchw_to_nhwc_f16(const void* x, int src_dtype, int N, int C, int H, int W, int C_padded, int planes,
                          void* out, p3d_stream_t stream);
@@ -407,6 +414,13 @@ int p3d_filtered_lrelu(const p3d_filtered_lrelu_args_t* args, p3d_stream_t strea
 int p3d_filtered_lrelu_act(void* x, unsigned char* s, int dtype, const int32_t x_shape[4], const int64_t x_stride[4],
                            const int32_t s_shape[2], const int32_t s_ofs[2], float gain, float slope, float clamp,
                            int sign_mode, p3d_stream_t stream);
+
+/* Broadcasting fused multiply-add y = a * b + c -- `fma(a, b, c)` of the reference (torch_utils/ops/fma.py:17-34, forward =
+ * torch.addcmul(c, a, b)): the demodulation + noise step of the non-fused modulated convolution (networks_stylegan2.py:79-82).
+ * y: dense [shape[0..3]] (row-major); a / b / c: element strides over the same four dimensions, 0 on broadcast dimensions.
+ * dtype: P3D_F16 (fp32 arithmetic, one rounding) / P3D_F32 / P3D_F64. */
+int p3d_fma(const void* a, const void* b, const void* c, void* y, int dtype, const int64_t shape[4], const int64_t a_stride[4],
+            const int64_t b_stride[4], const int64_t c_stride[4], p3d_stream_t stream);
 
 /* 4x4 FIR (upfirdn2d up=down=1) + noise + bias + lrelu + gain + clamp on NHWC tensors: the tail of an up=2
  * SynthesisLayer (networks_stylegan2.py:324-331 after conv2d_resample.py:128). in_dtype: P3D_F32 or P3D_F16;

@@ -478,6 +478,53 @@ __global__ void __launch_bounds__(256) affine_batch_kernel(const float* __restri
     }
 }
 
+// FullyConnectedLayer.forward (networks_stylegan2.py:111-123) for small batches (the mapping networks, B <= 64): one warp per
+// output feature streams its weight row once (x stays in L1) and finishes with bias + activation, i.e. addmm / matmul + bias_act
+// in one launch. Weight-bandwidth bound: out * in * 4 bytes per call.
+template <int kRows>
+__global__ void __launch_bounds__(256) fc_bias_act_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          float* __restrict__ y, int B, int in_f, int out_f, float w_gain, float b_gain,
+                                                          int act, float alpha, float act_gain) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= out_f) return;
+    const float* wr = w + (size_t)o * in_f;
+    const float bv = bias ? __ldg(bias + o) * b_gain : 0.f;
+    for (int b0 = 0; b0 < B; b0 += kRows) {
+        float acc[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r] = 0.f;
+        if ((in_f & 3) == 0) {
+            for (int k = lane * 4; k < in_f; k += 128) {
+                float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+                wv.x *= w_gain; wv.y *= w_gain; wv.z *= w_gain; wv.w *= w_gain;
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+                    if (b0 + r < B) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)(b0 + r) * in_f + k));
+                        acc[r] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[r]))));
+                    }
+            }
+        } else {
+            for (int k = lane; k < in_f; k += 32) {
+                const float wv = __ldg(wr + k) * w_gain;
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+                    if (b0 + r < B) acc[r] = fmaf(__ldg(x + (size_t)(b0 + r) * in_f + k), wv, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const float v = warp_sum(acc[r]);
+            if (lane == 0 && b0 + r < B) {
+                float t = v + bv;
+                if (act == 3) t = t > 0.f ? t : t * alpha;
+                if (act == 2) t = fmaxf(t, 0.f);
+                y[(size_t)(b0 + r) * out_f + o] = t * act_gain;
+            }
+        }
+    }
+}
+
 static unsigned grid1d(int64_t items, int block) {
     int64_t blocks = ceil_div64(items, block);
     int64_t cap = (int64_t)sm_count() * 32;
@@ -539,6 +586,17 @@ extern "C" int p3d_affine_batch(const float* ws, const float* weight, const floa
     if ((((uintptr_t)ws | (uintptr_t)weight) & 15) != 0 || (((uintptr_t)meta) & 15) != 0) return P3D_BAD_ARG;
     affine_batch_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(ws, weight, bias, reinterpret_cast<const int4*>(meta), out, B,
                                                                              num_ws, w_dim, rows);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+extern "C" int p3d_fc_bias_act(const float* x, const float* weight, const float* bias, float* y, int B, int in_features, int out_features,
+                               float weight_gain, float bias_gain, int act, float alpha, float act_gain, p3d_stream_t stream) {
+    if (!x || !weight || !y || B <= 0 || in_features <= 0 || out_features <= 0) return P3D_BAD_ARG;
+    if (act < 1 || act > 3) return P3D_UNSUPPORTED;          // linear, relu, lrelu (codes of p3d_bias_act)
+    if ((in_features & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)weight)) & 15) != 0) return P3D_BAD_ARG;
+    fc_bias_act_kernel<8><<<ceil_div(out_features, 8), 256, 0, (cudaStream_t)stream>>>(x, weight, bias, y, B, in_features, out_features,
+                                                                                       weight_gain, bias_gain, act, alpha, act_gain);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

@@ -455,3 +455,16 @@ def decoder_mlp(decoder, sampled_features):
     sigma = outs[sigma_net][1]
     rgb = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs], dim=-1)
     return {'rgb': rgb, 'sigma': sigma}
+
+
+def fc_bias_act(x, weight, bias, weight_gain, bias_gain, act, alpha, act_gain):
+    """FullyConnectedLayer.forward on p3d_fc_bias_act: x [B,in] fp32 (no gradients), act = p3d_bias_act code."""
+    xc, wc = _f32c(x.detach()), _f32c(weight.detach())
+    bc = None if bias is None else _f32c(bias.detach())
+    y = torch.empty(xc.shape[0], wc.shape[0], device=xc.device, dtype=torch.float32)
+    with torch.cuda.device(xc.device):
+        st = _lib.lib().p3d_fc_bias_act(_lib.ptr(xc), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(y), xc.shape[0], xc.shape[1], wc.shape[0],
+                                        float(weight_gain), float(bias_gain), int(act), float(alpha), float(act_gain), _lib.stream_ptr())
+    _lib.check(st, 'p3d_fc_bias_act')
+    _lib.bump()
+    return y

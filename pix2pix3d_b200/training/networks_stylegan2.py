@@ -98,7 +98,16 @@ class FullyConnectedLayer(torch.nn.Module):
         self.weight_gain = lr_multiplier / np.sqrt(in_features)
         self.bias_gain = lr_multiplier
 
+    _NATIVE_ACTS = {'linear': (1, 0.0, 1.0), 'relu': (2, 0.0, float(np.sqrt(2))), 'lrelu': (3, 0.2, float(np.sqrt(2)))}
+
     def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and x.ndim == 2 and 0 < x.shape[0] <= 64 and self.activation in self._NATIVE_ACTS
+                and self.weight.dtype == torch.float32
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad
+                                                      or (self.bias is not None and self.bias.requires_grad)))):
+            # small-batch inference (mapping networks): weight scaling + GEMM + bias + activation in one libp3d launch
+            from .. import native
+            return native.fc_bias_act(x, self.weight, self.bias, self.weight_gain, self.bias_gain, *self._NATIVE_ACTS[self.activation])
         w = self.weight.to(x.dtype) * self.weight_gain
         b = self.bias
         if b is not None:

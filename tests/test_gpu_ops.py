@@ -198,3 +198,66 @@ def test_dual_discriminator_cuda_forward():
     with torch.no_grad():
         out = D({'image': t('dd_image'), 'image_raw': t('dd_image_raw')}, t('dd_c').clone(), force_fp32=True)
     assert rel_err(out.cpu().numpy(), g['dd_logits']) < 1e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32, torch.float64])
+@pytest.mark.parametrize('shapes', [
+    ((2, 16, 8, 8), (2, 16, 1, 1), (2, 1, 8, 8)),        # modulated_conv2d: x * dcoefs + noise (networks_stylegan2.py:79-82), vector path
+    ((3, 5, 7, 9), (3, 5, 1, 1), (7, 9)),                # odd sizes: scalar path, lower-rank noise
+    ((2, 4, 6, 8), (2, 4, 6, 8), ()),                    # the gradient form: dout * b + 0
+    ((1, 1, 4, 16), (2, 3, 1, 1), (2, 1, 4, 1)),         # every operand broadcast somewhere
+    ((5, 12), (12,), (5, 1)),
+])
+def test_fma_kernel_matches_addcmul(dtype, shapes):
+    from pix2pix3d_b200 import _lib
+    from pix2pix3d_b200.torch_utils.ops import fma
+    torch.manual_seed(3)
+    a, b, c = (torch.randn(s, device='cuda', dtype=torch.float64).to(dtype) for s in shapes)
+    before = _lib.launch_count
+    y = fma.fma(a, b, c)
+    assert _lib.launch_count == before + 1
+    ref = torch.addcmul(c, a, b)
+    assert y.shape == ref.shape and y.dtype == ref.dtype
+    tol = {torch.float16: 1e-3, torch.float32: 2e-7, torch.float64: 1e-15}[dtype]
+    assert rel_err(y.double().cpu().numpy(), ref.double().cpu().numpy()) <= tol
+    if dtype == torch.float16:       # fp32 arithmetic, one rounding
+        exact = (a.double() * b.double() + c.double()).half()
+        assert (y != exact).float().mean().item() < 1e-3
+
+
+def test_fma_gradients_first_and_second_order():
+    from pix2pix3d_b200.torch_utils.ops import fma
+    torch.manual_seed(4)
+    a = torch.randn(2, 3, 4, 4, device='cuda', dtype=torch.float64, requires_grad=True)
+    b = torch.randn(2, 3, 1, 1, device='cuda', dtype=torch.float64, requires_grad=True)
+    c = torch.randn(2, 1, 4, 4, device='cuda', dtype=torch.float64, requires_grad=True)
+    assert torch.autograd.gradcheck(fma.fma, (a, b, c))
+    assert torch.autograd.gradgradcheck(fma.fma, (a, b, c))
+
+
+@pytest.mark.parametrize('act', ['linear', 'lrelu', 'relu'])
+@pytest.mark.parametrize('b,fin,fout,bias', [(4, 512, 512, True), (1, 25, 512, True), (17, 96, 33, False), (64, 512, 100, True)])
+def test_fully_connected_layer_small_batch_kernel(act, b, fin, fout, bias):
+    """FullyConnectedLayer.forward on p3d_fc_bias_act (no gradients, batch <= 64) against its torch formulation in float64."""
+    from pix2pix3d_b200 import _lib
+    from pix2pix3d_b200.training.networks_stylegan2 import FullyConnectedLayer
+    torch.manual_seed(9)
+    fc = FullyConnectedLayer(fin, fout, bias=bias, activation=act, lr_multiplier=0.01, bias_init=0.3).cuda()
+    x = torch.randn(b, fin, device='cuda')
+    before = _lib.launch_count
+    with torch.no_grad():
+        y = fc(x)
+    assert _lib.launch_count == before + 1
+    w = fc.weight.double() * fc.weight_gain
+    ref = x.double() @ w.t()
+    if bias:
+        ref = ref + fc.bias.double() * fc.bias_gain
+    if act == 'lrelu':
+        ref = torch.nn.functional.leaky_relu(ref, 0.2) * np.sqrt(2)
+    if act == 'relu':
+        ref = torch.relu(ref) * np.sqrt(2)
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    # gradients required -> the autograd formulation (cuBLAS + p3d_bias_act), same values
+    x2 = x.clone().requires_grad_(True)
+    y2 = fc(x2)
+    assert y2.requires_grad and rel_err(y2.detach().cpu().numpy(), ref.cpu().numpy()) < 2e-6
