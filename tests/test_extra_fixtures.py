@@ -60,6 +60,8 @@ def test_extra_generators_cuda_match_reference(name, force_fp32):
     res, g = _run(name, torch.device('cuda'), force_fp32)
     assert _lib.launch_count > before, 'native kernels were not used'
     for k, v in res.items():
-        full = k in ('image', 'semantic')
-        tol = 2e-2 if (full and not force_fp32) else 1e-3        # the SR stacks run fp16 unless force_fp32, as the reference on CUDA
+        # the SR stacks run fp16 unless force_fp32, as the reference on CUDA; with the 4X stack at its native input resolution the
+        # reference's SynthesisBlockNoUp adds its (fp16) ToRGB term IN PLACE into image_raw (superresolution.py:283)
+        fp16_part = k in ('image', 'semantic') or (k == 'image_raw' and name == 'sr4x_native')
+        tol = 2e-2 if (fp16_part and not force_fp32) else 1e-3
         assert rel_err(v, g['out_' + k]) < tol, (k, force_fp32)
