@@ -439,6 +439,13 @@ int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noi
                            float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                            p3d_stream_t stream);
 
+/* EXPERIMENT (A/B measurement of FIR formulations; same arguments, bit-identical results): variant 1 = the kernel behind the two
+ * entries above, 0 = persistent TMA-ring kernel on fp32 pairs (FFMA2), 2 = the same with the taps held in vector registers. */
+int p3d_fir_act_nhwc_variant(int variant, const void* x, int in_dtype, int split_in, const float* f, const float* noise, const float* bias,
+                             void* y, int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                             float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                             p3d_stream_t stream);
+
 
 /* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */
 int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream);

@@ -389,6 +389,220 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_kernel(const __grid_constant
     }
 }
 
+// ---- packed fp32 pairs: sm_100 issues two IEEE fp32 operations per lane with FFMA2 / FADD2 / FMUL2 (PTX .f32x2). Each half
+// is rounded exactly as the scalar instruction would, so a kernel written on pairs is bit-identical to its scalar form.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Persistent form of the kernel above (the one p3d_fir_act_nhwc launches): the grid is sized to the machine, every CTA walks
+// tiles (channel block fastest, so neighbouring CTAs read the two 128-byte halves of the same pixel rows) through a ring of
+// kStages TMA halo boxes, so the load of tile n + kStages - 1 is in flight while tile n is filtered and tile n - 1 is being
+// stored. The arithmetic runs on fp32 PAIRS of neighbouring channels (FFMA2): 8 instead of 16 multiply-add instructions per
+// output element, same operations in the same order as the scalar kernel (bit-identical results).
+template <class TIn, int VEC, bool kSplitIn, int kStages, bool kTapRegs = false>
+__global__ void __launch_bounds__(256) fir_act_nhwc_ring_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ f,
+                                                                const float* __restrict__ noise, const float* __restrict__ bias,
+                                                                __half* __restrict__ y, int out_planes, size_t out_plane_stride,
+                                                                int outH, int outW, int C, int padx0, int pady0, float fir_gain,
+                                                                int act, float alpha, float act_gain, float clamp, int B,
+                                                                int64_t noise_bstride, int tiles_x, int tiles_y, int cblocks, int n_tiles) {
+    extern __shared__ __align__(128) uint4 ring[];   // kStages x (209 pixels x 128 bytes) (x 2 planes when kSplitIn)
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ float tap_copies[kTapRegs ? 16 * 32 : 1];
+    constexpr int kTileVecs = kFirIH * kFirIW * 8;
+    constexpr int kStageVecs = kTileVecs * (kSplitIn ? 2 : 1);
+    constexpr int CB = 8 * VEC;                      // channels per block (8 vectors of 16 bytes)
+    constexpr int NP = VEC / 2;                      // fp32 pairs per thread and pixel
+    const int tid = threadIdx.x;
+
+    auto issue = [&](int tile, int stage) {          // thread 0: the halo box(es) of `tile` into ring slot `stage`
+        const int cb = tile % cblocks;
+        int t = tile / cblocks;
+        const int txi = t % tiles_x; t /= tiles_x;
+        const int tyi = t % tiles_y;
+        const int bb = t / tiles_y;
+        uint4* dst = ring + (size_t)stage * kStageVecs;
+        tc::mbar_expect_tx(&full_bar[stage], (uint32_t)(kStageVecs * 16));
+        tc::tma_load_4d(dst, &tmX, &full_bar[stage], cb * CB, txi * kFirTW - padx0, tyi * kFirTH - pady0, bb);
+        if (kSplitIn) tc::tma_load_4d(dst + kTileVecs, &tmX, &full_bar[stage], cb * CB, txi * kFirTW - padx0, tyi * kFirTH - pady0, B + bb);
+    };
+
+    if (tid == 0) {
+        tc::tma_prefetch_desc(&tmX);
+        for (int s = 0; s < kStages; ++s) tc::mbar_init(&full_bar[s], 1);
+        tc::fence_barrier_init();
+    }
+    uint64_t ft2[4][4];                              // mirrored taps (true convolution, flip_filter=False), gain folded, as (t, t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float t = __ldg(f + (3 - j) * 4 + (3 - i)) * fir_gain;
+            if (kTapRegs) {        // every lane reads its own copy: the tap lives in a vector register pair, not in a uniform register
+                tap_copies[(j * 4 + i) * 32 + (tid & 31)] = t;
+                __syncwarp();
+                t = *reinterpret_cast<volatile float*>(&tap_copies[(j * 4 + i) * 32 + (tid & 31)]);
+            }
+            ft2[j][i] = f2_pack(t, t);
+        }
+    const bool round16 = (sizeof(TIn) == 2) && !kSplitIn;     // a hi/lo input carries fp32 semantics
+    const int v = tid & 7, blk = tid >> 3;                    // 32 blocks: 4 rows x 8 cols of 2x2
+    const int by = (blk >> 3) * 2, bx = (blk & 7) * 2;
+    const bool fast_lrelu = alpha >= 0.f && alpha <= 1.f;
+    const uint64_t alpha2 = f2_pack(alpha, alpha), gain2 = f2_pack(act_gain, act_gain);
+    __syncthreads();                                 // barrier init visible to the waiters
+    if (tid == 0) {
+        for (int s = 0; s < kStages - 1; ++s) {
+            const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
+            if (tile < n_tiles) issue((int)tile, s);
+        }
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % kStages;
+        // refill: tile it + kStages - 1 goes into the slot that iteration it - 1 consumed (every thread left that iteration's
+        // __syncthreads after its last read of the slot)
+        if (tid == 0) {
+            const long long nt = (long long)tile + (long long)(kStages - 1) * gridDim.x;
+            if (nt < n_tiles) issue((int)nt, (it + kStages - 1) % kStages);
+        }
+        const int cb = tile % cblocks;
+        int tq = tile / cblocks;
+        const int tx0 = (tq % tiles_x) * kFirTW; tq /= tiles_x;
+        const int ty0 = (tq % tiles_y) * kFirTH;
+        const int b = tq / tiles_y;
+        const int c = cb * CB + v * VEC;
+        uint64_t bv2[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) bv2[k] = bias ? f2_pack(__ldg(bias + c + 2 * k), __ldg(bias + c + 2 * k + 1)) : f2_pack(0.f, 0.f);
+        tc::mbar_wait(&full_bar[stage], (uint32_t)((it / kStages) & 1));
+        const uint4* tile_s = ring + (size_t)stage * kStageVecs;
+        // ---- 2x2 outputs per thread; every window element feeds its (up to) four outputs as soon as it is converted ----
+        uint64_t acc[2][2][NP];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int k = 0; k < NP; ++k) acc[i][j][k] = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+#pragma unroll
+            for (int cc = 0; cc < 5; ++cc) {
+                const uint4 raw = tile_s[((by + r) * kFirIW + bx + cc) * 8 + v];
+                uint64_t w[NP];
+                if (sizeof(TIn) == 2) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                    if (kSplitIn) {
+                        const uint4 rawl = tile_s[kTileVecs + ((by + r) * kFirIW + bx + cc) * 8 + v];
+                        const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) {
+                            const float2 a = __half22float2(h[k % 4]), l = __half22float2(hl[k % 4]);
+                            w[k] = f2_add(f2_pack(a.x, a.y), f2_pack(l.x, l.y));
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) {
+                            const float2 a = __half22float2(h[k % 4]);
+                            w[k] = f2_pack(a.x, a.y);
+                        }
+                    }
+                } else {
+                    w[0] = f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y));
+                    w[NP - 1] = f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w));
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int ty = r - i;
+                    if (ty < 0 || ty > 3) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int tx = cc - j;
+                        if (tx < 0 || tx > 3) continue;
+#pragma unroll
+                        for (int k = 0; k < NP; ++k) acc[i][j][k] = f2_fma(ft2[ty][tx], w[k], acc[i][j][k]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                             // every thread has read its window: the slot may be refilled
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int py = ty0 + by + i, px = tx0 + bx + j;
+                if (py >= outH || px >= outW) continue;
+                const float nz = noise ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
+                const uint64_t nz2 = f2_pack(nz, nz);
+                const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
+                __align__(16) __half2 hv[NP], lv[NP];
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    uint64_t x2 = acc[i][j][k];
+                    if (round16) {   // the fp16 reference rounds the FIR output, and again after the in-place noise add
+                        float2 t = f2_unpack(x2);
+                        t = __half22float2(__floats2half2_rn(t.x, t.y));
+                        x2 = f2_add(f2_pack(t.x, t.y), nz2);
+                        if (noise) {
+                            t = f2_unpack(x2);
+                            t = __half22float2(__floats2half2_rn(t.x, t.y));
+                            x2 = f2_pack(t.x, t.y);
+                        }
+                    } else {
+                        x2 = f2_add(x2, nz2);
+                    }
+                    x2 = f2_add(x2, bv2[k]);
+                    float2 x = f2_unpack(x2);
+                    if (act == 3) {
+                        const float2 m = f2_unpack(f2_mul(x2, alpha2));
+                        if (fast_lrelu) { x.x = fmaxf(x.x, m.x); x.y = fmaxf(x.y, m.y); }
+                        else { x.x = x.x > 0.f ? x.x : m.x; x.y = x.y > 0.f ? x.y : m.y; }
+                    }
+                    x = f2_unpack(f2_mul(f2_pack(x.x, x.y), gain2));
+                    if (clamp >= 0.f) { x.x = fminf(fmaxf(x.x, -clamp), clamp); x.y = fminf(fmaxf(x.y, -clamp), clamp); }
+                    const __half2 hh = __floats2half2_rn(x.x, x.y);
+                    hv[k] = hh;
+                    if (out_planes == 2) {
+                        const float2 back = __half22float2(hh);
+                        lv[k] = __floats2half2_rn(x.x - back.x, x.y - back.y);
+                    }
+                }
+                if (VEC == 8) {
+                    *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
+                    if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
+                } else {
+                    *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
+                    if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
+                }
+            }
+        }
+    }
+}
+
 // upsample2d(img, [1,3,3,1]) on fp32 NHWC: zero-insert x2, pad (2,1), 4x4 FIR, gain 4 (upfirdn2d.py:344-350).
 // Polyphase form: one thread owns an input pixel (x VEC channels) and writes its 2x2 output quad from the 3x3 input
 // neighbourhood; output (2y+py, 2x+px) only sees filter taps of parity (py, px), i.e. 2x2 of the 16 taps.
@@ -626,13 +840,35 @@ extern "C" int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, 
     return P3D_OK;
 }
 
-static int fir_act_nhwc_impl(bool split_in, const void* x, int in_dtype, const float* f, const float* noise, const float* bias, void* y,
-                                int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_bstride, p3d_stream_t stream) {
+template <class TIn, int VEC, bool kSplitIn, int kStages, bool kTapRegs = false>
+static int fir_ring_launch(const CUtensorMap& tm, const float* f, const float* noise, const float* bias, __half* y, int out_planes,
+                           size_t ps, int outH, int outW, int C, int padx0, int pady0, float fir_gain, int act, float alpha,
+                           float act_gain, float clamp, int B, int64_t noise_bstride, int tiles_x, int tiles_y, int cblocks,
+                           cudaStream_t stream) {
+    auto kern = fir_act_nhwc_ring_kernel<TIn, VEC, kSplitIn, kStages, kTapRegs>;
+    const size_t smem = (size_t)kStages * kFirIH * kFirIW * 128 * (kSplitIn ? 2 : 1);
+    P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    P3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) return P3D_UNSUPPORTED;
+    const long long n_tiles = (long long)tiles_x * tiles_y * cblocks * B;
+    if (n_tiles > 0x7fffffffLL) return P3D_UNSUPPORTED;
+    long long ctas = (long long)sm_count() * per_sm;
+    if (ctas > n_tiles) ctas = n_tiles;
+    kern<<<(unsigned)ctas, 256, smem, stream>>>(tm, f, noise, bias, y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act, alpha,
+                                                act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, cblocks, (int)n_tiles);
+    return P3D_OK;
+}
+
+// variant 0: persistent TMA-ring kernel on fp32 pairs; variant 1: one tile per CTA, scalar arithmetic (kept for A/B runs)
+static int fir_act_nhwc_impl(int variant, bool split_in, const void* x, int in_dtype, const float* f, const float* noise, const float* bias,
+                             void* y, int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                             float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_bstride, p3d_stream_t stream) {
     if (!x || !f || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
     if (act != 1 && act != 3) return P3D_UNSUPPORTED;
     const size_t ps = (size_t)B * outH * outW * C;
-    const int tiles = ceil_div(outW, kFirTW) * ceil_div(outH, kFirTH);
+    const int tiles_x = ceil_div(outW, kFirTW), tiles_y = ceil_div(outH, kFirTH);
+    const int tiles = tiles_x * tiles_y;
     if (B > 65535) return P3D_UNSUPPORTED;
     if (in_dtype != P3D_F32 && in_dtype != P3D_F16) return P3D_BAD_ARG;
     if (split_in && in_dtype != P3D_F16) return P3D_BAD_ARG;
@@ -647,6 +883,29 @@ static int fir_act_nhwc_impl(bool split_in, const void* x, int in_dtype, const f
         int rc = make_tmap(&tm, x, in_dtype == P3D_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                            CU_TENSOR_MAP_SWIZZLE_NONE, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
+    }
+    if (variant == 2 && !split_in && in_dtype == P3D_F16) {
+        int rc = fir_ring_launch<__half, 8, false, 3, true>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain,
+                                                            act, alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb,
+                                                            (cudaStream_t)stream);
+        if (rc != P3D_OK) return rc;
+        P3D_LAUNCH_CHECK();
+        return P3D_OK;
+    }
+    if (variant == 0 || variant == 2) {
+        int rc;
+        if (split_in)
+            rc = fir_ring_launch<__half, 8, true, 2>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
+                                                     alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
+        else if (in_dtype == P3D_F32)
+            rc = fir_ring_launch<float, 4, false, 3>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
+                                                     alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
+        else
+            rc = fir_ring_launch<__half, 8, false, 3>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
+                                                      alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
+        if (rc != P3D_OK) return rc;
+        P3D_LAUNCH_CHECK();
+        return P3D_OK;
     }
     dim3 grid(tiles, C / cb, B);
     const size_t tile_bytes = (size_t)kFirIH * kFirIW * 128;
@@ -671,7 +930,7 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
                                 int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                                 float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                                 p3d_stream_t stream) {
-    return fir_act_nhwc_impl(false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
+    return fir_act_nhwc_impl(1, false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
                              alpha, act_gain, clamp, noise_batch_stride, stream);
 }
 
@@ -679,8 +938,16 @@ extern "C" int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const
                                       int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                                       float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                                       p3d_stream_t stream) {
-    return fir_act_nhwc_impl(true, x_hi_lo, P3D_F16, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain,
+    return fir_act_nhwc_impl(1, true, x_hi_lo, P3D_F16, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain,
                              act, alpha, act_gain, clamp, noise_batch_stride, stream);
+}
+
+extern "C" int p3d_fir_act_nhwc_variant(int variant, const void* x, int in_dtype, int split_in, const float* f, const float* noise, const float* bias, void* y,
+                                   int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                                   float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                                   p3d_stream_t stream) {
+    return fir_act_nhwc_impl(variant, split_in != 0, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0,
+                             fir_gain, act, alpha, act_gain, clamp, noise_batch_stride, stream);
 }
 
 extern "C" int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream) {

@@ -275,6 +275,9 @@ def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SC
     return out
 
 
+FIR_VARIANT = int(os.environ.get('P3D_FIR_VARIANT', '1'))     # read once by the host binding (A/B runs only)
+
+
 def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):
     """x [B,inH,inW,C] fp32/fp16 NHWC, or a split fp16 pair [2,B,inH,inW,C] -> [out_planes,B,outH,outW,C] fp16."""
     split_in = x.ndim == 5
@@ -289,7 +292,11 @@ def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.
     if noise is not None:
         assert noise.is_contiguous() and noise.dtype == torch.float32 and noise.shape[-2:] == (oh, ow)
     with torch.cuda.device(x.device):
-        if split_in:
+        if FIR_VARIANT != 1:        # A/B experiment: 0 / 2 = persistent fp32-pair kernels
+            st = _lib.lib().p3d_fir_act_nhwc_variant(FIR_VARIANT, _lib.ptr(x), _lib.DTYPE_CODE[x.dtype], int(split_in), _lib.ptr(f),
+                                                     _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0],
+                                                     pad0[1], fir_gain, act, alpha, act_gain, clamp, nbs, _lib.stream_ptr())
+        elif split_in:
             st = _lib.lib().p3d_fir_act_nhwc_split(_lib.ptr(x), _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b,
                                                    ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha, act_gain, clamp,
                                                    nbs, _lib.stream_ptr())
