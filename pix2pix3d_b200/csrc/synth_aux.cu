@@ -473,6 +473,8 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_ring_kernel(const __grid_con
     const int by = (blk >> 3) * 2, bx = (blk & 7) * 2;
     const bool fast_lrelu = alpha >= 0.f && alpha <= 1.f;
     const uint64_t alpha2 = f2_pack(alpha, alpha), gain2 = f2_pack(act_gain, act_gain);
+    const bool clamp_h_ok = clamp >= 0.f && __half2float(__float2half_rn(clamp)) == clamp;
+    const __half2 clamp_hi = __float2half2_rn(clamp), clamp_lo = __float2half2_rn(-clamp);
     __syncthreads();                                 // barrier init visible to the waiters
     if (tid == 0) {
         for (int s = 0; s < kStages - 1; ++s) {
@@ -583,8 +585,14 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_ring_kernel(const __grid_con
                         else { x.x = x.x > 0.f ? x.x : m.x; x.y = x.y > 0.f ? x.y : m.y; }
                     }
                     x = f2_unpack(f2_mul(f2_pack(x.x, x.y), gain2));
-                    if (clamp >= 0.f) { x.x = fminf(fmaxf(x.x, -clamp), clamp); x.y = fminf(fmaxf(x.y, -clamp), clamp); }
-                    const __half2 hh = __floats2half2_rn(x.x, x.y);
+                    __half2 hh;
+                    if (clamp_h_ok && out_planes == 1) {
+                        // round, then clamp on the packed halves: same result as clamp-then-round (the bound is an fp16 number)
+                        hh = __hmin2(__hmax2(__floats2half2_rn(x.x, x.y), clamp_lo), clamp_hi);
+                    } else {
+                        if (clamp >= 0.f) { x.x = fminf(fmaxf(x.x, -clamp), clamp); x.y = fminf(fmaxf(x.y, -clamp), clamp); }
+                        hh = __floats2half2_rn(x.x, x.y);
+                    }
                     hv[k] = hh;
                     if (out_planes == 2) {
                         const float2 back = __half22float2(hh);
@@ -885,7 +893,7 @@ static int fir_act_nhwc_impl(int variant, bool split_in, const void* x, int in_d
         if (rc != P3D_OK) return rc;
     }
     if (variant == 2 && !split_in && in_dtype == P3D_F16) {
-        int rc = fir_ring_launch<__half, 8, false, 3, true>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain,
+        int rc = fir_ring_launch<__half, 8, false, 2, true>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain,
                                                             act, alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb,
                                                             (cudaStream_t)stream);
         if (rc != P3D_OK) return rc;
@@ -901,7 +909,7 @@ static int fir_act_nhwc_impl(int variant, bool split_in, const void* x, int in_d
             rc = fir_ring_launch<float, 4, false, 3>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
                                                      alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
         else
-            rc = fir_ring_launch<__half, 8, false, 3>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
+            rc = fir_ring_launch<__half, 8, false, 2>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
                                                       alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
         if (rc != P3D_OK) return rc;
         P3D_LAUNCH_CHECK();

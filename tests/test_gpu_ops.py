@@ -256,8 +256,8 @@ def test_fully_connected_layer_small_batch_kernel(act, b, fin, fout, bias):
         ref = torch.nn.functional.leaky_relu(ref, 0.2) * np.sqrt(2)
     if act == 'relu':
         ref = torch.relu(ref) * np.sqrt(2)
-    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    assert rel_err(y.cpu().numpy(), ref.cpu().numpy()) < 1e-5
     # gradients required -> the autograd formulation (cuBLAS + p3d_bias_act), same values
     x2 = x.clone().requires_grad_(True)
     y2 = fc(x2)
-    assert y2.requires_grad and rel_err(y2.detach().cpu().numpy(), ref.cpu().numpy()) < 2e-6
+    assert y2.requires_grad and rel_err(y2.detach().cpu().numpy(), ref.cpu().numpy()) < 1e-5

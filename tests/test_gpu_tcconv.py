@@ -369,7 +369,7 @@ def test_merged_transposed_conv_phases_equal_separate_launches(b, c, cout, hw, s
     if split:
         # fp32 accumulators: the merged launch may pick another kernel shape (CTA pairs: M = 256 MMAs) or another split-K factor than
         # the separate launches do -> another summation grouping, equal to rounding
-        assert torch.allclose(outs[0], outs[1], rtol=0, atol=2e-6 * float(outs[1].abs().max()))
+        assert torch.allclose(outs[0], outs[1], rtol=0, atol=1e-5 * float(outs[1].abs().max()))
     else:
         assert torch.equal(outs[0], outs[1])
     if split:
