@@ -439,12 +439,16 @@ int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const float* noi
                            float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                            p3d_stream_t stream);
 
-/* EXPERIMENT (A/B measurement of FIR formulations; same arguments, bit-identical results): variant 1 = the kernel behind the two
- * entries above, 0 = persistent TMA-ring kernel on fp32 pairs (FFMA2), 2 = the same with the taps held in vector registers. */
-int p3d_fir_act_nhwc_variant(int variant, const void* x, int in_dtype, int split_in, const float* f, const float* noise, const float* bias,
-                             void* y, int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                             float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
-                             p3d_stream_t stream);
+/* The same operation for a SEPARABLE 4x4 filter f[j][i] = fy[j] * fx[i] (what upfirdn2d.setup_filter builds from a 1-D tap list,
+ * upfirdn2d.py:60-63): fx / fy are HOST arrays (the caller factors the filter once per buffer); the kernel runs the row pass and
+ * the column pass on a 4x2 output block per thread, 11 instead of 16 multiply-adds per output element. Same rounding points as
+ * p3d_fir_act_nhwc (fp32 accumulation, one rounding of the filtered value in the fp16 case); sums are formed in another order, so
+ * results agree with it to fp32 rounding, not bit for bit. */
+int p3d_fir_act_nhwc_sep(const void* x, int in_dtype, const float fx[4], const float fy[4], const float* noise, const float* bias,
+                         void* y, int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                         float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                         p3d_stream_t stream);
+
 
 
 /* upsample2d(img, f) with up=2 (upfirdn2d.py:315-350) on an fp32 NHWC image: [B,H,W,C] -> [B,2H,2W,C]. */

@@ -417,196 +417,141 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
     return d;
 }
 
-// Persistent form of the kernel above (the one p3d_fir_act_nhwc launches): the grid is sized to the machine, every CTA walks
-// tiles (channel block fastest, so neighbouring CTAs read the two 128-byte halves of the same pixel rows) through a ring of
-// kStages TMA halo boxes, so the load of tile n + kStages - 1 is in flight while tile n is filtered and tile n - 1 is being
-// stored. The arithmetic runs on fp32 PAIRS of neighbouring channels (FFMA2): 8 instead of 16 multiply-add instructions per
-// output element, same operations in the same order as the scalar kernel (bit-identical results).
-template <class TIn, int VEC, bool kSplitIn, int kStages, bool kTapRegs = false>
-__global__ void __launch_bounds__(256) fir_act_nhwc_ring_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ f,
-                                                                const float* __restrict__ noise, const float* __restrict__ bias,
-                                                                __half* __restrict__ y, int out_planes, size_t out_plane_stride,
-                                                                int outH, int outW, int C, int padx0, int pady0, float fir_gain,
-                                                                int act, float alpha, float act_gain, float clamp, int B,
-                                                                int64_t noise_bstride, int tiles_x, int tiles_y, int cblocks, int n_tiles) {
-    extern __shared__ __align__(128) uint4 ring[];   // kStages x (209 pixels x 128 bytes) (x 2 planes when kSplitIn)
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ float tap_copies[kTapRegs ? 16 * 32 : 1];
+// Separable form of the FIR tail for rank-1 filters f[j][i] = fy[j] * fx[i] (upfirdn2d.setup_filter([1,3,3,1]) is one: the
+// caller factors the filter once per buffer and hands the eight taps over BY VALUE, so they sit in the constant bank and cost no
+// registers). A thread owns a 4 (rows) x 2 (columns) output block of 4 channels: per window row two horizontal 4-tap sums, each
+// feeding up to four output rows -- 11 instead of 16 multiply-adds per output element, issued on fp32 pairs (FFMA2), and 35
+// instead of 50 half->float conversions per 8 outputs. The kernel is instruction-issue bound (ncu: 83 % issue-active at 48
+// instructions per output element in the 16-tap form), so the instruction count is what sets its speed.
+struct FirSepTaps { float fx[4], fy[4]; };        // already mirrored (true convolution) and with the gain folded into fx
+
+template <class TIn>
+__global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_constant__ CUtensorMap tmX, const FirSepTaps taps,
+                                                               const float* __restrict__ noise, const float* __restrict__ bias,
+                                                               __half* __restrict__ y, int out_planes, size_t out_plane_stride,
+                                                               int outH, int outW, int C, int padx0, int pady0, int act, float alpha,
+                                                               float act_gain, float clamp, int B, int64_t noise_bstride) {
+    extern __shared__ __align__(128) uint4 tile[];   // 209 pixels x 128 bytes
+    __shared__ __align__(8) uint64_t bar;
     constexpr int kTileVecs = kFirIH * kFirIW * 8;
-    constexpr int kStageVecs = kTileVecs * (kSplitIn ? 2 : 1);
-    constexpr int CB = 8 * VEC;                      // channels per block (8 vectors of 16 bytes)
-    constexpr int NP = VEC / 2;                      // fp32 pairs per thread and pixel
-    const int tid = threadIdx.x;
-
-    auto issue = [&](int tile, int stage) {          // thread 0: the halo box(es) of `tile` into ring slot `stage`
-        const int cb = tile % cblocks;
-        int t = tile / cblocks;
-        const int txi = t % tiles_x; t /= tiles_x;
-        const int tyi = t % tiles_y;
-        const int bb = t / tiles_y;
-        uint4* dst = ring + (size_t)stage * kStageVecs;
-        tc::mbar_expect_tx(&full_bar[stage], (uint32_t)(kStageVecs * 16));
-        tc::tma_load_4d(dst, &tmX, &full_bar[stage], cb * CB, txi * kFirTW - padx0, tyi * kFirTH - pady0, bb);
-        if (kSplitIn) tc::tma_load_4d(dst + kTileVecs, &tmX, &full_bar[stage], cb * CB, txi * kFirTW - padx0, tyi * kFirTH - pady0, B + bb);
-    };
-
-    if (tid == 0) {
-        tc::tma_prefetch_desc(&tmX);
-        for (int s = 0; s < kStages; ++s) tc::mbar_init(&full_bar[s], 1);
+    constexpr int NQ = 128 / (4 * (int)sizeof(TIn));          // 4-channel groups per 128-byte block: 16 (fp16) or 8 (fp32)
+    constexpr int CB = 4 * NQ;                                // channels per block
+    const int tiles_x = (outW + kFirTW - 1) / kFirTW;
+    const int tx0 = (blockIdx.x % tiles_x) * kFirTW, ty0 = (blockIdx.x / tiles_x) * kFirTH;
+    const int c0 = blockIdx.y * CB, b = blockIdx.z;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(&bar, 1);
         tc::fence_barrier_init();
+        tc::mbar_expect_tx(&bar, (uint32_t)(kTileVecs * 16));
+        tc::tma_load_4d(tile, &tmX, &bar, c0, tx0 - padx0, ty0 - pady0, b);
     }
-    uint64_t ft2[4][4];                              // mirrored taps (true convolution, flip_filter=False), gain folded, as (t, t)
+    const bool round16 = sizeof(TIn) == 2;
+    const int v = threadIdx.x % NQ, blk = threadIdx.x / NQ;   // 16 blocks: 2 (rows of 4) x 8 (columns of 2)
+    const int by = (blk >> 3) * 4, bx = (blk & 7) * 2;
+    const int c = c0 + v * 4;
+    uint64_t bv2[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int k = 0; k < 2; ++k) bv2[k] = bias ? f2_pack(__ldg(bias + c + 2 * k), __ldg(bias + c + 2 * k + 1)) : f2_pack(0.f, 0.f);
+    uint64_t fx2[4], fy2[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float t = __ldg(f + (3 - j) * 4 + (3 - i)) * fir_gain;
-            if (kTapRegs) {        // every lane reads its own copy: the tap lives in a vector register pair, not in a uniform register
-                tap_copies[(j * 4 + i) * 32 + (tid & 31)] = t;
-                __syncwarp();
-                t = *reinterpret_cast<volatile float*>(&tap_copies[(j * 4 + i) * 32 + (tid & 31)]);
-            }
-            ft2[j][i] = f2_pack(t, t);
-        }
-    const bool round16 = (sizeof(TIn) == 2) && !kSplitIn;     // a hi/lo input carries fp32 semantics
-    const int v = tid & 7, blk = tid >> 3;                    // 32 blocks: 4 rows x 8 cols of 2x2
-    const int by = (blk >> 3) * 2, bx = (blk & 7) * 2;
+    for (int k = 0; k < 4; ++k) { fx2[k] = f2_pack(taps.fx[k], taps.fx[k]); fy2[k] = f2_pack(taps.fy[k], taps.fy[k]); }
     const bool fast_lrelu = alpha >= 0.f && alpha <= 1.f;
     const uint64_t alpha2 = f2_pack(alpha, alpha), gain2 = f2_pack(act_gain, act_gain);
     const bool clamp_h_ok = clamp >= 0.f && __half2float(__float2half_rn(clamp)) == clamp;
     const __half2 clamp_hi = __float2half2_rn(clamp), clamp_lo = __float2half2_rn(-clamp);
     __syncthreads();                                 // barrier init visible to the waiters
-    if (tid == 0) {
-        for (int s = 0; s < kStages - 1; ++s) {
-            const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
-            if (tile < n_tiles) issue((int)tile, s);
-        }
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int stage = it % kStages;
-        // refill: tile it + kStages - 1 goes into the slot that iteration it - 1 consumed (every thread left that iteration's
-        // __syncthreads after its last read of the slot)
-        if (tid == 0) {
-            const long long nt = (long long)tile + (long long)(kStages - 1) * gridDim.x;
-            if (nt < n_tiles) issue((int)nt, (it + kStages - 1) % kStages);
-        }
-        const int cb = tile % cblocks;
-        int tq = tile / cblocks;
-        const int tx0 = (tq % tiles_x) * kFirTW; tq /= tiles_x;
-        const int ty0 = (tq % tiles_y) * kFirTH;
-        const int b = tq / tiles_y;
-        const int c = cb * CB + v * VEC;
-        uint64_t bv2[NP];
+    tc::mbar_wait(&bar, 0);
+    uint64_t acc[4][2][2];
 #pragma unroll
-        for (int k = 0; k < NP; ++k) bv2[k] = bias ? f2_pack(__ldg(bias + c + 2 * k), __ldg(bias + c + 2 * k + 1)) : f2_pack(0.f, 0.f);
-        tc::mbar_wait(&full_bar[stage], (uint32_t)((it / kStages) & 1));
-        const uint4* tile_s = ring + (size_t)stage * kStageVecs;
-        // ---- 2x2 outputs per thread; every window element feeds its (up to) four outputs as soon as it is converted ----
-        uint64_t acc[2][2][NP];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) { acc[i][j][0] = f2_pack(0.f, 0.f); acc[i][j][1] = f2_pack(0.f, 0.f); }
+    const uint8_t* tb = reinterpret_cast<const uint8_t*>(tile);
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        uint64_t w[5][2];
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) {
+            const uint8_t* src = tb + ((by + r) * kFirIW + bx + cc) * 128 + v * (4 * (int)sizeof(TIn));
+            if (sizeof(TIn) == 2) {
+                const uint2 raw = *reinterpret_cast<const uint2*>(src);
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), bq = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                w[cc][0] = f2_pack(a.x, a.y); w[cc][1] = f2_pack(bq.x, bq.y);
+            } else {
+                const uint4 raw = *reinterpret_cast<const uint4*>(src);
+                w[cc][0] = f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y));
+                w[cc][1] = f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w));
+            }
+        }
+        uint64_t h[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                uint64_t t = f2_mul(fx2[0], w[j][k]);
+                t = f2_fma(fx2[1], w[j + 1][k], t);
+                t = f2_fma(fx2[2], w[j + 2][k], t);
+                h[j][k] = f2_fma(fx2[3], w[j + 3][k], t);
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ty = r - i;
+            if (ty < 0 || ty > 3) continue;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int k = 0; k < NP; ++k) acc[i][j][k] = f2_pack(0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-#pragma unroll
-            for (int cc = 0; cc < 5; ++cc) {
-                const uint4 raw = tile_s[((by + r) * kFirIW + bx + cc) * 8 + v];
-                uint64_t w[NP];
-                if (sizeof(TIn) == 2) {
-                    const __half2* h = reinterpret_cast<const __half2*>(&raw);
-                    if (kSplitIn) {
-                        const uint4 rawl = tile_s[kTileVecs + ((by + r) * kFirIW + bx + cc) * 8 + v];
-                        const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) {
-                            const float2 a = __half22float2(h[k % 4]), l = __half22float2(hl[k % 4]);
-                            w[k] = f2_add(f2_pack(a.x, a.y), f2_pack(l.x, l.y));
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) {
-                            const float2 a = __half22float2(h[k % 4]);
-                            w[k] = f2_pack(a.x, a.y);
-                        }
-                    }
-                } else {
-                    w[0] = f2_pack(__uint_as_float(raw.x), __uint_as_float(raw.y));
-                    w[NP - 1] = f2_pack(__uint_as_float(raw.z), __uint_as_float(raw.w));
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int ty = r - i;
-                    if (ty < 0 || ty > 3) continue;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int tx = cc - j;
-                        if (tx < 0 || tx > 3) continue;
-#pragma unroll
-                        for (int k = 0; k < NP; ++k) acc[i][j][k] = f2_fma(ft2[ty][tx], w[k], acc[i][j][k]);
-                    }
-                }
-            }
+                for (int k = 0; k < 2; ++k) acc[i][j][k] = f2_fma(fy2[ty], h[j][k], acc[i][j][k]);
         }
-        __syncthreads();                             // every thread has read its window: the slot may be refilled
+    }
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int py = ty0 + by + i, px = tx0 + bx + j;
-                if (py >= outH || px >= outW) continue;
-                const float nz = noise ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
-                const uint64_t nz2 = f2_pack(nz, nz);
-                const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
-                __align__(16) __half2 hv[NP], lv[NP];
+        for (int j = 0; j < 2; ++j) {
+            const int py = ty0 + by + i, px = tx0 + bx + j;
+            if (py >= outH || px >= outW) continue;
+            const float nz = noise ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
+            const uint64_t nz2 = f2_pack(nz, nz);
+            const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
+            __align__(8) __half2 hv[2], lv[2];
 #pragma unroll
-                for (int k = 0; k < NP; ++k) {
-                    uint64_t x2 = acc[i][j][k];
-                    if (round16) {   // the fp16 reference rounds the FIR output, and again after the in-place noise add
-                        float2 t = f2_unpack(x2);
+            for (int k = 0; k < 2; ++k) {
+                uint64_t x2 = acc[i][j][k];
+                if (round16) {   // the fp16 reference rounds the FIR output, and again after the in-place noise add
+                    float2 t = f2_unpack(x2);
+                    t = __half22float2(__floats2half2_rn(t.x, t.y));
+                    x2 = f2_add(f2_pack(t.x, t.y), nz2);
+                    if (noise) {
+                        t = f2_unpack(x2);
                         t = __half22float2(__floats2half2_rn(t.x, t.y));
-                        x2 = f2_add(f2_pack(t.x, t.y), nz2);
-                        if (noise) {
-                            t = f2_unpack(x2);
-                            t = __half22float2(__floats2half2_rn(t.x, t.y));
-                            x2 = f2_pack(t.x, t.y);
-                        }
-                    } else {
-                        x2 = f2_add(x2, nz2);
+                        x2 = f2_pack(t.x, t.y);
                     }
-                    x2 = f2_add(x2, bv2[k]);
-                    float2 x = f2_unpack(x2);
-                    if (act == 3) {
-                        const float2 m = f2_unpack(f2_mul(x2, alpha2));
-                        if (fast_lrelu) { x.x = fmaxf(x.x, m.x); x.y = fmaxf(x.y, m.y); }
-                        else { x.x = x.x > 0.f ? x.x : m.x; x.y = x.y > 0.f ? x.y : m.y; }
-                    }
-                    x = f2_unpack(f2_mul(f2_pack(x.x, x.y), gain2));
-                    __half2 hh;
-                    if (clamp_h_ok && out_planes == 1) {
-                        // round, then clamp on the packed halves: same result as clamp-then-round (the bound is an fp16 number)
-                        hh = __hmin2(__hmax2(__floats2half2_rn(x.x, x.y), clamp_lo), clamp_hi);
-                    } else {
-                        if (clamp >= 0.f) { x.x = fminf(fmaxf(x.x, -clamp), clamp); x.y = fminf(fmaxf(x.y, -clamp), clamp); }
-                        hh = __floats2half2_rn(x.x, x.y);
-                    }
-                    hv[k] = hh;
-                    if (out_planes == 2) {
-                        const float2 back = __half22float2(hh);
-                        lv[k] = __floats2half2_rn(x.x - back.x, x.y - back.y);
-                    }
-                }
-                if (VEC == 8) {
-                    *reinterpret_cast<uint4*>(y + o) = *reinterpret_cast<const uint4*>(hv);
-                    if (out_planes == 2) *reinterpret_cast<uint4*>(y + out_plane_stride + o) = *reinterpret_cast<const uint4*>(lv);
                 } else {
-                    *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
-                    if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
+                    x2 = f2_add(x2, nz2);
+                }
+                x2 = f2_add(x2, bv2[k]);
+                float2 x = f2_unpack(x2);
+                if (act == 3) {
+                    const float2 m = f2_unpack(f2_mul(x2, alpha2));
+                    if (fast_lrelu) { x.x = fmaxf(x.x, m.x); x.y = fmaxf(x.y, m.y); }
+                    else { x.x = x.x > 0.f ? x.x : m.x; x.y = x.y > 0.f ? x.y : m.y; }
+                }
+                x = f2_unpack(f2_mul(f2_pack(x.x, x.y), gain2));
+                __half2 hh;
+                if (clamp_h_ok && out_planes == 1) {
+                    // round, then clamp on the packed halves: same result as clamp-then-round (the bound is an fp16 number)
+                    hh = __hmin2(__hmax2(__floats2half2_rn(x.x, x.y), clamp_lo), clamp_hi);
+                } else {
+                    if (clamp >= 0.f) { x.x = fminf(fmaxf(x.x, -clamp), clamp); x.y = fminf(fmaxf(x.y, -clamp), clamp); }
+                    hh = __floats2half2_rn(x.x, x.y);
+                }
+                hv[k] = hh;
+                if (out_planes == 2) {
+                    const float2 back = __half22float2(hh);
+                    lv[k] = __floats2half2_rn(x.x - back.x, x.y - back.y);
                 }
             }
+            *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
+            if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
         }
     }
 }
@@ -848,28 +793,7 @@ extern "C" int p3d_nhwc_to_nchw_f32(const float* x, int N, int C, int H, int W, 
     return P3D_OK;
 }
 
-template <class TIn, int VEC, bool kSplitIn, int kStages, bool kTapRegs = false>
-static int fir_ring_launch(const CUtensorMap& tm, const float* f, const float* noise, const float* bias, __half* y, int out_planes,
-                           size_t ps, int outH, int outW, int C, int padx0, int pady0, float fir_gain, int act, float alpha,
-                           float act_gain, float clamp, int B, int64_t noise_bstride, int tiles_x, int tiles_y, int cblocks,
-                           cudaStream_t stream) {
-    auto kern = fir_act_nhwc_ring_kernel<TIn, VEC, kSplitIn, kStages, kTapRegs>;
-    const size_t smem = (size_t)kStages * kFirIH * kFirIW * 128 * (kSplitIn ? 2 : 1);
-    P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    P3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
-    if (per_sm < 1) return P3D_UNSUPPORTED;
-    const long long n_tiles = (long long)tiles_x * tiles_y * cblocks * B;
-    if (n_tiles > 0x7fffffffLL) return P3D_UNSUPPORTED;
-    long long ctas = (long long)sm_count() * per_sm;
-    if (ctas > n_tiles) ctas = n_tiles;
-    kern<<<(unsigned)ctas, 256, smem, stream>>>(tm, f, noise, bias, y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act, alpha,
-                                                act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, cblocks, (int)n_tiles);
-    return P3D_OK;
-}
-
-// variant 0: persistent TMA-ring kernel on fp32 pairs; variant 1: one tile per CTA, scalar arithmetic (kept for A/B runs)
-static int fir_act_nhwc_impl(int variant, bool split_in, const void* x, int in_dtype, const float* f, const float* noise, const float* bias,
+static int fir_act_nhwc_impl(bool split_in, const void* x, int in_dtype, const float* f, const float* noise, const float* bias,
                              void* y, int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                              float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_bstride, p3d_stream_t stream) {
     if (!x || !f || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
@@ -891,29 +815,6 @@ static int fir_act_nhwc_impl(int variant, bool split_in, const void* x, int in_d
         int rc = make_tmap(&tm, x, in_dtype == P3D_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                            CU_TENSOR_MAP_SWIZZLE_NONE, 4, dims, str, box);
         if (rc != P3D_OK) return rc;
-    }
-    if (variant == 2 && !split_in && in_dtype == P3D_F16) {
-        int rc = fir_ring_launch<__half, 8, false, 2, true>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain,
-                                                            act, alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb,
-                                                            (cudaStream_t)stream);
-        if (rc != P3D_OK) return rc;
-        P3D_LAUNCH_CHECK();
-        return P3D_OK;
-    }
-    if (variant == 0 || variant == 2) {
-        int rc;
-        if (split_in)
-            rc = fir_ring_launch<__half, 8, true, 2>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
-                                                     alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
-        else if (in_dtype == P3D_F32)
-            rc = fir_ring_launch<float, 4, false, 3>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
-                                                     alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
-        else
-            rc = fir_ring_launch<__half, 8, false, 2>(tm, f, noise, bias, (__half*)y, out_planes, ps, outH, outW, C, padx0, pady0, fir_gain, act,
-                                                      alpha, act_gain, clamp, B, noise_bstride, tiles_x, tiles_y, C / cb, (cudaStream_t)stream);
-        if (rc != P3D_OK) return rc;
-        P3D_LAUNCH_CHECK();
-        return P3D_OK;
     }
     dim3 grid(tiles, C / cb, B);
     const size_t tile_bytes = (size_t)kFirIH * kFirIW * 128;
@@ -938,7 +839,7 @@ extern "C" int p3d_fir_act_nhwc(const void* x, int in_dtype, const float* f, con
                                 int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                                 float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                                 p3d_stream_t stream) {
-    return fir_act_nhwc_impl(1, false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
+    return fir_act_nhwc_impl(false, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain, act,
                              alpha, act_gain, clamp, noise_batch_stride, stream);
 }
 
@@ -946,16 +847,46 @@ extern "C" int p3d_fir_act_nhwc_split(const void* x_hi_lo, const float* f, const
                                       int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
                                       float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
                                       p3d_stream_t stream) {
-    return fir_act_nhwc_impl(1, true, x_hi_lo, P3D_F16, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain,
+    return fir_act_nhwc_impl(true, x_hi_lo, P3D_F16, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0, fir_gain,
                              act, alpha, act_gain, clamp, noise_batch_stride, stream);
 }
 
-extern "C" int p3d_fir_act_nhwc_variant(int variant, const void* x, int in_dtype, int split_in, const float* f, const float* noise, const float* bias, void* y,
-                                   int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
-                                   float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
-                                   p3d_stream_t stream) {
-    return fir_act_nhwc_impl(variant, split_in != 0, x, in_dtype, f, noise, bias, y, out_planes, B, inH, inW, outH, outW, C, padx0, pady0,
-                             fir_gain, act, alpha, act_gain, clamp, noise_batch_stride, stream);
+extern "C" int p3d_fir_act_nhwc_sep(const void* x, int in_dtype, const float fx[4], const float fy[4], const float* noise, const float* bias,
+                                     void* y, int out_planes, int B, int inH, int inW, int outH, int outW, int C, int padx0, int pady0,
+                                     float fir_gain, int act, float alpha, float act_gain, float clamp, int64_t noise_batch_stride,
+                                     p3d_stream_t stream) {
+    if (!x || !fx || !fy || !y || B <= 0 || C <= 0 || out_planes < 1 || out_planes > 2) return P3D_BAD_ARG;
+    if (act != 1 && act != 3) return P3D_UNSUPPORTED;
+    if (B > 65535) return P3D_UNSUPPORTED;
+    if (in_dtype != P3D_F32 && in_dtype != P3D_F16) return P3D_BAD_ARG;
+    const int es = in_dtype == P3D_F32 ? 4 : 2, cb = 128 / es;
+    if (C % cb) return P3D_UNSUPPORTED;
+    if (((uintptr_t)x & 15) != 0 || ((uintptr_t)y & 7) != 0) return P3D_BAD_ARG;
+    const size_t ps = (size_t)B * outH * outW * C;
+    const int tiles = ceil_div(outW, kFirTW) * ceil_div(outH, kFirTH);
+    CUtensorMap tm;
+    {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)inW, (uint64_t)inH, (uint64_t)B};
+        uint64_t str[3] = {(uint64_t)C * es, (uint64_t)inW * C * es, (uint64_t)inH * inW * C * es};
+        uint32_t box[4] = {(uint32_t)cb, (uint32_t)kFirIW, (uint32_t)kFirIH, 1};
+        int rc = make_tmap(&tm, x, in_dtype == P3D_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, 4, dims, str, box);
+        if (rc != P3D_OK) return rc;
+    }
+    FirSepTaps taps;                                 // mirrored: true convolution (flip_filter=False), gain folded into the row taps
+    for (int k = 0; k < 4; ++k) { taps.fx[k] = fx[3 - k] * fir_gain; taps.fy[k] = fy[3 - k]; }
+    dim3 grid(tiles, C / cb, B);
+    const size_t tile_bytes = (size_t)kFirIH * kFirIW * 128;
+    if (in_dtype == P3D_F32)
+        fir_act_nhwc_sep_kernel<float><<<grid, 128, tile_bytes, (cudaStream_t)stream>>>(tm, taps, noise, bias, (__half*)y, out_planes, ps, outH,
+                                                                                         outW, C, padx0, pady0, act, alpha, act_gain, clamp, B,
+                                                                                         noise_batch_stride);
+    else
+        fir_act_nhwc_sep_kernel<__half><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(tm, taps, noise, bias, (__half*)y, out_planes, ps, outH,
+                                                                                          outW, C, padx0, pady0, act, alpha, act_gain, clamp, B,
+                                                                                          noise_batch_stride);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
 }
 
 extern "C" int p3d_upsample2x_nhwc(const float* x, const float* f, float* y, int B, int H, int W, int C, p3d_stream_t stream) {

@@ -275,7 +275,27 @@ def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SC
     return out
 
 
-FIR_VARIANT = int(os.environ.get('P3D_FIR_VARIANT', '1'))     # read once by the host binding (A/B runs only)
+FIR_VARIANT = int(os.environ.get('P3D_FIR_VARIANT', '1'))     # read once by the host binding (A/B runs only); 3 = separable kernel
+
+_SEP_CACHE = {}
+
+
+def separable_factors(f):
+    """(fx, fy) as ctypes float[4] arrays with f[j][i] == fy[j] * fx[i] exactly (in fp32), or None. Looked up once per filter
+    buffer (a device -> host copy), so it must first happen outside CUDA-graph capture; upfirdn2d.setup_filter([1,3,3,1]) qualifies."""
+    key = (f.data_ptr(), f._version, f.device)
+    hit = _SEP_CACHE.get(key)
+    if hit is None:
+        res = False
+        if tuple(f.shape) == (4, 4) and f.dtype == torch.float32:
+            m = f.detach().cpu()
+            if float(m[0, 0]) != 0.0:
+                fx = m[0].clone()
+                fy = (m[:, 0] / m[0, 0]).clone()
+                if torch.equal(fy[:, None] * fx[None, :], m):
+                    res = ((ctypes.c_float * 4)(*fx.tolist()), (ctypes.c_float * 4)(*fy.tolist()))
+        _SEP_CACHE[key] = hit = res
+    return hit or None
 
 
 def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):
@@ -291,11 +311,12 @@ def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.
     nbs = 0 if (noise is None or noise.ndim == 2) else oh * ow          # per-sample noise images (noise_mode='random')
     if noise is not None:
         assert noise.is_contiguous() and noise.dtype == torch.float32 and noise.shape[-2:] == (oh, ow)
+    sep = separable_factors(f) if (FIR_VARIANT == 3 and not split_in) else None
     with torch.cuda.device(x.device):
-        if FIR_VARIANT != 1:        # A/B experiment: 0 / 2 = persistent fp32-pair kernels
-            st = _lib.lib().p3d_fir_act_nhwc_variant(FIR_VARIANT, _lib.ptr(x), _lib.DTYPE_CODE[x.dtype], int(split_in), _lib.ptr(f),
-                                                     _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0],
-                                                     pad0[1], fir_gain, act, alpha, act_gain, clamp, nbs, _lib.stream_ptr())
+        if sep is not None:
+            st = _lib.lib().p3d_fir_act_nhwc_sep(_lib.ptr(x), _lib.DTYPE_CODE[x.dtype], sep[0], sep[1], _lib.ptr(noise), _lib.ptr(bias),
+                                                 _lib.ptr(y), out_planes, b, ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha,
+                                                 act_gain, clamp, nbs, _lib.stream_ptr())
         elif split_in:
             st = _lib.lib().p3d_fir_act_nhwc_split(_lib.ptr(x), _lib.ptr(f), _lib.ptr(noise), _lib.ptr(bias), _lib.ptr(y), out_planes, b,
                                                    ih, iw, oh, ow, c, pad0[0], pad0[1], fir_gain, act, alpha, act_gain, clamp,

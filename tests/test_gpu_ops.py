@@ -248,10 +248,10 @@ def test_fully_connected_layer_small_batch_kernel(act, b, fin, fout, bias):
     with torch.no_grad():
         y = fc(x)
     assert _lib.launch_count == before + 1
-    w = fc.weight.double() * fc.weight_gain
+    w = fc.weight.detach().double() * fc.weight_gain
     ref = x.double() @ w.t()
     if bias:
-        ref = ref + fc.bias.double() * fc.bias_gain
+        ref = ref + fc.bias.detach().double() * fc.bias_gain
     if act == 'lrelu':
         ref = torch.nn.functional.leaky_relu(ref, 0.2) * np.sqrt(2)
     if act == 'relu':
