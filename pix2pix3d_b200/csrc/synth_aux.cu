@@ -151,6 +151,43 @@ __device__ __forceinline__ void modulate_row(const float* __restrict__ wt, const
             if (lane == 0) dsm[b] = (demod ? rsqrtf(acc + 1e-8f) : 1.f) * out_scale;
         }
         __syncthreads();
+        if (cin_off == 0 && (Cin & 7) == 0 && nb <= 8) {
+            // common case (whole-tensor inputs, batches of up to 8): every weight vector is read ONCE (two 16-byte loads) and reused
+            // for all samples, whose style x demodulation factors for this thread's 8 channels sit in registers
+            const bool live = ip < Cin;
+            float sv[8][8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < nb) {
+                    const float ds = dsm[b];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) sv[b][k] = live ? __ldg(styles + (size_t)(b0 + b) * Cin + ip + k) * pre_scale * ds : 0.f;
+                }
+            }
+            for (int t = trow; t < ktaps; t += tstep) {
+                const float* wr = wt + ((size_t)o * ktaps + t) * Cin + ip;
+                float wv[8];
+                if (live) {
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr) + 1);
+                    wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) wv[k] = 0.f;
+                }
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    if (b < nb) {
+                        __half* dst = out + ((size_t)(b0 + b) * Cout_p + o) * row_elems;
+                        __align__(16) __half hv[8], lv[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) split_half(wv[k] * sv[b][k], hv[k], lv[k]);
+                        *reinterpret_cast<uint4*>(dst + (size_t)t * Cin_p + ip) = *reinterpret_cast<const uint4*>(hv);
+                        if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride + (size_t)t * Cin_p + ip) = *reinterpret_cast<const uint4*>(lv);
+                    }
+                }
+            }
+            continue;
+        }
         for (int b = 0; b < nb; ++b) {
             const float ds = dsm[b];
             float sv[8];
@@ -459,6 +496,15 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_cons
     const uint64_t alpha2 = f2_pack(alpha, alpha), gain2 = f2_pack(act_gain, act_gain);
     const bool clamp_h_ok = clamp >= 0.f && __half2float(__float2half_rn(clamp)) == clamp;
     const __half2 clamp_hi = __float2half2_rn(clamp), clamp_lo = __float2half2_rn(-clamp);
+    // the per-pixel noise values are fetched before the tile is waited for, so their latency hides under the TMA load and the filter
+    float nzv[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int py = ty0 + by + i, px = tx0 + bx + j;
+            nzv[i][j] = (noise && py < outH && px < outW) ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
+        }
     __syncthreads();                                 // barrier init visible to the waiters
     tc::mbar_wait(&bar, 0);
     uint64_t acc[4][2][2];
@@ -509,7 +555,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_cons
         for (int j = 0; j < 2; ++j) {
             const int py = ty0 + by + i, px = tx0 + bx + j;
             if (py >= outH || px >= outW) continue;
-            const float nz = noise ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
+            const float nz = nzv[i][j];
             const uint64_t nz2 = f2_pack(nz, nz);
             const size_t o = (((size_t)b * outH + py) * outW + px) * C + c;
             __align__(8) __half2 hv[2], lv[2];

@@ -275,7 +275,8 @@ def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SC
     return out
 
 
-FIR_VARIANT = int(os.environ.get('P3D_FIR_VARIANT', '1'))     # read once by the host binding (A/B runs only); 3 = separable kernel
+# 3: separable filters (setup_filter builds them) take p3d_fir_act_nhwc_sep; 1: always the 16-tap kernel (A/B runs). Read once here.
+FIR_VARIANT = int(os.environ.get('P3D_FIR_VARIANT', '3'))
 
 _SEP_CACHE = {}
 

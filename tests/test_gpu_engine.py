@@ -133,7 +133,7 @@ def test_graphed_synthesis_replays_and_matches_eager():
     ws, c = torch.from_numpy(g['ws']).cuda(), torch.from_numpy(g['c']).cuda()
     kw = dict(noise_mode='const', neural_rendering_resolution=case['nrr'])
     gs = GraphedSynthesis(G, ws, c, **kw)
-    assert gs.native_launches > 60
+    assert gs.native_launches > 40      # libp3d launches captured in the graph (an up layer is 2: merged phases + FIR)
     torch.manual_seed(123)
     a = {k: v.clone() for k, v in gs(ws, c).items()}
     torch.cuda.synchronize()

@@ -39,7 +39,7 @@ def test_synthesis_cuda_matches_reference(name, force_fp32):
         torch.rand_like, torch.rand = o_like, o_rand
     assert _lib.launch_count > before, 'native kernels were not used'
     if name == 'seg_nrr64':
-        assert _lib.launch_count - before > 60, 'whole-generator tensor-core path was expected here'
+        assert _lib.launch_count - before > 40, 'whole-generator tensor-core path was expected here'
     # renderer outputs are fp32 in both modes; the SR stacks run fp16 unless force_fp32 (superresolution.py:304)
     for k in ('image_raw', 'image_depth', 'semantic_raw'):
         if k in out:
