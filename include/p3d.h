@@ -177,16 +177,19 @@ int p3d_sample_from_planes_bwd(const float* grad_features, const float* coords, 
  *   x = mean over the 3 planes of feats [N,3,M,32];  h = softplus(w1 x + b1);  o = w2 h + b2   (w1 [64,32], w2 [33,64], runtime
  *   gains of FullyConnectedLayer already applied by the caller, networks_stylegan2.py:111-119; Softplus(beta 1, threshold 20))
  *   out_sigma [N*M] = o[0];  out_rgb [N*M,32][k] = bit k of sigmoid_mask ? sigmoid(o[1+k]) * 1.002 - 0.001 : o[1+k].
- * One launch instead of mean + addmm + softplus + addmm + slices + sigmoid + cat. */
+ * out_pre (optional, [N*M,64]): the hidden pre-activations w1 x + b1, which p3d_decoder_mlp_bwd consumes (pass NULL when no
+ * gradient will be taken). One launch instead of mean + addmm + softplus + addmm + slices + sigmoid + cat. */
 int p3d_decoder_mlp_fwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
-                        const float* b2, uint32_t sigmoid_mask, float* out_rgb, float* out_sigma, p3d_stream_t stream);
+                        const float* b2, uint32_t sigmoid_mask, float* out_rgb, float* out_sigma, float* out_pre,
+                        p3d_stream_t stream);
 
 /* First-order backward of p3d_decoder_mlp_fwd (what autograd derives from the module's forward): g_rgb [N*M,32] / g_sigma [N*M]
  * (either may be NULL = zeros) -> g_feats [N,3,M,32] and g_params [4257] = dL/dw1 [64,32] | dL/db1 [64] | dL/dw2 [33,64] |
- * dL/db2 [33]. The forward is recomputed per point; parameter gradients are accumulated per CTA and added in a fixed order
- * (deterministic). workspace: fp32 scratch of at least p3d_decoder_mlp_bwd_workspace_floats() elements. */
+ * dL/db2 [33]. pre / out_rgb: the forward's out_pre and out_rgb (nothing of the forward GEMMs is recomputed; the sigmoid
+ * derivative follows from the output). Parameter gradients are accumulated per CTA and added in a fixed order (deterministic).
+ * workspace: fp32 scratch of at least p3d_decoder_mlp_bwd_workspace_floats() elements. */
 int p3d_decoder_mlp_bwd_workspace_floats(void);
-int p3d_decoder_mlp_bwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
+int p3d_decoder_mlp_bwd(const float* feats, const float* pre, const float* out_rgb, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
                         const float* b2, uint32_t sigmoid_mask, const float* g_rgb, const float* g_sigma, float* g_feats,
                         float* g_params, float* workspace, int64_t workspace_floats, p3d_stream_t stream);
 

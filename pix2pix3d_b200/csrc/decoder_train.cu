@@ -90,7 +90,8 @@ __device__ __forceinline__ float dec_softplus(float a, float& dsp) {
 __global__ void __launch_bounds__(128) decoder_mlp_fwd_kernel(const float* __restrict__ feats, int64_t N, int64_t M,
                                                                const float* __restrict__ w1, const float* __restrict__ b1,
                                                                const float* __restrict__ w2, const float* __restrict__ b2,
-                                                               uint32_t mask, float* __restrict__ out_rgb, float* __restrict__ out_sigma) {
+                                                               uint32_t mask, float* __restrict__ out_rgb, float* __restrict__ out_sigma,
+                                                               float* __restrict__ out_pre) {
     __shared__ __align__(16) DecSmemW s;
     dec_load_weights(s, w1, b1, w2, b2);
     __syncthreads();
@@ -101,11 +102,15 @@ __global__ void __launch_bounds__(128) decoder_mlp_fwd_kernel(const float* __res
         float o[kDecOut];
 #pragma unroll
         for (int k = 0; k < kDecOut; ++k) o[k] = s.b2[k];
-#pragma unroll 4
-        for (int j = 0; j < kDecHid; ++j) {
-            float dsp;
-            const float h = dec_softplus(dec_hidden_pre(s, j, x), dsp);
-            dec_out_accum(s, j, h, o);
+        for (int j4 = 0; j4 < kDecHid; j4 += 4) {
+            float a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float dsp;
+                a[u] = dec_hidden_pre(s, j4 + u, x);
+                dec_out_accum(s, j4 + u, dec_softplus(a[u], dsp), o);
+            }
+            if (out_pre) *reinterpret_cast<float4*>(out_pre + pt * kDecHid + j4) = make_float4(a[0], a[1], a[2], a[3]);
         }
         out_sigma[pt] = o[0];
         float4* dst = reinterpret_cast<float4*>(out_rgb + pt * 32);
@@ -124,12 +129,13 @@ __global__ void __launch_bounds__(128) decoder_mlp_fwd_kernel(const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward: tiles of 64 points per CTA of 128 threads. Phase A: a lane PAIR owns a point and splits the 64 hidden units (the
-// two partial output rows / input gradients are exchanged with shuffles), recomputes the forward and forms dL/do, dL/da1, dL/dx.
-// Phase B: the CTA turns the tile's rows of (h, dL/da1, dL/do, x) kept in shared memory into parameter-gradient contributions
-// (thread = half a row of dW2 and dW1, looping over the tile's points); partial sums stay in registers across the CTA's tiles
-// and are written once per CTA; a second kernel adds the CTAs in a fixed order. 70 KB of shared memory per CTA -> 3 CTAs
-// (12 warps) per SM: the per-point chains of dependent FMAs need the other warps to hide their latency.
+// backward: tiles of 64 points per CTA of 128 threads. The forward saved the hidden pre-activations a1 [points, 64]; together with
+// the op's own output (sigmoid'(o) = s (1 - s) with s = (rgb + 0.001) / 1.002) nothing of the forward GEMMs is recomputed.
+// Phase A: a lane PAIR owns a point and splits the 64 hidden units: h = softplus(a1), dL/dh = W2^T dL/do, dL/da1 = dL/dh * sigmoid(a1),
+// partial dL/dx = W1^T dL/da1 (exchanged with shuffles). Phase B: the CTA turns the tile's rows of (h, dL/da1, dL/do, x) kept in
+// shared memory into parameter-gradient contributions (thread = half a row of dW2 and dW1, looping over the tile's points);
+// partial sums stay in registers across the CTA's tiles and are written once per CTA; a second kernel adds the CTAs in a fixed
+// order. 70 KB of shared memory per CTA -> 3 CTAs (12 warps) per SM.
 // ---------------------------------------------------------------------------------------------
 constexpr int kBwdTile = 64;
 constexpr int kHS = kDecHid + 2;                  // row stride of the h / da1 tiles: unit j lives in column j + (j >= 32), which keeps
@@ -141,12 +147,13 @@ constexpr int kBwdCtasPerSm = 3;
 struct DecSmemBwd {
     DecSmemW w;
     float h[kBwdTile * kHS];
-    float ga[kBwdTile * kHS];                     // sigmoid(a1) while the tile is being recomputed, then dL/da1
+    float ga[kBwdTile * kHS];
     float go[kBwdTile * kGS];
     float x[kBwdTile * kXS];
 };
 
-__global__ void __launch_bounds__(128, kBwdCtasPerSm) decoder_mlp_bwd_kernel(const float* __restrict__ feats, int64_t N, int64_t M,
+__global__ void __launch_bounds__(128, kBwdCtasPerSm) decoder_mlp_bwd_kernel(const float* __restrict__ feats, const float* __restrict__ pre,
+                                                               const float* __restrict__ out_rgb, int64_t N, int64_t M,
                                                                const float* __restrict__ w1, const float* __restrict__ b1,
                                                                const float* __restrict__ w2, const float* __restrict__ b2, uint32_t mask,
                                                                const float* __restrict__ g_rgb, const float* __restrict__ g_sigma,
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(128, kBwdCtasPerSm) decoder_mlp_bwd_kernel(con
     DecSmemBwd& s = *reinterpret_cast<DecSmemBwd*>(smem_raw);
     dec_load_weights(s.w, w1, b1, w2, b2);
     const int t = threadIdx.x;
-    // phase A: point of the tile and half of the hidden units
+    // phase A: point of the tile and half of the hidden units / input channels
     const int pl = t >> 1, q = t & 1, j0 = 32 * q;
     // phase B: parameter-gradient ownership, j = hidden unit, half = which half of the row
     const int j = t & 63, half = t >> 6, jc = j + (j >> 5);
@@ -171,47 +178,36 @@ __global__ void __launch_bounds__(128, kBwdCtasPerSm) decoder_mlp_bwd_kernel(con
         const int64_t pt = tile * kBwdTile + pl;
         const bool valid = pt < P;
         const int64_t n = valid ? pt / M : 0, m = valid ? pt % M : 0;
-        // ---- phase A: recompute the forward, then dL/do, dL/da1, dL/dx ----
-        float x[kDecIn];
-        if (valid) dec_load_mean(feats, n, m, M, x);
-        else {
+        // ---- phase A ----
+        // x (mean over the planes): each lane of the pair loads and stores half of the channels (phase B needs the row)
 #pragma unroll
-            for (int i = 0; i < kDecIn; ++i) x[i] = 0.f;
+        for (int u = 0; u < 4; ++u) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const int64_t base = (n * 3 * M + m) * kDecIn + 16 * q + 4 * u;
+                const float4 a = __ldg(reinterpret_cast<const float4*>(feats + base)),
+                             bq = __ldg(reinterpret_cast<const float4*>(feats + base + M * kDecIn)),
+                             cq = __ldg(reinterpret_cast<const float4*>(feats + base + 2 * M * kDecIn));
+                v.x = ((a.x + bq.x) + cq.x) * (1.f / 3.f); v.y = ((a.y + bq.y) + cq.y) * (1.f / 3.f);
+                v.z = ((a.z + bq.z) + cq.z) * (1.f / 3.f); v.w = ((a.w + bq.w) + cq.w) * (1.f / 3.f);
+            }
+            *reinterpret_cast<float4*>(s.x + pl * kXS + 16 * q + 4 * u) = v;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {               // each lane of the pair stores half of the row
-            const int c = 16 * q + 4 * u;
-            float4 v;
-            v.x = q ? x[16 + 4 * u] : x[4 * u]; v.y = q ? x[17 + 4 * u] : x[4 * u + 1];
-            v.z = q ? x[18 + 4 * u] : x[4 * u + 2]; v.w = q ? x[19 + 4 * u] : x[4 * u + 3];
-            *reinterpret_cast<float4*>(s.x + pl * kXS + c) = v;
-        }
+        // dL/do: both lanes of the pair hold all 33 values
         float o[kDecOut];
-#pragma unroll
-        for (int k = 0; k < kDecOut; ++k) o[k] = q ? 0.f : s.w.b2[k];
-#pragma unroll 4
-        for (int jj = 0; jj < 32; ++jj) {
-            float dsp;
-            const float h = dec_softplus(dec_hidden_pre(s.w, j0 + jj, x), dsp);
-            s.h[pl * kHS + j0 + q + jj] = h;
-            s.ga[pl * kHS + j0 + q + jj] = dsp;
-            dec_out_accum(s.w, j0 + jj, h, o);
-        }
-#pragma unroll
-        for (int k = 0; k < kDecOut; ++k) o[k] += __shfl_xor_sync(0xffffffffu, o[k], 1);
-        // dL/do (reuses o; both lanes of the pair hold it)
         o[0] = (valid && g_sigma) ? __ldg(g_sigma + pt) : 0.f;
 #pragma unroll
         for (int qq = 0; qq < 8; ++qq) {
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f), yv = g;
             if (valid && g_rgb) g = __ldg(reinterpret_cast<const float4*>(g_rgb + pt * 32) + qq);
-            const float gv[4] = {g.x, g.y, g.z, g.w};
+            if (valid && mask) yv = __ldg(reinterpret_cast<const float4*>(out_rgb + pt * 32) + qq);
+            const float gv[4] = {g.x, g.y, g.z, g.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int k = 4 * qq + u;
                 float d = gv[u];
                 if ((mask >> k) & 1u) {
-                    const float sg = 1.f / (1.f + expf(-o[1 + k]));
+                    const float sg = (yy[u] + 0.001f) * (1.f / 1.002f);      // y = 1.002 s - 0.001
                     d *= 1.002f * (sg * (1.f - sg));
                 }
                 o[1 + k] = d;
@@ -226,25 +222,36 @@ __global__ void __launch_bounds__(128, kBwdCtasPerSm) decoder_mlp_bwd_kernel(con
         float gx[kDecIn];
 #pragma unroll
         for (int i = 0; i < kDecIn; ++i) gx[i] = 0.f;
-#pragma unroll 4
-        for (int jj = 0; jj < 32; ++jj) {
-            const float4* w = reinterpret_cast<const float4*>(s.w.w2t + (j0 + jj) * kW2Stride);
-            float gh0 = 0.f, gh1 = 0.f;
+        const float* prow = pre + pt * kDecHid + j0;
+#pragma unroll 2
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) av = __ldg(reinterpret_cast<const float4*>(prow + j4));
+            const float a4[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-            for (int qq = 0; qq < 8; qq += 2) {
-                const float4 wa = w[qq], wb = w[qq + 1];
-                gh0 = fmaf(wa.x, o[4 * qq], gh0); gh0 = fmaf(wa.y, o[4 * qq + 1], gh0); gh0 = fmaf(wa.z, o[4 * qq + 2], gh0); gh0 = fmaf(wa.w, o[4 * qq + 3], gh0);
-                gh1 = fmaf(wb.x, o[4 * qq + 4], gh1); gh1 = fmaf(wb.y, o[4 * qq + 5], gh1); gh1 = fmaf(wb.z, o[4 * qq + 6], gh1); gh1 = fmaf(wb.w, o[4 * qq + 7], gh1);
-            }
-            const float gh = fmaf(s.w.w2t[(j0 + jj) * kW2Stride + 32], o[32], gh0 + gh1);
-            const float ga = gh * s.ga[pl * kHS + j0 + q + jj];
-            s.ga[pl * kHS + j0 + q + jj] = ga;
-            const float4* w1r = reinterpret_cast<const float4*>(s.w.w1 + (j0 + jj) * kDecIn);
+            for (int u = 0; u < 4; ++u) {
+                const int jj = j4 + u;
+                float dsp;
+                const float h = dec_softplus(a4[u], dsp);
+                s.h[pl * kHS + j0 + q + jj] = h;
+                const float4* w = reinterpret_cast<const float4*>(s.w.w2t + (j0 + jj) * kW2Stride);
+                float gh0 = 0.f, gh1 = 0.f;
 #pragma unroll
-            for (int qq = 0; qq < kDecIn / 4; ++qq) {
-                const float4 ww = w1r[qq];
-                gx[4 * qq] = fmaf(ww.x, ga, gx[4 * qq]); gx[4 * qq + 1] = fmaf(ww.y, ga, gx[4 * qq + 1]);
-                gx[4 * qq + 2] = fmaf(ww.z, ga, gx[4 * qq + 2]); gx[4 * qq + 3] = fmaf(ww.w, ga, gx[4 * qq + 3]);
+                for (int qq = 0; qq < 8; qq += 2) {
+                    const float4 wa = w[qq], wb = w[qq + 1];
+                    gh0 = fmaf(wa.x, o[4 * qq], gh0); gh0 = fmaf(wa.y, o[4 * qq + 1], gh0); gh0 = fmaf(wa.z, o[4 * qq + 2], gh0); gh0 = fmaf(wa.w, o[4 * qq + 3], gh0);
+                    gh1 = fmaf(wb.x, o[4 * qq + 4], gh1); gh1 = fmaf(wb.y, o[4 * qq + 5], gh1); gh1 = fmaf(wb.z, o[4 * qq + 6], gh1); gh1 = fmaf(wb.w, o[4 * qq + 7], gh1);
+                }
+                const float gh = fmaf(s.w.w2t[(j0 + jj) * kW2Stride + 32], o[32], gh0 + gh1);
+                const float ga = gh * dsp;
+                s.ga[pl * kHS + j0 + q + jj] = ga;
+                const float4* w1r = reinterpret_cast<const float4*>(s.w.w1 + (j0 + jj) * kDecIn);
+#pragma unroll
+                for (int qq = 0; qq < kDecIn / 4; ++qq) {
+                    const float4 ww = w1r[qq];
+                    gx[4 * qq] = fmaf(ww.x, ga, gx[4 * qq]); gx[4 * qq + 1] = fmaf(ww.y, ga, gx[4 * qq + 1]);
+                    gx[4 * qq + 2] = fmaf(ww.z, ga, gx[4 * qq + 2]); gx[4 * qq + 3] = fmaf(ww.w, ga, gx[4 * qq + 3]);
+                }
             }
         }
 #pragma unroll
@@ -307,33 +314,35 @@ __global__ void __launch_bounds__(256) decoder_mlp_reduce_kernel(const float* __
 using namespace p3d;
 
 extern "C" int p3d_decoder_mlp_fwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
-                                   const float* b2, uint32_t sigmoid_mask, float* out_rgb, float* out_sigma, p3d_stream_t stream) {
+                                   const float* b2, uint32_t sigmoid_mask, float* out_rgb, float* out_sigma, float* out_pre,
+                                   p3d_stream_t stream) {
     if (!feats || !w1 || !b1 || !w2 || !b2 || !out_rgb || !out_sigma || N <= 0 || M <= 0) return P3D_BAD_ARG;
-    if (((((uintptr_t)feats) | ((uintptr_t)out_rgb)) & 15) != 0) return P3D_BAD_ARG;
+    if (((((uintptr_t)feats) | ((uintptr_t)out_rgb) | ((uintptr_t)out_pre)) & 15) != 0) return P3D_BAD_ARG;
     const int64_t P = N * M;
     int64_t blocks = (P + 127) / 128;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    decoder_mlp_fwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(feats, N, M, w1, b1, w2, b2, sigmoid_mask, out_rgb, out_sigma);
+    decoder_mlp_fwd_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(feats, N, M, w1, b1, w2, b2, sigmoid_mask, out_rgb, out_sigma,
+                                                                                  out_pre);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
 
 extern "C" int p3d_decoder_mlp_bwd_workspace_floats(void) { return sm_count() * kBwdCtasPerSm * kDecParams; }
 
-extern "C" int p3d_decoder_mlp_bwd(const float* feats, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
+extern "C" int p3d_decoder_mlp_bwd(const float* feats, const float* pre, const float* out_rgb, int64_t N, int64_t M, const float* w1, const float* b1, const float* w2,
                                    const float* b2, uint32_t sigmoid_mask, const float* g_rgb, const float* g_sigma, float* g_feats,
                                    float* g_params, float* workspace, int64_t workspace_floats, p3d_stream_t stream) {
-    if (!feats || !w1 || !b1 || !w2 || !b2 || !g_feats || !g_params || !workspace || N <= 0 || M <= 0) return P3D_BAD_ARG;
-    if (((((uintptr_t)feats) | ((uintptr_t)g_feats) | ((uintptr_t)g_rgb)) & 15) != 0) return P3D_BAD_ARG;
+    if (!feats || !pre || !out_rgb || !w1 || !b1 || !w2 || !b2 || !g_feats || !g_params || !workspace || N <= 0 || M <= 0) return P3D_BAD_ARG;
+    if (((((uintptr_t)feats) | ((uintptr_t)pre) | ((uintptr_t)out_rgb) | ((uintptr_t)g_feats) | ((uintptr_t)g_rgb)) & 15) != 0) return P3D_BAD_ARG;
     const int64_t P = N * M, n_tiles = (P + kBwdTile - 1) / kBwdTile;
     int64_t ctas = (int64_t)sm_count() * kBwdCtasPerSm;
     if (ctas > n_tiles) ctas = n_tiles;
     if (workspace_floats < ctas * kDecParams) return P3D_BAD_ARG;
     const size_t smem = sizeof(DecSmemBwd);
     P3D_CUDA_TRY(cudaFuncSetAttribute(decoder_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    decoder_mlp_bwd_kernel<<<(unsigned)ctas, 128, smem, (cudaStream_t)stream>>>(feats, N, M, w1, b1, w2, b2, sigmoid_mask, g_rgb, g_sigma,
-                                                                               g_feats, workspace);
+    decoder_mlp_bwd_kernel<<<(unsigned)ctas, 128, smem, (cudaStream_t)stream>>>(feats, pre, out_rgb, N, M, w1, b1, w2, b2, sigmoid_mask, g_rgb,
+                                                                               g_sigma, g_feats, workspace);
     P3D_LAUNCH_CHECK();
     decoder_mlp_reduce_kernel<<<ceil_div(kDecParams, 256), 256, 0, (cudaStream_t)stream>>>(workspace, (int)ctas, g_params);
     P3D_LAUNCH_CHECK();

@@ -151,36 +151,38 @@ __device__ __forceinline__ void modulate_row(const float* __restrict__ wt, const
             if (lane == 0) dsm[b] = (demod ? rsqrtf(acc + 1e-8f) : 1.f) * out_scale;
         }
         __syncthreads();
-        if (cin_off == 0 && (Cin & 7) == 0 && nb <= 8) {
-            // common case (whole-tensor inputs, batches of up to 8): every weight vector is read ONCE (two 16-byte loads) and reused
-            // for all samples, whose style x demodulation factors for this thread's 8 channels sit in registers
+        if (cin_off == 0 && (Cin & 7) == 0 && nb <= 8 && ktaps <= 3 * tstep) {
+            // common case (whole-tensor inputs, batches of up to 8): all of this thread's weight vectors (at most three taps x 8
+            // channels) are requested up front -- six 16-byte loads in flight per thread instead of two -- and each is reused for
+            // every sample; the samples' style x demodulation factors of the thread's 8 channels sit in registers
             const bool live = ip < Cin;
-            float sv[8][8];
+            float wv[3][8];
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (b < nb) {
-                    const float ds = dsm[b];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) sv[b][k] = live ? __ldg(styles + (size_t)(b0 + b) * Cin + ip + k) * pre_scale * ds : 0.f;
-                }
-            }
-            for (int t = trow; t < ktaps; t += tstep) {
-                const float* wr = wt + ((size_t)o * ktaps + t) * Cin + ip;
-                float wv[8];
-                if (live) {
-                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr) + 1);
-                    wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+            for (int u = 0; u < 3; ++u) {
+                const int t = trow + u * tstep;
+                if (live && t < ktaps) {
+                    const float4* wr = reinterpret_cast<const float4*>(wt + ((size_t)o * ktaps + t) * Cin + ip);
+                    const float4 w0 = __ldg(wr), w1 = __ldg(wr + 1);
+                    wv[u][0] = w0.x; wv[u][1] = w0.y; wv[u][2] = w0.z; wv[u][3] = w0.w;
+                    wv[u][4] = w1.x; wv[u][5] = w1.y; wv[u][6] = w1.z; wv[u][7] = w1.w;
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) wv[k] = 0.f;
+                    for (int k = 0; k < 8; ++k) wv[u][k] = 0.f;
                 }
+            }
+            for (int b = 0; b < nb; ++b) {
+                const float ds = dsm[b];
+                float sv[8];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    if (b < nb) {
-                        __half* dst = out + ((size_t)(b0 + b) * Cout_p + o) * row_elems;
+                for (int k = 0; k < 8; ++k) sv[k] = live ? __ldg(styles + (size_t)(b0 + b) * Cin + ip + k) * pre_scale * ds : 0.f;
+                __half* dst = out + ((size_t)(b0 + b) * Cout_p + o) * row_elems;
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int t = trow + u * tstep;
+                    if (t < ktaps) {
                         __align__(16) __half hv[8], lv[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) split_half(wv[k] * sv[b][k], hv[k], lv[k]);
+                        for (int k = 0; k < 8; ++k) split_half(wv[u][k] * sv[k], hv[k], lv[k]);
                         *reinterpret_cast<uint4*>(dst + (size_t)t * Cin_p + ip) = *reinterpret_cast<const uint4*>(hv);
                         if (planes == 2) *reinterpret_cast<uint4*>(dst + plane_stride + (size_t)t * Cin_p + ip) = *reinterpret_cast<const uint4*>(lv);
                     }
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(256) modulate_weights_t_kernel(const float* __
 }
 
 // every layer of a synthesis stack in ONE launch: block -> (layer, output channel) through a lookup table
-__global__ void __launch_bounds__(256) modulate_weights_batch_kernel(const p3d_modw_desc_t* __restrict__ descs,
+__global__ void __launch_bounds__(256, 3) modulate_weights_batch_kernel(const p3d_modw_desc_t* __restrict__ descs,
                                                                      const int32_t* __restrict__ block_layer,
                                                                      const float* __restrict__ styles_base,
                                                                      __half* __restrict__ out_base, int B) {

@@ -396,19 +396,22 @@ class _DecoderMLP(torch.autograd.Function):
         n, _, m, _ = f.shape
         rgb = torch.empty(n, m, 32, device=f.device, dtype=torch.float32)
         sigma = torch.empty(n, m, 1, device=f.device, dtype=torch.float32)
+        # hidden pre-activations for the backward pass (256 bytes per point), only when a gradient can be asked for
+        pre = torch.empty(n * m, 64, device=f.device, dtype=torch.float32) if any(ctx.needs_input_grad) else None
         with torch.cuda.device(f.device):
             st = _lib.lib().p3d_decoder_mlp_fwd(_lib.ptr(f), n, m, _lib.ptr(w1c), _lib.ptr(b1c), _lib.ptr(w2c), _lib.ptr(b2c), int(mask),
-                                                _lib.ptr(rgb), _lib.ptr(sigma), _lib.stream_ptr())
+                                                _lib.ptr(rgb), _lib.ptr(sigma), _lib.ptr(pre), _lib.stream_ptr())
         _lib.check(st, 'p3d_decoder_mlp_fwd')
         _lib.bump()
-        ctx.save_for_backward(f, w1c, b1c, w2c, b2c)
+        if pre is not None:
+            ctx.save_for_backward(f, w1c, b1c, w2c, b2c, pre, rgb)
         ctx.mask = int(mask)
         return rgb, sigma
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_rgb, g_sigma):
-        f, w1, b1, w2, b2 = ctx.saved_tensors
+        f, w1, b1, w2, b2, pre, rgb = ctx.saved_tensors
         n, _, m, _ = f.shape
         gr = None if g_rgb is None else _f32c(g_rgb)
         gs = None if g_sigma is None else _f32c(g_sigma)
@@ -417,7 +420,7 @@ class _DecoderMLP(torch.autograd.Function):
         with torch.cuda.device(f.device):
             nws = _lib.lib().p3d_decoder_mlp_bwd_workspace_floats()
             ws = torch.empty(nws, device=f.device, dtype=torch.float32)
-            st = _lib.lib().p3d_decoder_mlp_bwd(_lib.ptr(f), n, m, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), ctx.mask,
+            st = _lib.lib().p3d_decoder_mlp_bwd(_lib.ptr(f), _lib.ptr(pre), _lib.ptr(rgb), n, m, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), ctx.mask,
                                                 _lib.ptr(gr), _lib.ptr(gs), _lib.ptr(g_feats), _lib.ptr(g_params), _lib.ptr(ws), nws,
                                                 _lib.stream_ptr())
         _lib.check(st, 'p3d_decoder_mlp_bwd')
