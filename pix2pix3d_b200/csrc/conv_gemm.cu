@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(192, 2) conv_gemm_kernel(const __grid_constant
 constexpr int kPStages = 4;
 
 template <int kAct, bool kClamp>
-__global__ void __launch_bounds__(416, 1) conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                     const __grid_constant__ CUtensorMap tmB,
                                                                     const ConvKernelArgs a, int n_tiles, int tiles_n) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];

@@ -13,7 +13,6 @@ draws one noise image per sample and layer with the reference's own `torch.randn
 keeps the generic op-by-op formulation.
 """
 import logging
-import os
 import weakref
 
 import numpy as np
@@ -549,19 +548,6 @@ def generator_supported(gen, ws, c, synthesis_kwargs, use_cached_backbone):
     return True
 
 
-# A/B switch (results do not depend on it): P3D_SR_STREAMS=0 runs the two super-resolution stacks one after the other
-SR_TWO_STREAMS = os.environ.get('P3D_SR_STREAMS') != '0'
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    st = _SIDE_STREAMS.get(key)
-    if st is None:
-        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return st
-
-
 def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=False, noise_mode='random', force_fp32=False):
     """TriPlaneGenerator / TriPlaneSemanticEntangleGenerator.synthesis (triplane_cond.py:661-697, 1020-1061) without
     leaving the NHWC representation between the backbone, the fused renderer and the super-resolution stacks."""
@@ -640,21 +626,6 @@ def generator_synthesis(gen, ws, c, cache_backbone=False, use_cached_backbone=Fa
         x, im = synthesis_block(sr.block1, x, im, st[n0:], noise_mode=sr_noise, force_fp32=force_fp32, upsample=True, final_nchw=True)
         return im, raw.permute(0, 3, 1, 2).contiguous()
 
-    if semantic and SR_TWO_STREAMS and native.kernel_events is None:
-        # The two super-resolution stacks are independent: the semantic one runs on a second stream (a fork / join the CUDA graph
-        # keeps), so one stack's FIR and ToRGB kernels (CUDA-core, HBM-bound work) share the SMs with the other's tensor-core
-        # GEMMs, and the tail of every persistent launch is filled by the other stack. Same kernels, same results.
-        cs = gen.semantic_channels
-        main = torch.cuda.current_stream(ws.device)
-        side = _side_stream(ws.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            sem, sem_raw = run_sr(gen.superresolution_semantic, half, cs, styles[n_net + n_sr:])
-        image, image_raw = run_sr(gen.superresolution, 0, 3, styles[n_net:n_net + n_sr])
-        main.wait_stream(side)
-        for t in (sem, sem_raw):
-            t.record_stream(main)
-        return {'image': image, 'image_raw': image_raw, 'image_depth': depth_image, 'semantic': sem, 'semantic_raw': sem_raw}
     image, image_raw = run_sr(gen.superresolution, 0, 3, styles[n_net:n_net + n_sr])
     out = {'image': image, 'image_raw': image_raw, 'image_depth': depth_image}
     if semantic:
