@@ -45,6 +45,10 @@ def conv2d(input, weight, bias=None, stride=1, padding=0, dilation=1, groups=1):
 
 
 def conv_transpose2d(input, weight, bias=None, stride=1, padding=0, output_padding=0, groups=1, dilation=1):
+    from . import native_conv
+    if native_conv.applies_transposed(input, weight, bias, _pair(stride), _pair(padding), _pair(output_padding), _pair(dilation), groups):
+        # fp32 up=2 layers of the generator's training passes: phase GEMMs forward, stride-2 convolution for the input gradient
+        return native_conv.conv_transpose2d(input, weight)
     if _use_custom(input):
         return _make_op(True, weight.shape, _pair(stride), _pair(padding), _pair(output_padding), _pair(dilation),
                         groups).apply(input, weight, bias)

@@ -103,3 +103,33 @@ def test_generator_training_gradients_use_the_native_node():
     worst = max(rel_err(ga[k].float().cpu().numpy(), gb[k].float().cpu().numpy()) for k in ga if gb[k].abs().max() > 0)
     assert worst < 2e-3, worst
 
+
+
+@pytest.mark.parametrize('b,cin,cout,h,w', [(4, 64, 64, 16, 16), (2, 256, 128, 32, 32), (1, 512, 512, 16, 16), (2, 96, 104, 17, 19)])
+def test_transposed_convolution_and_gradients_match_fp64(b, cin, cout, h, w):
+    """conv_transpose2d(stride 2, padding 0) of the up=2 layers (conv2d_resample.py:114-128): forward on the merged phase GEMMs,
+    input gradient on the stride-2 convolution, weight gradient on ATen."""
+    from pix2pix3d_b200 import _lib
+    from pix2pix3d_b200.torch_utils.ops import conv2d_gradfix, native_conv
+    dev = torch.device('cuda')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1)
+    x = torch.randn(b, cin, h, w, device=dev, requires_grad=True)
+    wt = (torch.randn(cin, cout, 3, 3, device=dev) / (cin * 9) ** 0.5).requires_grad_(True)
+    n0 = _lib.launch_count
+    with native_conv.first_order():
+        y = conv2d_gradfix.conv_transpose2d(x, wt, stride=2, padding=0)
+    assert _lib.launch_count - n0 >= 3, 'the native node was expected'
+    assert tuple(y.shape) == (b, cout, 2 * h + 1, 2 * w + 1)
+    gy = torch.randn_like(y) * 1e-6
+    dx, dw = torch.autograd.grad((y * gy).sum(), [x, wt])
+    xr, wr = x.detach().double().requires_grad_(True), wt.detach().double().requires_grad_(True)
+    yr = torch.nn.functional.conv_transpose2d(xr, wr, stride=2)
+    dxr, dwr = torch.autograd.grad((yr * gy.double()).sum(), [xr, wr])
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < 2e-5
+    assert rel_err(dx.cpu().numpy(), dxr.cpu().numpy()) < 2e-5
+    assert rel_err(dw.cpu().numpy(), dwr.cpu().numpy()) < 1e-4
+    # outside a first_order() region (the discriminators' R1 differentiates twice) the ATen node is used
+    n1 = _lib.launch_count
+    conv2d_gradfix.conv_transpose2d(x, wt, stride=2, padding=0)
+    assert _lib.launch_count == n1
