@@ -313,6 +313,21 @@ typedef struct {
     /* noise_mode='random' (networks_stylegan2.py:320-321): noise is [B, oH*oW], one image per sample; elements between
      * consecutive samples. 0 = the single [oH*oW] image of noise_mode='const' shared by the batch. */
     int64_t noise_batch_stride;
+    /* Fused 1x1 ToRGB of the NEXT layer (ABI 5; all zero = off): a launch whose single channel tile holds every output channel
+     * (Cout == Cout_padded <= 128, a multiple of 32; out_mode 0; 1:1 output map; persistent kernel) also evaluates, per pixel,
+     *   rgb[c] = round16(clamp(dot(x_out[:], rgb_w[b][c][:]) * rgb_acc_scale + rgb_bias[c]))       c < rgb_cout <= 8
+     * on the fp16-rounded outputs it has in registers, and writes rgb_out [B, rgb_cout, oH, oW] (fp32 NCHW) =
+     * upsample2d(rgb_prev [B, oH/2, oW/2, rgb_cout] fp32 NHWC, rgb_filter) + rgb -- SynthesisBlock.forward's ToRGB + skip
+     * (networks_stylegan2.py:452-458) of the last super-resolution block without re-reading its input. rgb_w: fp16
+     * [B][rgb_w_rows][Cout] (the modulated ToRGB weights). rgb_skip_x != 0: y itself is not written (nothing reads it).
+     * P3D_UNSUPPORTED when the launch shape does not qualify (callers then run the ToRGB convolution separately). */
+    const void* rgb_w;
+    const float* rgb_bias;
+    const float* rgb_prev;
+    const float* rgb_filter;
+    float* rgb_out;
+    int32_t rgb_cout, rgb_w_rows, rgb_skip_x;
+    float rgb_clamp, rgb_acc_scale;
 } p3d_conv_args_t;
 
 /* One implicit-GEMM convolution launch (tcgen05 + TMA): 3x3 / 1x1 convolutions and the four phases of a stride-2

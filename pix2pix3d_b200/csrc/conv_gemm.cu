@@ -64,6 +64,10 @@ struct ConvKernelArgs {
     const float* residual;            // fp32 [B, oH, oW, Cout]: added after the activation (resnet skip), or NULL
     int round16, out_nchw;            // round y to fp16 first (fp16 blocks); write [B, Cout, oH, oW] instead of NHWC
     float pre_gain, post_gain;        // gain folded into scale/bias/noise (lrelu is positively homogeneous) or applied last
+    // fused ToRGB of the next layer (persistent kernel only; p3d_conv_args_t::rgb_*)
+    const __half* rgb_w; const float* rgb_bias; const float* rgb_prev; const float* rgb_f; float* rgb_out;
+    int rgb_cout, rgb_w_rows, rgb_skip_x;
+    float rgb_clamp, rgb_acc_scale;
 };
 
 // phase that owns tile `t` of the launch's tile order (phases are consecutive ranges starting at ph[q].t0)
@@ -103,7 +107,7 @@ __device__ __forceinline__ float conv_epilogue_act(float x, float alpha, float p
 template <int kAct, bool kClamp>
 __device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32_t (&v)[32], const float* s_scale,
                                                  const float* s_bias, int c0, int ch0, size_t off, float nz, bool vec_ok,
-                                                 int b, int Y, int X) {
+                                                 int b, int Y, int X, float* xq = nullptr, bool do_store = true) {
     const float alpha = a.alpha, post_gain = a.post_gain, clampv = a.clamp;
     const int out_mode = a.out_mode;
     if (a.up_prev) {
@@ -219,13 +223,17 @@ __device__ __forceinline__ void conv_store_chunk(const ConvKernelArgs& a, uint32
                             for (int t = 0; t < 8; ++t) {
                                 const __half2 hv = __floats2half2_rn(r[2 * t], r[2 * t + 1]);
                                 oh[t] = *reinterpret_cast<const uint32_t*>(&hv);
+                                if (xq) {           // the fp16-rounded outputs, for the fused ToRGB of the next layer
+                                    const float2 back = __half22float2(hv);
+                                    xq[16 * j + 2 * t] = back.x; xq[16 * j + 2 * t + 1] = back.y;
+                                }
                                 if (out_mode == 1) {
                                     const float2 back = __half22float2(hv);
                                     const __half2 lv = __floats2half2_rn(r[2 * t] - back.x, r[2 * t + 1] - back.y);
                                     ol[t] = *reinterpret_cast<const uint32_t*>(&lv);
                                 }
                             }
-                            st_global_256(reinterpret_cast<__half*>(a.y) + off + 16 * j, oh);
+                            if (do_store) st_global_256(reinterpret_cast<__half*>(a.y) + off + 16 * j, oh);
                             if (out_mode == 1) st_global_256(reinterpret_cast<__half*>(a.y_lo) + off + 16 * j, ol);
                         }
                     }
@@ -414,6 +422,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* s_const = reinterpret_cast<float*>(smem + kPStages * stage_bytes + 128);     // [2 parities][scale 128 | bias 128]
+    float* s_rgbw = s_const + 512;                                                      // [2 parities][8][128] (fused ToRGB only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -510,6 +519,15 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
                 s_scale[et] = sc;
                 s_bias[et] = bi;
             }
+            float* s_rw = s_rgbw + parity * 1024;
+            if (a.rgb_w) {
+                // modulated ToRGB weights of this tile's sample as fp32 [8][128] (rows beyond rgb_cout are zero)
+                for (int i = et; i < 8 * 128; i += 256) {
+                    const int c = i >> 7, k = i & 127;
+                    s_rw[i] = (c < a.rgb_cout && k < a.Cout)
+                                  ? __half2float(__ldg(a.rgb_w + ((size_t)b * a.rgb_w_rows + c) * a.Cout + k)) : 0.f;
+                }
+            }
             tc::named_bar_sync(1, 256);                 // constants of this tile visible to all epilogue warps
             const int gy = (ty * 2 + mt) * a.BH + m / a.BW, gx = tx * a.BW + m % a.BW;
             const bool pix_ok = (gy < P.gH) && (gx < P.gW);
@@ -522,17 +540,71 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_persist_kernel(const __grid_
             tc::mbar_wait(&tmem_full_bar[as], aphase);
             tc::tc_fence_after();
             const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + mt * 128);
+            float dot[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dot[c] = 0.f;
             for (int c0 = 0; c0 < a.BN; c0 += 32) {
                 uint32_t v[32];
                 tc::tmem_ld_32x32(acc + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
                 const int ch0 = n0 + c0;
                 if (!pix_ok || ch0 >= a.Cout) continue;
-                conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok, b, Y, X);
+                if (a.rgb_w) {
+                    // fused ToRGB of the next layer: dot products of this pixel's fp16-rounded outputs with the 1x1 weights
+                    float xq[32];
+                    conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok, b, Y, X,
+                                                   xq, a.rgb_skip_x == 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c < a.rgb_cout) {
+                            const float4* wr = reinterpret_cast<const float4*>(s_rw + c * 128 + c0);
+                            float acc_c = dot[c];
+#pragma unroll
+                            for (int qd = 0; qd < 8; ++qd) {
+                                const float4 w4 = wr[qd];
+                                acc_c = fmaf(xq[4 * qd], w4.x, acc_c); acc_c = fmaf(xq[4 * qd + 1], w4.y, acc_c);
+                                acc_c = fmaf(xq[4 * qd + 2], w4.z, acc_c); acc_c = fmaf(xq[4 * qd + 3], w4.w, acc_c);
+                            }
+                            dot[c] = acc_c;
+                        }
+                    }
+                } else {
+                    conv_store_chunk<kAct, kClamp>(a, v, s_scale, s_bias, c0, ch0, pix * a.y_cstride + a.y_coff + ch0, nz, vec_ok, b, Y, X);
+                }
             }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[as]);      // 8 warps -> accumulator pair free for the MMA warp
+            if (a.rgb_w && pix_ok) {
+                // out = upsample2d(prev)[b, Y, X, :] + round16(clamp(dot * scale + bias)), written NCHW (lanes = consecutive X)
+                const int ph = a.oH >> 1, pw = a.oW >> 1, C = a.rgb_cout;
+                const int iy = Y >> 1, py = Y & 1, ix = X >> 1, px = X & 1;
+                float w4[2][2];
+                const float* pp[2][2];
+#pragma unroll
+                for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int ry = iy - 1 + py + aa, rx = ix - 1 + px + cc;
+                        const bool ok = ry >= 0 && ry < ph && rx >= 0 && rx < pw;
+                        w4[aa][cc] = ok ? __ldg(a.rgb_f + (3 - (py + 2 * aa)) * 4 + (3 - (px + 2 * cc))) * 4.f : 0.f;
+                        pp[aa][cc] = a.rgb_prev + (((size_t)b * ph + (ok ? ry : 0)) * pw + (ok ? rx : 0)) * C;
+                    }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c < C) {
+                        float u = 0.f;
+#pragma unroll
+                        for (int aa = 0; aa < 2; ++aa)
+#pragma unroll
+                            for (int cc = 0; cc < 2; ++cc) u = fmaf(w4[aa][cc], __ldg(pp[aa][cc] + c), u);
+                        float x = fmaf(dot[c], a.rgb_acc_scale, a.rgb_bias ? __ldg(a.rgb_bias + c) : 0.f);
+                        if (a.rgb_clamp >= 0.f) x = fminf(fmaxf(x, -a.rgb_clamp), a.rgb_clamp);
+                        x = __half2float(__float2half_rn(x));
+                        a.rgb_out[(((size_t)b * C + c) * a.oH + Y) * a.oW + X] = u + x;
+                    }
+                }
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
             parity ^= 1;
         }
@@ -792,7 +864,7 @@ static int conv_launch(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t
                       r->y_coff != p->y_coff || r->out_mode != p->out_mode || r->bias != p->bias || r->noise != p->noise ||
                       r->dscale != p->dscale || r->act != p->act || r->alpha != p->alpha || r->gain != p->gain || r->clamp != p->clamp ||
                       r->acc_scale != p->acc_scale || r->up_prev || p->up_prev || r->residual || p->residual || r->stride != p->stride ||
-                      r->noise_batch_stride != p->noise_batch_stride))
+                      r->noise_batch_stride != p->noise_batch_stride || r->rgb_w || p->rgb_w))
             return P3D_BAD_ARG;
         taps_total += r->n_taps;
         if (r->n_taps > taps_max) taps_max = r->n_taps;
@@ -902,6 +974,20 @@ static int conv_launch(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t
     a.base_aligned = ((((uintptr_t)p->y) | ((uintptr_t)p->y_lo)) & 31) == 0;
     a.up_prev = p->up_prev; a.up_f = p->up_filter; a.round16 = p->round16; a.out_nchw = p->out_nchw;
     a.stride = stride; a.residual = p->residual;
+    if (p->rgb_w) {
+        // fused ToRGB of the next layer: one channel tile holding every output channel, fp16 output, 1:1 output map, persistent
+        // single-CTA kernel (its epilogue thread sees all channels of its pixel)
+        if (n_phases != 1 || !persist || pair || p->up_prev || p->residual || p->out_mode != 0 || p->Cout != p->Cout_padded ||
+            p->Cout > 128 || p->Cout % 32 != 0 || p->sy != 1 || p->sx != 1 || p->oy != 0 || p->ox != 0 || p->gH != p->oH ||
+            p->gW != p->oW || (p->oH & 1) || (p->oW & 1) || stride != 1 || p->y_coff != 0 || p->y_cstride != p->Cout)
+            return P3D_UNSUPPORTED;
+        if (!p->rgb_prev || !p->rgb_filter || !p->rgb_out || p->rgb_cout < 1 || p->rgb_cout > 8 || p->rgb_w_rows < p->rgb_cout ||
+            !a.base_aligned)
+            return P3D_BAD_ARG;
+        a.rgb_w = reinterpret_cast<const __half*>(p->rgb_w); a.rgb_bias = p->rgb_bias; a.rgb_prev = p->rgb_prev; a.rgb_f = p->rgb_filter;
+        a.rgb_out = p->rgb_out; a.rgb_cout = p->rgb_cout; a.rgb_w_rows = p->rgb_w_rows; a.rgb_skip_x = p->rgb_skip_x;
+        a.rgb_clamp = p->rgb_clamp; a.rgb_acc_scale = p->rgb_acc_scale;
+    }
     if (p->residual && (p->up_prev || p->out_mode > 2 || p->sy != 1 || p->sx != 1 || p->oy != 0 || p->ox != 0 ||
                         (((uintptr_t)p->residual) & 31) != 0))
         return P3D_BAD_ARG;
@@ -963,7 +1049,7 @@ static int conv_launch(const p3d_conv_args_t* phases, int n_phases, p3d_stream_t
         a.splits = 1; a.partial = nullptr; a.Cout_pad = p->Cout_padded;
         const int n_tiles = (int)base_ctas;
         const size_t stage_bytes_p = 2 * (size_t)kBM * 128 + (size_t)BN * 128;
-        const size_t smem_p = kPStages * stage_bytes_p + 128 + 2 * 256 * sizeof(float) + 1024;
+        const size_t smem_p = kPStages * stage_bytes_p + 128 + 2 * 256 * sizeof(float) + 2 * 1024 * sizeof(float) + 1024;
         const int ctas = n_tiles < sm_count() ? n_tiles : sm_count();
 #define P3D_LAUNCH_PERSIST(ACT, CL)                                                                                           \
     do {                                                                                                                      \

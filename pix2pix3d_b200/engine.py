@@ -269,8 +269,16 @@ def _alloc(planes, b, h, w, c, cp, device):
     return torch.zeros(shape, device=device, dtype=torch.float16) if cp != c else torch.empty(shape, device=device, dtype=torch.float16)
 
 
-def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0):
-    """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]; styles = layer.affine(w)."""
+# A/B switch (same results to fp16 rounding): P3D_FUSE_RGB=0 keeps the last block's ToRGB a separate launch
+FUSE_RGB = os.environ.get('P3D_FUSE_RGB') != '0'
+
+
+def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0, rgb_tail=None):
+    """SynthesisLayer.forward (networks_stylegan2.py:313-332) on NHWC tensors. x: [planes,B,h,w,Cp]; styles = layer.affine(w).
+
+    rgb_tail = dict(torgb=ToRGBLayer, styles=ReadyWeights, prev=[B,h/2,w/2,Ci] fp32 skip image, filter=f): also evaluate the
+    block's ToRGB + skip (:452-458) in this layer's epilogue and return (None, image [B,Ci,h,w]) -- the last super-resolution
+    block, whose x nobody reads; returns None when the launch shape does not qualify (the caller then runs the two layers)."""
     planes = 2 if split else 1
     cin_p = x.shape[-1]
     cout = layer.out_channels
@@ -289,6 +297,19 @@ def synthesis_layer(layer, x, styles, noise_mode, split, gain=1.0, cin_offset=0)
     dev = x.device
     if layer.up == 1:
         h, w = x.shape[2], x.shape[3]
+        if rgb_tail is not None:
+            torgb, st = rgb_tail['torgb'], rgb_tail['styles']
+            ci = torgb.out_channels
+            if (split or cout_p != cout or not isinstance(st, ReadyWeights) or st.wk.shape[0] != 1 or st.wk.shape[-1] != cout
+                    or ci > 8 or rgb_tail['prev'].shape[-1] != ci):
+                return None
+            y = torch.empty(1, b, h, w, cout, device=dev, dtype=torch.float16)       # never written (rgb_skip_x); the ABI wants a buffer
+            image = torch.empty(b, ci, h, w, device=dev, dtype=torch.float32)
+            rgb = dict(w=st.wk[0], bias=_bias(torgb, ci), prev=rgb_tail['prev'].contiguous(), filter=rgb_tail['filter'], out=image,
+                       clamp=float(torgb.conv_clamp) if torgb.conv_clamp is not None else -1.0, skip_x=True)
+            ok = tcconv.conv_gemm_try(x, wk, cout, tcconv.TAPS_3X3, (h, w), y[0], out_mode=0, split=False, bias=bias, noise=noise, act=3,
+                                      alpha=0.2, gain=act_gain, clamp=clamp, rgb=rgb)
+            return (None, image) if ok else None
         y = _alloc(planes, b, h, w, cout, cout_p, dev)
         tcconv.conv_gemm(x, wk, cout, tcconv.TAPS_3X3, (h, w), y[0], out_lo=(y[1] if split else None), out_mode=1 if split else 0,
                          split=split, bias=bias, noise=noise, act=3, alpha=0.2, gain=act_gain, clamp=clamp)
@@ -373,7 +394,17 @@ def synthesis_block(block, x, img, styles, noise_mode='const', force_fp32=False,
         if x.shape[0] != planes:   # precision change between blocks
             x = x[:1].contiguous() if planes == 1 else torch.stack([x[0], torch.zeros_like(x[0])])
         x = synthesis_layer(block.conv0, x, next(s_iter), noise_mode, split, cin_offset=cin_offset)
-        x = synthesis_layer(block.conv1, x, next(s_iter), noise_mode, split)
+        st1 = next(s_iter)
+        if final_nchw and FUSE_RGB and upsample and img is not None and not split:
+            # last block: ToRGB + skip in conv1's epilogue (its output x is read by nothing else)
+            st_rgb = next(s_iter)
+            fused = synthesis_layer(block.conv1, x, st1, noise_mode, split,
+                                    rgb_tail=dict(torgb=block.torgb, styles=st_rgb, prev=img, filter=block.resample_filter))
+            if fused is not None:
+                return fused
+            x = synthesis_layer(block.conv1, x, st1, noise_mode, split)
+            return x, torgb_layer(block.torgb, x, st_rgb, img, split, upsample_filter=block.resample_filter, final_nchw=True)
+        x = synthesis_layer(block.conv1, x, st1, noise_mode, split)
     if upsample and img is not None:
         img = torgb_layer(block.torgb, x, next(s_iter), img, split, upsample_filter=block.resample_filter, final_nchw=final_nchw)
     else:

@@ -32,6 +32,9 @@ class ConvArgs(ctypes.Structure):  # p3d_conv_args_t
         ('up_prev', ctypes.c_void_p), ('up_filter', ctypes.c_void_p), ('round16', ctypes.c_int32), ('out_nchw', ctypes.c_int32),
         ('stride', ctypes.c_int32), ('launch_flags', ctypes.c_int32), ('residual', ctypes.c_void_p),
         ('splitk_scratch', ctypes.c_void_p), ('splitk_scratch_bytes', ctypes.c_int64), ('noise_batch_stride', ctypes.c_int64),
+        ('rgb_w', ctypes.c_void_p), ('rgb_bias', ctypes.c_void_p), ('rgb_prev', ctypes.c_void_p), ('rgb_filter', ctypes.c_void_p),
+        ('rgb_out', ctypes.c_void_p), ('rgb_cout', ctypes.c_int32), ('rgb_w_rows', ctypes.c_int32), ('rgb_skip_x', ctypes.c_int32),
+        ('rgb_clamp', ctypes.c_float), ('rgb_acc_scale', ctypes.c_float),
     ]
 
 
@@ -161,7 +164,7 @@ def _splitk_scratch(device):
 
 def _conv_args(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=(1, 0, 1, 0), y_coff=0, split=False, bias=None,
                noise=None, dscale=None, act=1, alpha=0.2, gain=1.0, clamp=-1.0, acc_scale=1.0 / WEIGHT_SCALE, split_k=True,
-               up_prev=None, up_filter=None, round16=False, out_nchw=False, stride=1, residual=None):
+               up_prev=None, up_filter=None, round16=False, out_nchw=False, stride=1, residual=None, rgb=None):
     """The p3d_conv_args_t of one convolution launch (see conv_gemm)."""
     xp, b, h, wd, c = x.shape
     wp, bw, op, kk = w.shape
@@ -209,6 +212,15 @@ def _conv_args(x, w, cout, taps, grid_hw, out, out_lo=None, out_mode=0, out_map=
     if split_k:
         scratch = _splitk_scratch(x.device)
         a.splitk_scratch, a.splitk_scratch_bytes = scratch.data_ptr(), scratch.numel() * 4
+    if rgb is not None:          # fused ToRGB of the next layer (p3d_conv_args_t::rgb_*)
+        rw, rprev, rout = rgb['w'], rgb['prev'], rgb['out']
+        assert rw.dtype == torch.float16 and rw.is_contiguous() and rw.ndim == 3 and rw.shape[0] == b and rw.shape[2] == cout
+        assert rprev.dtype == torch.float32 and rprev.is_contiguous() and rout.dtype == torch.float32 and rout.is_contiguous()
+        a.rgb_w, a.rgb_prev, a.rgb_out = rw.data_ptr(), rprev.data_ptr(), rout.data_ptr()
+        a.rgb_bias = None if rgb.get('bias') is None else rgb['bias'].data_ptr()
+        a.rgb_filter = rgb['filter'].contiguous().data_ptr()
+        a.rgb_cout, a.rgb_w_rows, a.rgb_skip_x = rout.shape[1], rw.shape[1], int(bool(rgb.get('skip_x', False)))
+        a.rgb_clamp, a.rgb_acc_scale = float(rgb.get('clamp', -1.0)), float(rgb.get('acc_scale', 1.0 / WEIGHT_SCALE))
     return a
 
 
@@ -237,6 +249,28 @@ def conv_gemm(x, w, cout, taps, grid_hw, out, split=False, **kw):
     flops = 2.0 * x.shape[1] * grid_hw[0] * grid_hw[1] * cout * len(taps) * x.shape[4]
     _launch(x.device, lambda: _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr()), 'p3d_conv_gemm', flops, split)
     return out
+
+
+def conv_gemm_try(x, w, cout, taps, grid_hw, out, split=False, **kw):
+    """conv_gemm that reports P3D_UNSUPPORTED (-1) as False instead of raising: for optional fusions (`rgb=`) whose launch shape
+    the library decides on; the caller then takes the unfused sequence."""
+    from . import native
+    a = _conv_args(x, w, cout, taps, grid_hw, out, split=split, **kw)
+    ev = None
+    if native.kernel_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    with torch.cuda.device(x.device):
+        st = _lib.lib().p3d_conv_gemm(ctypes.byref(a), _lib.stream_ptr())
+    if st == -1:
+        return False
+    if ev is not None:
+        ev[1].record()
+        flops = 2.0 * x.shape[1] * grid_hw[0] * grid_hw[1] * cout * (len(taps) * x.shape[4] + (a.rgb_cout if a.rgb_w else 0))
+        native.kernel_events.append(('conv_gemm', ev[0], ev[1], flops, flops * (3 if split else 1)))
+    _lib.check(st, 'p3d_conv_gemm')
+    _lib.bump()
+    return True
 
 
 TAPS_3X3 = [(ky - 1, kx - 1, ky * 3 + kx) for ky in range(3) for kx in range(3)]

@@ -393,3 +393,61 @@ def test_conv_gemm_phases_rejects_mismatched_phases():
     arr[1] = tcconv._conv_args(x, wk, 16, tcconv.tconv_phase_taps(0, 1), (5, 4), other, out_map=(2, 0, 2, 1))
     assert _lib.lib().p3d_conv_gemm_phases(arr, 2, _lib.stream_ptr()) == -2
     assert _lib.lib().p3d_conv_gemm_phases(arr, 5, _lib.stream_ptr()) == -2
+
+
+@pytest.mark.parametrize('cout,ci,hw,b', [(128, 3, (256, 256), 2), (128, 6, (192, 256), 2), (64, 3, (256, 256), 3)])
+def test_torgb_fused_into_the_producing_convolution(cout, ci, hw, b):
+    """p3d_conv_args_t::rgb_*: the 3x3 convolution of the last super-resolution block also evaluates the block's ToRGB + skip
+    (networks_stylegan2.py:452-458) on the outputs it holds -- against the two separate launches it replaces."""
+    from pix2pix3d_b200 import tcconv
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    torch.manual_seed(31)
+    c = 128
+    h, w = hw
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    x = torch.randn(b, c, h, w, device='cuda')
+    w3 = torch.randn(cout, c, 3, 3, device='cuda') / np.sqrt(9 * c)
+    wrgb = torch.randn(ci, cout, 1, 1, device='cuda') / np.sqrt(cout)
+    styles = torch.randn(b, cout, device='cuda') + 1
+    bias3, brgb = torch.randn(cout, device='cuda') * 0.1, torch.randn(ci, device='cuda')
+    prev = torch.randn(b, h // 2, w // 2, ci, device='cuda')
+    xn = tcconv.to_nhwc_f16(x)
+    wk = _weights_kmajor(w3, scale=tcconv.WEIGHT_SCALE)
+    wk_rgb = tcconv.modulate_weights(wrgb, styles, demodulate=False, pre_scale=0.7)       # [1,B,16,cout]: per-sample ToRGB weights
+    # separate launches: conv -> fp16 x, then the fused-tail ToRGB convolution on it
+    y = torch.empty(1, b, h, w, cout, device='cuda', dtype=torch.float16)
+    tcconv.conv_gemm(xn, wk, cout, tcconv.TAPS_3X3, (h, w), y[0], out_mode=0, bias=bias3, act=3, alpha=0.2, gain=float(np.sqrt(2)), clamp=256.0)
+    ref = torch.empty(b, ci, h, w, device='cuda')
+    tcconv.conv_gemm(y, wk_rgb, ci, tcconv.TAPS_1X1, (h, w), ref, out_mode=2, bias=brgb, act=1, gain=1.0, clamp=256.0, up_prev=prev,
+                     up_filter=f, round16=True, out_nchw=True)
+    for skip_x in (False, True):
+        y2 = torch.full_like(y, float('nan'))
+        out = torch.full((b, ci, h, w), float('nan'), device='cuda')
+        ok = tcconv.conv_gemm_try(xn, wk, cout, tcconv.TAPS_3X3, (h, w), y2[0], out_mode=0, bias=bias3, act=3, alpha=0.2,
+                                  gain=float(np.sqrt(2)), clamp=256.0,
+                                  rgb=dict(w=wk_rgb[0], bias=brgb, prev=prev, filter=f, out=out, clamp=256.0, skip_x=skip_x))
+        assert ok, 'this launch shape qualifies for the fused ToRGB'
+        assert torch.isfinite(out).all()
+        # same fp16 inputs and weights, fp32 dot products summed in another order, then one fp16 rounding: a rare 1-ulp flip
+        assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < 2e-3
+        assert (out - ref).abs().mean().item() < 1e-4 * ref.abs().mean().item()
+        if skip_x:
+            assert torch.isnan(y2).all(), 'rgb_skip_x: the convolution output itself must not be written'
+        else:
+            assert torch.equal(y2, y)
+
+
+def test_torgb_fusion_is_refused_for_other_launch_shapes():
+    from pix2pix3d_b200 import tcconv
+    from pix2pix3d_b200.torch_utils.ops import upfirdn2d
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda()
+    b, c, cout, ci, h = 1, 64, 64, 3, 16            # 1 tile: not the persistent kernel
+    xn = tcconv.to_nhwc_f16(torch.randn(b, c, h, h, device='cuda'))
+    wk = _weights_kmajor(torch.randn(cout, c, 3, 3, device='cuda'))
+    wk_rgb = _weights_kmajor(torch.randn(ci, cout, 1, 1, device='cuda'))
+    y = torch.empty(b, h, h, cout, device='cuda', dtype=torch.float16)
+    out = torch.empty(b, ci, h, h, device='cuda')
+    prev = torch.zeros(b, h // 2, h // 2, ci, device='cuda')
+    ok = tcconv.conv_gemm_try(xn, wk, cout, tcconv.TAPS_3X3, (h, h), y, out_mode=0,
+                              rgb=dict(w=wk_rgb[0].expand(b, -1, -1).contiguous(), prev=prev, filter=f, out=out))
+    assert ok is False
