@@ -13,6 +13,7 @@ draws one noise image per sample and layer with the reference's own `torch.randn
 keeps the generic op-by-op formulation.
 """
 import logging
+import os
 import weakref
 
 import numpy as np
