@@ -415,3 +415,52 @@ def test_plane_index_shares_one_plane_set_between_views(impl):
                               plane_index=torch.tensor([1, 0], dtype=torch.int32))
     swap = native.render_fwd(native.planes_to_channels_last(planes[[1, 0]].contiguous()), dec, o, d, dc, u, opts['box_warp'], impl=impl)
     assert torch.equal(mixed[0], swap[0])
+
+
+@pytest.mark.parametrize('kind', ['osg', 'semantic_raw', 'semantic_sigmoid', 'entangle_6', 'entangle_19', 'entangle_sigmoid', 'late_19'])
+@pytest.mark.parametrize('impl', ['tc', 'simt'])
+def test_fused_renderer_decoder_kinds_match_the_staged_modules(kind, impl, monkeypatch):
+    """Every decoder layout native.describe_decoder maps onto the fused kernels (one or two nets, per-channel sigmoid masks:
+    triplane.py:112-135, triplane_cond.py:859-970) against ImportanceRenderer's staged path, which evaluates the decoder MODULE
+    (mirror of the reference's forward) between the stage kernels, on the same rays and the same random draws."""
+    from pix2pix3d_b200 import native
+    from pix2pix3d_b200.training import triplane, triplane_cond as tc
+    from pix2pix3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    dev = torch.device('cuda')
+    base = {'decoder_lr_mul': 1.0, 'decoder_output_dim': 32}
+    make = {
+        'osg': lambda: triplane.OSGDecoder(32, dict(base)),
+        'semantic_raw': lambda: tc.OSGDecoder_semantic(32, dict(base, sigmoid=False)),
+        'semantic_sigmoid': lambda: tc.OSGDecoder_semantic(32, dict(base, sigmoid=True)),
+        'entangle_6': lambda: tc.OSGDecoder_semantic_entangle(32, dict(base, sigmoid=False, semantic_channels=6)),
+        'entangle_19': lambda: tc.OSGDecoder_semantic_entangle(32, dict(base, sigmoid=False, semantic_channels=19)),
+        'entangle_sigmoid': lambda: tc.OSGDecoder_semantic_entangle(32, dict(base, sigmoid=True, semantic_channels=1)),
+        'late_19': lambda: tc.OSGDecoder_semantic_lateSeparate(32, dict(base, sigmoid=False, semantic_channels=19)),
+    }[kind]
+    torch.manual_seed(17)
+    dec = make().to(dev).requires_grad_(False)
+    for p in dec.parameters():
+        p.normal_(0, 0.6)
+    B, H, nrr, Sc, Sf = 2, 48, 16, 16, 16
+    planes = torch.randn(B, 3, 32, H, H, device=dev)
+    g = load_golden('renderer_seg')
+    c2w = torch.from_numpy(g['cam2world'][:1]).to(dev).repeat(B, 1, 1)
+    K = torch.from_numpy(g['intrinsics'][:1]).to(dev).repeat(B, 1, 1)
+    o, d = native.ray_sampler(c2w, K, nrr)
+    opts = dict(depth_resolution=Sc, depth_resolution_importance=Sf, ray_start=2.25, ray_end=3.3, box_warp=1.0,
+                disparity_space_sampling=False, clamp_mode='softplus', white_back=False)
+    monkeypatch.setattr(native, 'render_impl', impl)
+    outs = []
+    for fused in (True, False):
+        r = ImportanceRenderer().to(dev)
+        torch.manual_seed(99)                       # same torch.rand stream: jitter, then u
+        if fused:
+            with torch.no_grad():
+                outs.append(r(planes, dec, o, d, opts))
+        else:
+            # gradients required -> the staged path; decoder kernels off -> the decoder MODULE's torch forward between the stages
+            monkeypatch.setattr(native, 'decoder_mlp_supported', lambda *a, **k: False)
+            outs.append(tuple(t.detach() for t in r(planes.clone().requires_grad_(True), dec, o, d, opts)))
+    for a, b_, name in zip(outs[0], outs[1], ('features', 'depth', 'weights')):
+        assert a.shape == b_.shape, name
+        assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) < 1e-3, (kind, name)
