@@ -464,7 +464,11 @@ __device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
 // instructions per output element in the 16-tap form), so the instruction count is what sets its speed.
 struct FirSepTaps { float fx[4], fy[4]; };        // already mirrored (true convolution) and with the gain folded into fx
 
-template <class TIn>
+// kSplitOut: hi/lo output planes; kNoise: a noise image is added. Compile-time so that each instance carries ONE epilogue: the
+// all-in-one kernel was 2 900 SASS instructions and stalled on instruction fetch (ncu: `no_instruction` 1.1 per issue).
+// kFast: leaky ReLU with 0 <= alpha <= 1 (max form) and a clamp that is absent or (single fp16 plane) an fp16 number -- the
+// configuration of every synthesis layer; anything else takes the instance with the run-time branches.
+template <class TIn, bool kSplitOut, bool kNoise, bool kFast>
 __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_constant__ CUtensorMap tmX, const FirSepTaps taps,
                                                                const float* __restrict__ noise, const float* __restrict__ bias,
                                                                __half* __restrict__ y, int out_planes, size_t out_plane_stride,
@@ -505,7 +509,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int py = ty0 + by + i, px = tx0 + bx + j;
-            nzv[i][j] = (noise && py < outH && px < outW) ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
+            nzv[i][j] = (kNoise && py < outH && px < outW) ? __ldg(noise + (size_t)b * noise_bstride + (size_t)py * outW + px) : 0.f;
         }
     __syncthreads();                                 // barrier init visible to the waiters
     tc::mbar_wait(&bar, 0);
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_cons
                     float2 t = f2_unpack(x2);
                     t = __half22float2(__floats2half2_rn(t.x, t.y));
                     x2 = f2_add(f2_pack(t.x, t.y), nz2);
-                    if (noise) {
+                    if (kNoise) {
                         t = f2_unpack(x2);
                         t = __half22float2(__floats2half2_rn(t.x, t.y));
                         x2 = f2_pack(t.x, t.y);
@@ -578,14 +582,17 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_cons
                 }
                 x2 = f2_add(x2, bv2[k]);
                 float2 x = f2_unpack(x2);
-                if (act == 3) {
+                if (kFast || act == 3) {
                     const float2 m = f2_unpack(f2_mul(x2, alpha2));
-                    if (fast_lrelu) { x.x = fmaxf(x.x, m.x); x.y = fmaxf(x.y, m.y); }
+                    if (kFast || fast_lrelu) { x.x = fmaxf(x.x, m.x); x.y = fmaxf(x.y, m.y); }
                     else { x.x = x.x > 0.f ? x.x : m.x; x.y = x.y > 0.f ? x.y : m.y; }
                 }
                 x = f2_unpack(f2_mul(f2_pack(x.x, x.y), gain2));
                 __half2 hh;
-                if (clamp_h_ok && out_planes == 1) {
+                if (kFast && !kSplitOut) {
+                    hh = __floats2half2_rn(x.x, x.y);
+                    if (clamp >= 0.f) hh = __hmin2(__hmax2(hh, clamp_lo), clamp_hi);
+                } else if (clamp_h_ok && !kSplitOut) {
                     // round, then clamp on the packed halves: same result as clamp-then-round (the bound is an fp16 number)
                     hh = __hmin2(__hmax2(__floats2half2_rn(x.x, x.y), clamp_lo), clamp_hi);
                 } else {
@@ -593,13 +600,13 @@ __global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_cons
                     hh = __floats2half2_rn(x.x, x.y);
                 }
                 hv[k] = hh;
-                if (out_planes == 2) {
+                if (kSplitOut) {
                     const float2 back = __half22float2(hh);
                     lv[k] = __floats2half2_rn(x.x - back.x, x.y - back.y);
                 }
             }
             *reinterpret_cast<uint2*>(y + o) = *reinterpret_cast<const uint2*>(hv);
-            if (out_planes == 2) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
+            if (kSplitOut) *reinterpret_cast<uint2*>(y + out_plane_stride + o) = *reinterpret_cast<const uint2*>(lv);
         }
     }
 }
@@ -925,14 +932,24 @@ extern "C" int p3d_fir_act_nhwc_sep(const void* x, int in_dtype, const float fx[
     for (int k = 0; k < 4; ++k) { taps.fx[k] = fx[3 - k] * fir_gain; taps.fy[k] = fy[3 - k]; }
     dim3 grid(tiles, C / cb, B);
     const size_t tile_bytes = (size_t)kFirIH * kFirIW * 128;
-    if (in_dtype == P3D_F32)
-        fir_act_nhwc_sep_kernel<float><<<grid, 128, tile_bytes, (cudaStream_t)stream>>>(tm, taps, noise, bias, (__half*)y, out_planes, ps, outH,
-                                                                                         outW, C, padx0, pady0, act, alpha, act_gain, clamp, B,
-                                                                                         noise_batch_stride);
-    else
-        fir_act_nhwc_sep_kernel<__half><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(tm, taps, noise, bias, (__half*)y, out_planes, ps, outH,
-                                                                                          outW, C, padx0, pady0, act, alpha, act_gain, clamp, B,
-                                                                                          noise_batch_stride);
+#define P3D_FIR_SEP3(T, THREADS, SO, NZ, FA)                                                                                                 \
+    fir_act_nhwc_sep_kernel<T, SO, NZ, FA><<<grid, THREADS, tile_bytes, (cudaStream_t)stream>>>(tm, taps, noise, bias, (__half*)y, out_planes,  \
+                                                                                                  ps, outH, outW, C, padx0, pady0, act, alpha,    \
+                                                                                                  act_gain, clamp, B, noise_batch_stride)
+#define P3D_FIR_SEP(T, THREADS, SO, NZ) do { if (fast) P3D_FIR_SEP3(T, THREADS, SO, NZ, true); else P3D_FIR_SEP3(T, THREADS, SO, NZ, false); } while (0)
+    const bool so = out_planes == 2, nz = noise != nullptr;
+    // fast instance: lrelu in its max form, clamp absent or exactly representable in fp16 (when a single fp16 plane is written)
+    const __half clamp_h = __float2half_rn(clamp);
+    const bool fast = act == 3 && alpha >= 0.f && alpha <= 1.f && (clamp < 0.f || so || __half2float(clamp_h) == clamp);
+    if (in_dtype == P3D_F32) {
+        if (so) { if (nz) P3D_FIR_SEP(float, 128, true, true); else P3D_FIR_SEP(float, 128, true, false); }
+        else { if (nz) P3D_FIR_SEP(float, 128, false, true); else P3D_FIR_SEP(float, 128, false, false); }
+    } else {
+        if (so) { if (nz) P3D_FIR_SEP(__half, 256, true, true); else P3D_FIR_SEP(__half, 256, true, false); }
+        else { if (nz) P3D_FIR_SEP(__half, 256, false, true); else P3D_FIR_SEP(__half, 256, false, false); }
+    }
+#undef P3D_FIR_SEP
+#undef P3D_FIR_SEP3
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
