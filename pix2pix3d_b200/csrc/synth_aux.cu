@@ -469,7 +469,7 @@ struct FirSepTaps { float fx[4], fy[4]; };        // already mirrored (true conv
 // kFast: leaky ReLU with 0 <= alpha <= 1 (max form) and a clamp that is absent or (single fp16 plane) an fp16 number -- the
 // configuration of every synthesis layer; anything else takes the instance with the run-time branches.
 template <class TIn, bool kSplitOut, bool kNoise, bool kFast>
-__global__ void __launch_bounds__(256, 4) fir_act_nhwc_sep_kernel(const __grid_constant__ CUtensorMap tmX, const FirSepTaps taps,
+__global__ void __launch_bounds__(256) fir_act_nhwc_sep_kernel(const __grid_constant__ CUtensorMap tmX, const FirSepTaps taps,
                                                                const float* __restrict__ noise, const float* __restrict__ bias,
                                                                __half* __restrict__ y, int out_planes, size_t out_plane_stride,
                                                                int outH, int outW, int C, int padx0, int pady0, int act, float alpha,
