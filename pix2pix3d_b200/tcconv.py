@@ -312,16 +312,13 @@ def conv_transpose3x3_s2(x, w, cout, out, split=False, acc_scale=1.0 / WEIGHT_SC
 # 3: separable filters (setup_filter builds them) take p3d_fir_act_nhwc_sep; 1: always the 16-tap kernel (A/B runs). Read once here.
 FIR_VARIANT = int(os.environ.get('P3D_FIR_VARIANT', '3'))
 
-_SEP_CACHE = {}
-
-
 def separable_factors(f):
     """(fx, fy) as ctypes float[4] arrays with f[j][i] == fy[j] * fx[i] exactly (in fp32), or None. Looked up once per filter
-    buffer (a device -> host copy), so it must first happen outside CUDA-graph capture; upfirdn2d.setup_filter([1,3,3,1]) qualifies."""
-    key = (f.data_ptr(), f._version, f.device)
-    hit = _SEP_CACHE.get(key)
-    if hit is None:
-        res = False
+    tensor and version (a device -> host copy; the result is kept ON the tensor object, so a new tensor that happens to reuse the
+    address never inherits it), hence it must first happen outside CUDA-graph capture; upfirdn2d.setup_filter([1,3,3,1]) qualifies."""
+    hit = getattr(f, '_p3d_separable', None)
+    if hit is None or hit[0] != f._version:
+        res = None
         if tuple(f.shape) == (4, 4) and f.dtype == torch.float32:
             m = f.detach().cpu()
             if float(m[0, 0]) != 0.0:
@@ -329,8 +326,9 @@ def separable_factors(f):
                 fy = (m[:, 0] / m[0, 0]).clone()
                 if torch.equal(fy[:, None] * fx[None, :], m):
                     res = ((ctypes.c_float * 4)(*fx.tolist()), (ctypes.c_float * 4)(*fy.tolist()))
-        _SEP_CACHE[key] = hit = res
-    return hit or None
+        hit = (f._version, res)
+        f._p3d_separable = hit
+    return hit[1]
 
 
 def fir_act_nhwc(x, f, noise, bias, out_planes, out_hw, pad0=(1, 1), fir_gain=4.0, act=3, alpha=0.2, act_gain=1.0, clamp=-1.0):

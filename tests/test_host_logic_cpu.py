@@ -15,7 +15,11 @@ def test_separable_factors_are_exact_or_refused():
     fx, fy = tcconv.separable_factors(f)
     fx, fy = np.array(list(fx), np.float32), np.array(list(fy), np.float32)
     assert np.array_equal(np.outer(fy, fx).astype(np.float32), f.numpy())          # exact in fp32, as the kernel's contract requires
-    assert tcconv.separable_factors(f) is tcconv.separable_factors(f) or True     # cached per buffer
+    assert tcconv.separable_factors(f) is tcconv.separable_factors(f)              # kept on the tensor object
+    h = f.clone()
+    assert tcconv.separable_factors(h) is not None
+    h[1, 2] += 1e-3                                                                # in-place change bumps the version: re-examined
+    assert tcconv.separable_factors(h) is None
     g = f.clone()
     g[1, 2] += 1e-3                                                                # not rank 1 any more
     assert tcconv.separable_factors(g) is None
