@@ -361,6 +361,52 @@ def sample_from_planes_backward(grad_out, plane_shape, coordinates, box_warp):
     return out.astype(f32)
 
 
+def decoder_backward(dec, sampled_features, g_rgb, g_sigma):
+    """First-order gradients of `decoder_forward` (what autograd derives from triplane.py:122-135 / triplane_cond.py:869-970 with
+    FullyConnectedLayer networks_stylegan2.py:111-123 and torch.nn.Softplus): sampled_features [N,3,M,32], upstream g_rgb [N,M,Co],
+    g_sigma [N,M,1] -> (g_features [N,3,M,32], [per net dict(w1, b1, w2, b2)] = gradients of the RAW parameters). float64."""
+    f = np.asarray(sampled_features, np.float64)
+    x = ((f[:, 0] + f[:, 1]) + f[:, 2]) / 3.0
+    n, m, c = x.shape
+    x = x.reshape(n * m, c)
+    lr = float(dec.get('lr_mul', 1.0))
+    kind = dec['kind']
+    g_rgb = np.asarray(g_rgb, np.float64).reshape(n * m, -1)
+    g_sig = np.asarray(g_sigma, np.float64).reshape(n * m, 1)
+    gx = np.zeros_like(x)
+    grads = []
+    for k, net in enumerate(dec['nets']):
+        w1, b1, w2, b2 = (np.asarray(net[q], np.float64) for q in ('w1', 'b1', 'w2', 'b2'))
+        g1, g2 = lr / np.sqrt(w1.shape[1]), lr / np.sqrt(w2.shape[1])                # weight_gain; bias_gain = lr (:108-109)
+        a1 = x @ (w1 * g1).T + b1 * lr
+        z = np.exp(np.minimum(a1, 20.0))
+        h = np.where(a1 > 20, a1, np.log1p(z))                                       # Softplus(beta 1, threshold 20)
+        dsp = np.where(a1 > 20, 1.0, z / (z + 1.0))
+        o = h @ (w2 * g2).T + b2 * lr
+        # upstream gradient of this net's 33 outputs
+        go = np.zeros_like(o)
+        if kind == 'OSGDecoder' or (kind == 'OSGDecoder_semantic'):
+            sig_on, grgb, has_sigma = (True if kind == 'OSGDecoder' else bool(dec['sigmoid'])), g_rgb, True
+        elif kind == 'OSGDecoder_semantic_lateSeparate':                             # net 0: colours, net 1: semantics + sigma
+            sig_on = True if k == 0 else bool(dec['sigmoid'])
+            grgb, has_sigma = g_rgb[:, 32 * k:32 * (k + 1)], k == 1
+        else:
+            raise ValueError(kind)
+        if sig_on:
+            sg = 1.0 / (1.0 + np.exp(-o[:, 1:]))
+            go[:, 1:] = grgb * (1 + 2 * 0.001) * sg * (1.0 - sg)                     # y = sigmoid(o) * 1.002 - 0.001
+        else:
+            go[:, 1:] = grgb
+        if has_sigma:
+            go[:, 0:1] = g_sig
+        gh = go @ (w2 * g2)
+        ga = gh * dsp
+        gx += ga @ (w1 * g1)
+        grads.append(dict(w1=(ga.T @ x) * g1, b1=ga.sum(0) * lr, w2=(go.T @ h) * g2, b2=go.sum(0) * lr))
+    gf = np.broadcast_to((gx / 3.0).reshape(n, 1, m, c), (n, 3, m, c)).copy()
+    return gf, grads
+
+
 def ray_march_backward(colors, densities, depths, g_rgb, g_depth, g_weights, white_back=False, clamp_range=None):
     """Gradients of `ray_march` w.r.t. colors [B,R,S,C] and densities [B,R,S,1] for upstream gradients of its three
     outputs (g_rgb [B,R,C], g_depth [B,R,1] or None, g_weights [B,R,S-1,1] or None). Depths carry no gradient in the

@@ -166,3 +166,70 @@ def _aten_sample(rr, plane_features, coordinates, box_warp):
     grid = rr.project_onto_planes(rr.generate_planes().to(coordinates.device), (2 / box_warp) * coordinates).unsqueeze(1)
     out = torch.nn.functional.grid_sample(feats, grid.float(), mode='bilinear', padding_mode='zeros', align_corners=False)
     return out.permute(0, 3, 2, 1).reshape(n, n_planes, m, c)
+
+
+# ---------------------------------------------------------------------------------------------
+# OSG decoder: oracle backward (hand-derived) vs autograd of the decoder modules (CPU), CUDA kernels vs the oracle (GPU)
+# ---------------------------------------------------------------------------------------------
+def _decoder_case(kind, seed=5, n=2, m=37, lr=1.0):
+    from pix2pix3d_b200.training import triplane, triplane_cond as tc
+    base = {'decoder_lr_mul': lr, 'decoder_output_dim': 32}
+    torch.manual_seed(seed)
+    if kind == 'osg':
+        mod, okind, sig = triplane.OSGDecoder(32, dict(base)), 'OSGDecoder', None
+    elif kind in ('semantic_raw', 'semantic_sigmoid'):
+        sig = kind.endswith('sigmoid')
+        mod, okind = tc.OSGDecoder_semantic(32, dict(base, sigmoid=sig)), 'OSGDecoder_semantic'
+    else:
+        sig = kind == 'late1'
+        mod, okind = tc.OSGDecoder_semantic_lateSeparate(32, dict(base, sigmoid=sig, semantic_channels=1 if sig else 6)), \
+            'OSGDecoder_semantic_lateSeparate'
+    for p in mod.parameters():
+        p.data.normal_(0, 0.7)
+    nets = [mod.net] + ([mod.net_semantic] if okind.endswith('lateSeparate') else [])
+    dec = dict(kind=okind, lr_mul=lr, sigmoid=sig,
+               nets=[dict(w1=t[0].weight.detach().numpy(), b1=t[0].bias.detach().numpy(), w2=t[2].weight.detach().numpy(),
+                          b2=t[2].bias.detach().numpy()) for t in nets])
+    feats = torch.randn(n, 3, m, 32) * 2
+    co = 32 * len(nets)
+    return mod, nets, dec, feats, torch.randn(n, m, co), torch.randn(n, m, 1)
+
+
+DEC_KINDS = ['osg', 'semantic_raw', 'semantic_sigmoid', 'late6', 'late1']
+
+
+@pytest.mark.parametrize('kind', DEC_KINDS)
+@pytest.mark.parametrize('lr', [1.0, 0.5])
+def test_oracle_decoder_backward_matches_autograd(kind, lr):
+    mod, nets, dec, feats, g_rgb, g_sigma = _decoder_case(kind, lr=lr)
+    mod = mod.double()
+    f = feats.double().requires_grad_(True)
+    out = mod(f, None)
+    params = [p for t in nets for p in (t[0].weight, t[0].bias, t[2].weight, t[2].bias)]
+    want = torch.autograd.grad((out['rgb'] * g_rgb.double()).sum() + (out['sigma'] * g_sigma.double()).sum(), [f] + params)
+    rgb, sigma = O.renderer.decoder_forward(dec, feats.numpy())
+    assert rel_err(rgb, out['rgb'].detach().numpy()) < 1e-5 and rel_err(sigma, out['sigma'].detach().numpy()) < 1e-5
+    gf, grads = O.renderer.decoder_backward(dec, feats.numpy(), g_rgb.numpy(), g_sigma.numpy())
+    assert rel_err(gf, want[0].numpy()) < 1e-10
+    got = [g[q] for g in grads for q in ('w1', 'b1', 'w2', 'b2')]
+    for a, b in zip(got, want[1:]):
+        assert rel_err(a, b.numpy()) < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('kind', DEC_KINDS)
+def test_decoder_kernels_match_the_oracle(kind):
+    """p3d_decoder_mlp_fwd / _bwd through the decoder modules on CUDA against the oracle's forward and backward."""
+    mod, nets, dec, feats, g_rgb, g_sigma = _decoder_case(kind, n=2, m=1000)
+    mod = mod.cuda()
+    f = feats.cuda().requires_grad_(True)
+    out = mod(f, None)
+    params = [p for t in nets for p in (t[0].weight, t[0].bias, t[2].weight, t[2].bias)]
+    got = torch.autograd.grad((out['rgb'] * g_rgb.cuda()).sum() + (out['sigma'] * g_sigma.cuda()).sum(), [f] + params)
+    rgb, sigma = O.renderer.decoder_forward(dec, feats.numpy())
+    assert rel_err(out['rgb'].detach().cpu().numpy(), rgb) < 1e-5 and rel_err(out['sigma'].detach().cpu().numpy(), sigma) < 1e-5
+    gf, grads = O.renderer.decoder_backward(dec, feats.numpy(), g_rgb.numpy(), g_sigma.numpy())
+    assert rel_err(got[0].cpu().numpy(), gf) < 2e-5
+    want = [g[q] for g in grads for q in ('w1', 'b1', 'w2', 'b2')]
+    for a, b in zip(got[1:], want):
+        assert rel_err(a.cpu().numpy(), b) < 2e-5
