@@ -13,6 +13,10 @@
 //   hi*hi + hi*lo + lo*hi, accumulated in the same fp32 TMEM tile (error ~2^-22, products are exact in fp32).
 // * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer, warps 2-5 = epilogue
 //   (tcgen05.ld -> scale/noise/bias/activation/clamp -> NHWC store). mbarrier ring of kStages smem stages.
+// * A launch may carry up to four PHASES (ConvPhase: tap subset, grid, output offset): the four parities of a stride-2
+//   transposed 3x3 convolution run as one launch whose tile order walks them heaviest first (p3d_conv_gemm_phases).
+// * The persistent kernel can also evaluate the NEXT layer's 1x1 ToRGB + skip on the outputs it holds (rgb_* arguments): the last
+//   super-resolution block then needs no ToRGB launch and never writes its activation tensor.
 #include <stdlib.h>
 #include <string.h>
 #include "p3d_common.cuh"

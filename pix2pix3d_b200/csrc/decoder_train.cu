@@ -11,8 +11,10 @@
 // already applied (W * weight_gain, b * bias_gain: networks_stylegan2.py:111-119), so the gains stay in autograd's hands.
 //
 // fp32 CUDA-core arithmetic with the exact library exp / log1p (the op must agree with torch's to ~1e-6: its results train the
-// network). Work per point: 4.2 kFMA forward, 12.5 kFMA backward; bytes per point: 384 in + 132 out forward, 516 in + 384 out
-// backward -- the kernels are FMA-pipe bound (weights are broadcast from shared memory).
+// network). Work per point: 4.2 kFMA forward, 8.3 kFMA backward (the forward saves the hidden pre-activations, so the backward
+// recomputes neither GEMM). Bytes per point: forward 384 in + 132 out (+ 256 for the saved pre-activations when a gradient can
+// follow); backward 384 (features) + 256 (pre-activations) + 128 (the op's rgb output: sigmoid') + 132 (upstream gradients) in,
+// 384 out. Both kernels are bound by fp32 FMA issue (weights are broadcast from shared memory), not by memory.
 #include "p3d_common.cuh"
 
 namespace p3d {
